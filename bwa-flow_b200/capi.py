@@ -1,0 +1,288 @@
+"""ctypes binding of libbwaflow_cuda.so (include/bwaflow_cuda.h).  Fails loudly when the CUDA library
+is missing or no GPU is present -- there is no CPU fallback on this path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbwaflow_cuda.so")
+
+INTV = np.dtype([("x0", "<u8"), ("x1", "<u8"), ("x2", "<u8"), ("info", "<u8")])
+SEED = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4"), ("score", "<i4"), ("pad", "<i4")])
+CHAIN = np.dtype([("pos", "<i8"), ("n_seeds", "<i4"), ("rid", "<i4"), ("frac_rep", "<f4"), ("flags", "<u4"),
+                  ("seed_off", "<i8")])
+ALNREG = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("rid", "<i4"), ("score", "<i4"),
+                   ("truesc", "<i4"), ("sub", "<i4"), ("alt_sc", "<i4"), ("csub", "<i4"), ("sub_n", "<i4"),
+                   ("w", "<i4"), ("seedcov", "<i4"), ("secondary", "<i4"), ("secondary_all", "<i4"),
+                   ("seedlen0", "<i4"), ("n_comp_is_alt", "<u4"), ("frac_rep", "<f4"), ("hash", "<u8")])
+EXT_JOB = np.dtype([("qlen", "<i4"), ("tlen", "<i4"), ("w", "<i4"), ("h0", "<i4"), ("end_bonus", "<i4"),
+                    ("zdrop", "<i4"), ("q_off", "<i8"), ("t_off", "<i8")])
+EXT_RES = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"), ("gscore", "<i4"),
+                    ("max_off", "<i4")])
+assert EXT_JOB.itemsize == 40 and EXT_RES.itemsize == 24 and ALNREG.itemsize == 88
+
+
+class Index(C.Structure):
+    _fields_ = [("primary", C.c_uint64), ("L2", C.c_uint64 * 5), ("seq_len", C.c_uint64), ("bwt_size", C.c_uint64),
+                ("bwt", C.c_void_p), ("n_sa", C.c_uint64), ("sa_intv", C.c_int64), ("sa", C.c_void_p),
+                ("l_pac", C.c_int64), ("pac", C.c_void_p), ("n_seqs", C.c_int32), ("_pad", C.c_int32),
+                ("ctg_offset", C.c_void_p), ("ctg_len", C.c_void_p)]
+
+
+class Opt(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("a", "b", "o_del", "e_del", "o_ins", "e_ins", "pen_clip5", "pen_clip3", "w",
+                                         "zdrop", "min_seed_len", "split_width", "max_occ", "max_mem_intv")] + \
+               [("split_factor", C.c_float), ("mat", C.c_int8 * 25), ("_pad", C.c_int8 * 3)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
+                ("n_launches", C.c_int32), ("_pad", C.c_int32), ("work_units", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
+
+
+class BwaflowError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BwaflowError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(no CPU fallback exists for this path)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.bwaflow_last_error.restype = C.c_char_p
+        L.bwaflow_host_alloc.restype = C.c_void_p
+        L.bwaflow_host_alloc.argtypes = [C.c_uint64]
+        L.bwaflow_host_free.argtypes = [C.c_void_p]
+        L.bwaflow_opt_default.argtypes = [C.POINTER(Opt)]
+        L.bwaflow_ctx_create.argtypes = [C.c_int, C.POINTER(Index), C.POINTER(Opt), C.POINTER(C.c_void_p)]
+        L.bwaflow_ctx_destroy.argtypes = [C.c_void_p]
+        L.bwaflow_ctx_set_opt.argtypes = [C.c_void_p, C.POINTER(Opt)]
+        L.bwaflow_ext_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
+        L.bwaflow_ext_batch_destroy.argtypes = [C.c_void_p]
+        L.bwaflow_ext_submit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        L.bwaflow_ext_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(Timing)]
+        L.bwaflow_ext_rerun.argtypes = [C.c_void_p]
+        if hasattr(L, "bwaflow_c2a_batch_create"):
+            L.bwaflow_c2a_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
+            L.bwaflow_c2a_batch_destroy.argtypes = [C.c_void_p]
+            L.bwaflow_c2a_submit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+            L.bwaflow_c2a_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Timing)]
+            L.bwaflow_c2a_rerun.argtypes = [C.c_void_p]
+        if hasattr(L, "bwaflow_smem_batch_create"):
+            L.bwaflow_smem_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
+            L.bwaflow_smem_batch_destroy.argtypes = [C.c_void_p]
+            L.bwaflow_smem_submit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+            L.bwaflow_smem_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Timing)]
+            L.bwaflow_smem_rerun.argtypes = [C.c_void_p]
+            L.bwaflow_smem_seed_positions.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Timing)]
+            L.bwaflow_sa_lookup.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise BwaflowError("bwaflow error %d: %s" % (rc, lib().bwaflow_last_error().decode()))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _view(ptr, count, dtype):
+    """zero-copy numpy view of library-owned pinned memory"""
+    if count == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (count * dtype.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype)
+
+
+def default_opt():
+    o = Opt()
+    lib().bwaflow_opt_default(C.byref(o))
+    return o
+
+
+def pinned(shape, dtype):
+    """numpy array backed by pinned host memory (bwaflow_host_alloc); freed when garbage-collected."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    ptr = lib().bwaflow_host_alloc(max(1, n * dtype.itemsize))
+    if not ptr:
+        raise BwaflowError(lib().bwaflow_last_error().decode())
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _PinnedOwner(arr, ptr)
+    return arr
+
+
+class _PinnedOwner:
+    _live = {}
+
+    def __init__(self, arr, ptr):
+        import weakref
+        self.ptr = ptr
+        _PinnedOwner._live[ptr] = self
+        weakref.finalize(arr, _PinnedOwner._release, ptr)
+
+    @staticmethod
+    def _release(ptr):
+        if _PinnedOwner._live.pop(ptr, None) is not None and _lib is not None:
+            _lib.bwaflow_host_free(ptr)
+
+
+class Context:
+    """One per GPU: index + options resident in HBM (BWAOCLEnv's role, src/fpga/BWAOCLEnv.h)."""
+
+    def __init__(self, device=0, index: Index | None = None, opt: Opt | None = None, keepalive=None):
+        self.L = lib()
+        self.h = C.c_void_p()
+        self._keep = keepalive
+        self.opt = opt if opt is not None else default_opt()
+        check(self.L.bwaflow_ctx_create(device, C.byref(index) if index is not None else None, C.byref(self.opt), C.byref(self.h)))
+
+    def set_opt(self, opt: Opt):
+        self.opt = opt
+        check(self.L.bwaflow_ctx_set_opt(self.h, C.byref(opt)))
+
+    def close(self):
+        if self.h:
+            self.L.bwaflow_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def sa_lookup(self, k):
+        k = np.ascontiguousarray(k, dtype=np.uint64)
+        out = np.zeros(len(k), dtype=np.uint64)
+        check(self.L.bwaflow_sa_lookup(self.h, len(k), _p(k), _p(out)))
+        return out
+
+
+def make_index(view_like, ctg_off, ctg_len):
+    """Build a bwaflow_index_t from any struct with the bwt_t/bntseq_t-shaped fields (e.g. the oracle's IndexView)
+    plus contig tables.  Returns (Index, keepalive tuple)."""
+    ix = Index()
+    for k in ("primary", "seq_len", "bwt_size", "bwt", "n_sa", "sa_intv", "sa", "l_pac", "pac", "n_seqs"):
+        setattr(ix, k, getattr(view_like, k))
+    for i in range(5):
+        ix.L2[i] = view_like.L2[i]
+    co = np.ascontiguousarray(ctg_off, dtype=np.int64)
+    cl = np.ascontiguousarray(ctg_len, dtype=np.int32)
+    ix.ctg_offset = co.ctypes.data
+    ix.ctg_len = cl.ctypes.data
+    return ix, (co, cl, view_like)
+
+
+class ExtBatch:
+    """SWTask-shaped batch of raw ksw_extend2 jobs."""
+
+    def __init__(self, ctx: Context, max_jobs, max_qbytes, max_tbytes):
+        self.L = ctx.L
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        check(self.L.bwaflow_ext_batch_create(ctx.h, max_jobs, max_qbytes, max_tbytes, C.byref(self.h)))
+        self.n = 0
+
+    def submit(self, jobs, qpool, tpool):
+        assert jobs.dtype == EXT_JOB
+        self._keep = (jobs, qpool, tpool)
+        self.n = len(jobs)
+        check(self.L.bwaflow_ext_submit(self.h, len(jobs), _p(jobs), _p(qpool), len(qpool), _p(tpool), len(tpool)))
+
+    def rerun(self):
+        check(self.L.bwaflow_ext_rerun(self.h))
+
+    def collect(self):
+        out = C.c_void_p()
+        t = Timing()
+        check(self.L.bwaflow_ext_collect(self.h, C.byref(out), C.byref(t)))
+        return _view(out.value, self.n, EXT_RES), t
+
+    def close(self):
+        if self.h:
+            self.L.bwaflow_ext_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class C2ABatch:
+    """ChainsToRegions-shaped batch: chains of many reads -> mem_alnreg_t lists."""
+
+    def __init__(self, ctx: Context, max_reads, max_bases, max_chains, max_seeds):
+        self.L = ctx.L
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        check(self.L.bwaflow_c2a_batch_create(ctx.h, max_reads, max_bases, max_chains, max_seeds, C.byref(self.h)))
+        self.n = 0
+
+    def submit(self, bases, read_off, chains, chain_off, seeds):
+        assert chains.dtype == CHAIN and seeds.dtype == SEED
+        read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        chain_off = np.ascontiguousarray(chain_off, dtype=np.int64)
+        self._keep = (bases, read_off, chains, chain_off, seeds)
+        self.n = len(read_off) - 1
+        check(self.L.bwaflow_c2a_submit(self.h, self.n, _p(bases), _p(read_off), _p(chains), _p(chain_off), _p(seeds), len(seeds)))
+
+    def rerun(self):
+        check(self.L.bwaflow_c2a_rerun(self.h))
+
+    def collect(self):
+        regs, off = C.c_void_p(), C.c_void_p()
+        n = C.c_int64()
+        t = Timing()
+        check(self.L.bwaflow_c2a_collect(self.h, C.byref(regs), C.byref(off), C.byref(n), C.byref(t)))
+        return _view(regs.value, n.value, ALNREG), _view(off.value, self.n + 1, np.dtype("<i8")), t
+
+    def close(self):
+        if self.h:
+            self.L.bwaflow_c2a_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class SmemBatch:
+    """SMemTask-shaped batch: reads -> sorted bwtintv_t lists (+ seed positions for chaining)."""
+
+    def __init__(self, ctx: Context, max_reads, max_bases):
+        self.L = ctx.L
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        check(self.L.bwaflow_smem_batch_create(ctx.h, max_reads, max_bases, C.byref(self.h)))
+        self.n = 0
+
+    def submit(self, bases, read_off):
+        read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        self._keep = (bases, read_off)
+        self.n = len(read_off) - 1
+        check(self.L.bwaflow_smem_submit(self.h, self.n, _p(bases), _p(read_off)))
+
+    def rerun(self):
+        check(self.L.bwaflow_smem_rerun(self.h))
+
+    def collect(self):
+        a, off = C.c_void_p(), C.c_void_p()
+        n = C.c_int64()
+        t = Timing()
+        check(self.L.bwaflow_smem_collect(self.h, C.byref(a), C.byref(off), C.byref(n), C.byref(t)))
+        self.n_intv = n.value
+        return _view(a.value, n.value, INTV), _view(off.value, self.n + 1, np.dtype("<i8")), t
+
+    def seed_positions(self):
+        a, off = C.c_void_p(), C.c_void_p()
+        n = C.c_int64()
+        t = Timing()
+        check(self.L.bwaflow_smem_seed_positions(self.h, C.byref(a), C.byref(off), C.byref(n), C.byref(t)))
+        return _view(a.value, n.value, np.dtype("<i8")), _view(off.value, self.n_intv + 1, np.dtype("<i8")), t
+
+    def close(self):
+        if self.h:
+            self.L.bwaflow_smem_batch_destroy(self.h)
+            self.h = C.c_void_p()

@@ -1,0 +1,293 @@
+// Batched ksw_extend2 jobs (bwa/ksw.c:380-479), the device counterpart of the FPGA SWTask batch
+// (src/fpga/SWTask.h:9-50): submit = async H2D + device-side length binning + persistent kernels
+// + async D2H; collect = wait.
+//
+// Device pipeline per submit:
+//   1. ext_key_kernel      one key per job = qlen class (sizes the shared-memory row state) | work estimate
+//   2. cub radix sort      jobs ordered class-major, longest first (LPT order for the work queues)
+//   3. ext_ranges_kernel   per-class [begin,end) + work-queue heads
+//   4. ext_kernel<...>     one persistent launch per qlen class; every lane owns one job at a time and
+//                          pulls the next from its class queue when enough lanes of the warp are idle
+#include <cub/device/device_radix_sort.cuh>
+#include <string.h>
+#include <stdlib.h>
+#include "internal.cuh"
+#include "ksw_lane.cuh"
+
+namespace bwaflow {
+
+constexpr int EXT_NCLASS = 8;
+// qlen <= qmax runs in class c with `threads` lanes per block; row state = threads*(qmax+1)*4 bytes
+__constant__ int c_ext_qmax[EXT_NCLASS] = {31, 63, 95, 127, 159, 255, 511, 1023};
+static const int h_ext_qmax[EXT_NCLASS] = {31, 63, 95, 127, 159, 255, 511, 1023};
+static const int h_ext_threads[EXT_NCLASS] = {64, 64, 64, 64, 64, 64, 64, 32};
+
+struct ExtArgs {
+  const bwaflow_ext_job_t *jobs;
+  const uint8_t *qpool, *tpool;
+  const uint32_t *order;
+  int *queue;                 // [EXT_NCLASS] heads, [EXT_NCLASS] ends
+  bwaflow_ext_result_t *out;
+  int *err;
+  int cls, qmax;
+  int refill;                 // refill idle lanes once at least this many are idle
+  DevScore sc;
+};
+
+__global__ void ext_key_kernel(const bwaflow_ext_job_t *jobs, int64_t n, uint32_t *keys, uint32_t *vals, int *hist, int *err)
+{
+  __shared__ int sh[EXT_NCLASS];
+  if (threadIdx.x < EXT_NCLASS) sh[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int qlen = jobs[i].qlen, tlen = jobs[i].tlen;
+    int c = 0;
+    while (c < EXT_NCLASS - 1 && qlen > c_ext_qmax[c]) ++c;
+    if (qlen > c_ext_qmax[EXT_NCLASS - 1] || qlen < 0 || tlen < 0) { atomicExch(err, 1); }
+    // rows are at most tlen, columns per row at most min(qlen, 2w+1): a cheap upper bound of the cell count
+    int64_t est = (int64_t)qlen * tlen;
+    if (est > 0xFFFFFF) est = 0xFFFFFF;
+    keys[i] = (uint32_t)c << 24 | (uint32_t)est;
+    vals[i] = (uint32_t)i;
+    atomicAdd(&sh[c], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < EXT_NCLASS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void ext_ranges_kernel(const int *hist, int *queue)
+{ // keys are sorted descending, so the highest class comes first
+  int pos = 0;
+  for (int c = EXT_NCLASS - 1; c >= 0; --c) {
+    queue[c] = pos;
+    pos += hist[c];
+    queue[EXT_NCLASS + c] = pos;
+  }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) ext_kernel(const ExtArgs a)
+{
+  extern __shared__ uint32_t s_rows[];
+  const int stride = THREADS;
+  uint32_t *col = s_rows + threadIdx.x;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int *head = a.queue + a.cls;
+  const int q_end = a.queue[EXT_NCLASS + a.cls];
+
+  KswLane k;
+  bool active = false, drained = false;
+  int job = -1;
+  const uint8_t *tp = nullptr;
+
+  for (;;) {
+    const unsigned idle = __ballot_sync(full, !active);
+    if (idle == full || (!drained && __popc(idle) >= a.refill)) {
+      const int n_idle = __popc(idle);
+      int base = 0;
+      if (!drained) {
+        if (lane == 0) base = atomicAdd(head, n_idle);
+        base = __shfl_sync(full, base, 0);
+        if (base + n_idle >= q_end) drained = true;
+      } else base = q_end;
+      if (!active) {
+        const int slot = base + __popc(idle & ((1u << lane) - 1));
+        if (slot < q_end) {
+          job = (int)a.order[slot];
+          const bwaflow_ext_job_t jb = a.jobs[job];
+          const uint8_t *qp = a.qpool + jb.q_off;
+          tp = a.tpool + jb.t_off;
+          const bool ok = jb.qlen >= 0 && jb.qlen <= a.qmax &&
+                          k.begin(col, stride, a.sc, jb.qlen, jb.tlen, jb.w, jb.h0, jb.end_bonus,
+                                  [&](int j) { return (uint32_t)qp[j]; });
+          if (!ok) {
+            atomicExch(a.err, 2);
+            a.out[job] = bwaflow_ext_result_t{0, 0, 0, 0, 0, 0};
+          } else if (jb.tlen <= 0) {
+            a.out[job] = bwaflow_ext_result_t{k.best, 0, 0, 0, -1, 0};
+          } else active = true;
+        }
+      }
+      if (__ballot_sync(full, active) == 0) break;
+    }
+    if (active) {
+      if (k.row(col, stride, a.sc, (int)tp[k.i])) {
+        a.out[job] = bwaflow_ext_result_t{k.best, k.best_j + 1, k.best_i + 1, k.end_i + 1, k.gscore, k.max_off};
+        active = false;
+      }
+    }
+  }
+}
+
+} // namespace bwaflow
+
+using namespace bwaflow;
+
+struct bwaflow_ext_batch {
+  bwaflow_ctx_t *ctx;
+  cudaStream_t stream;
+  Timer tm;
+  int64_t max_jobs, max_q, max_t, n_jobs;
+  bwaflow_ext_job_t *d_jobs;
+  uint8_t *d_q, *d_t;
+  uint32_t *d_keys[2], *d_vals[2];
+  void *d_tmp; size_t tmp_bytes;
+  int *d_ctl;                       // hist[8] | queue[16] | err
+  bwaflow_ext_result_t *d_out, *h_out;
+  int *h_err;
+  int blocks[EXT_NCLASS];
+  int refill;
+  bool pending;
+  double cells_hint;
+};
+
+static int ext_launch(bwaflow_ext_batch *b)
+{
+  const int64_t n = b->n_jobs;
+  int *hist = b->d_ctl, *queue = b->d_ctl + EXT_NCLASS, *err = b->d_ctl + 3 * EXT_NCLASS;
+  BF_CUDA(cudaMemsetAsync(b->d_ctl, 0, (3 * EXT_NCLASS + 1) * sizeof(int), b->stream));
+  if (n == 0) return 0;
+  ext_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_jobs, n, b->d_keys[0], b->d_vals[0], hist, err);
+  cub::DoubleBuffer<uint32_t> keys(b->d_keys[0], b->d_keys[1]), vals(b->d_vals[0], b->d_vals[1]);
+  size_t tmp = b->tmp_bytes;
+  BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(b->d_tmp, tmp, keys, vals, (int)n, 0, 27, b->stream));
+  ext_ranges_kernel<<<1, 1, 0, b->stream>>>(hist, queue);
+  ExtArgs a;
+  a.jobs = b->d_jobs; a.qpool = b->d_q; a.tpool = b->d_t; a.order = vals.Current(); a.queue = queue;
+  a.out = b->d_out; a.err = err; a.refill = b->refill; a.sc = b->ctx->par.sc;
+  for (int c = EXT_NCLASS - 1; c >= 0; --c) {
+    a.cls = c; a.qmax = h_ext_qmax[c];
+    const size_t smem = (size_t)h_ext_threads[c] * (h_ext_qmax[c] + 1) * sizeof(uint32_t);
+    if (h_ext_threads[c] == 64) ext_kernel<64><<<b->blocks[c], 64, smem, b->stream>>>(a);
+    else ext_kernel<32><<<b->blocks[c], 32, smem, b->stream>>>(a);
+  }
+  BF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_qbytes, int64_t max_tbytes,
+                             bwaflow_ext_batch_t **out)
+{
+  BF_REQUIRE(ctx && out, -22, "bwaflow_ext_batch_create: null argument");
+  BF_REQUIRE(max_jobs > 0 && max_jobs < (1LL << 31), -22, "max_jobs out of range");
+  BF_CUDA(cudaSetDevice(ctx->device));
+  bwaflow_ext_batch *b = (bwaflow_ext_batch *)calloc(1, sizeof(*b));
+  b->ctx = ctx; b->max_jobs = max_jobs; b->max_q = max_qbytes; b->max_t = max_tbytes;
+  b->refill = 8;
+  if (const char *s = getenv("BWAFLOW_EXT_REFILL")) b->refill = atoi(s) > 0 ? atoi(s) : 8;
+  BF_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  if (b->tm.init()) return -5;
+  BF_CUDA(cudaMalloc(&b->d_jobs, max_jobs * sizeof(bwaflow_ext_job_t)));
+  BF_CUDA(cudaMalloc(&b->d_q, max_qbytes + 16));
+  BF_CUDA(cudaMalloc(&b->d_t, max_tbytes + 16));
+  for (int i = 0; i < 2; ++i) {
+    BF_CUDA(cudaMalloc(&b->d_keys[i], max_jobs * 4));
+    BF_CUDA(cudaMalloc(&b->d_vals[i], max_jobs * 4));
+  }
+  cub::DoubleBuffer<uint32_t> keys(b->d_keys[0], b->d_keys[1]), vals(b->d_vals[0], b->d_vals[1]);
+  BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, b->tmp_bytes, keys, vals, (int)max_jobs, 0, 27, b->stream));
+  BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
+  BF_CUDA(cudaMalloc(&b->d_ctl, (3 * EXT_NCLASS + 1) * sizeof(int)));
+  BF_CUDA(cudaMalloc(&b->d_out, max_jobs * sizeof(bwaflow_ext_result_t)));
+  BF_CUDA(cudaMallocHost(&b->h_out, max_jobs * sizeof(bwaflow_ext_result_t)));
+  BF_CUDA(cudaMallocHost(&b->h_err, sizeof(int)));
+  for (int c = 0; c < EXT_NCLASS; ++c) {
+    const size_t smem = (size_t)h_ext_threads[c] * (h_ext_qmax[c] + 1) * sizeof(uint32_t);
+    int per_sm = 0;
+    if (h_ext_threads[c] == 64) {
+      BF_CUDA(cudaFuncSetAttribute(ext_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_kernel<64>, 64, smem));
+    } else {
+      BF_CUDA(cudaFuncSetAttribute(ext_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_kernel<32>, 32, smem));
+    }
+    BF_REQUIRE(per_sm > 0, -12, "extension kernel class %d does not fit on an SM", c);
+    b->blocks[c] = per_sm * ctx->n_sm;
+  }
+  *out = b;
+  return 0;
+}
+
+void bwaflow_ext_batch_destroy(bwaflow_ext_batch_t *b)
+{
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->stream);
+  cudaFree(b->d_jobs); cudaFree(b->d_q); cudaFree(b->d_t);
+  for (int i = 0; i < 2; ++i) { cudaFree(b->d_keys[i]); cudaFree(b->d_vals[i]); }
+  cudaFree(b->d_tmp); cudaFree(b->d_ctl); cudaFree(b->d_out);
+  cudaFreeHost(b->h_out); cudaFreeHost(b->h_err);
+  b->tm.destroy();
+  cudaStreamDestroy(b->stream);
+  free(b);
+}
+
+static int ext_queue_d2h(bwaflow_ext_batch *b)
+{
+  BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
+  if (b->n_jobs) BF_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, b->n_jobs * sizeof(bwaflow_ext_result_t), cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_ctl + 3 * EXT_NCLASS, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaEventRecord(b->tm.ev[3], b->stream));
+  b->pending = true;
+  return 0;
+}
+
+int bwaflow_ext_submit(bwaflow_ext_batch_t *b, int64_t n_jobs, const bwaflow_ext_job_t *jobs,
+                       const uint8_t *qpool, int64_t qbytes, const uint8_t *tpool, int64_t tbytes)
+{
+  BF_REQUIRE(b && (n_jobs == 0 || (jobs && qpool && tpool)), -22, "bwaflow_ext_submit: null argument");
+  BF_REQUIRE(n_jobs >= 0 && n_jobs <= b->max_jobs && qbytes <= b->max_q && tbytes <= b->max_t, -7,
+             "bwaflow_ext_submit: batch capacity exceeded (%lld jobs, %lld+%lld bytes)", (long long)n_jobs, (long long)qbytes, (long long)tbytes);
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  b->n_jobs = n_jobs;
+  BF_CUDA(cudaEventRecord(b->tm.ev[0], b->stream));
+  if (n_jobs) {
+    BF_CUDA(cudaMemcpyAsync(b->d_jobs, jobs, n_jobs * sizeof(bwaflow_ext_job_t), cudaMemcpyHostToDevice, b->stream));
+    BF_CUDA(cudaMemcpyAsync(b->d_q, qpool, qbytes, cudaMemcpyHostToDevice, b->stream));
+    BF_CUDA(cudaMemcpyAsync(b->d_t, tpool, tbytes, cudaMemcpyHostToDevice, b->stream));
+  }
+  BF_CUDA(cudaEventRecord(b->tm.ev[1], b->stream));
+  int r = ext_launch(b);
+  if (r) return r;
+  return ext_queue_d2h(b);
+}
+
+int bwaflow_ext_rerun(bwaflow_ext_batch_t *b)
+{
+  BF_REQUIRE(b, -22, "bwaflow_ext_rerun: null batch");
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  BF_CUDA(cudaEventRecord(b->tm.ev[0], b->stream));
+  BF_CUDA(cudaEventRecord(b->tm.ev[1], b->stream));
+  int r = ext_launch(b);
+  if (r) return r;
+  BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_ctl + 3 * EXT_NCLASS, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaEventRecord(b->tm.ev[3], b->stream));
+  b->pending = true;
+  return 0;
+}
+
+int bwaflow_ext_collect(bwaflow_ext_batch_t *b, const bwaflow_ext_result_t **out, bwaflow_timing_t *t)
+{
+  BF_REQUIRE(b && b->pending, -22, "bwaflow_ext_collect: nothing submitted");
+  BF_CUDA(cudaStreamSynchronize(b->stream));
+  b->pending = false;
+  if (t) {
+    memset(t, 0, sizeof(*t));
+    cudaEventElapsedTime(&t->h2d_ms, b->tm.ev[0], b->tm.ev[1]);
+    cudaEventElapsedTime(&t->kernel_ms, b->tm.ev[1], b->tm.ev[2]);
+    cudaEventElapsedTime(&t->d2h_ms, b->tm.ev[2], b->tm.ev[3]);
+    cudaEventElapsedTime(&t->total_ms, b->tm.ev[0], b->tm.ev[3]);
+    t->n_launches = b->n_jobs ? 3 + EXT_NCLASS + 7 : 0;   // key + ranges + 8 class kernels + cub passes
+  }
+  BF_REQUIRE(*b->h_err != 1, -34, "extension job with qlen > %d (or negative length)", h_ext_qmax[EXT_NCLASS - 1]);
+  BF_REQUIRE(*b->h_err != 2, -34, "extension job whose scores may exceed %d (h0 + qlen*max_mat) or with h0 <= 0", KSW_MAX_SCORE);
+  if (out) *out = b->h_out;
+  return 0;
+}
+
+} // extern "C"

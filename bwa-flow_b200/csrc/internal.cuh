@@ -1,0 +1,79 @@
+// Shared internals of libbwaflow_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/bwaflow_cuda.h"
+
+namespace bwaflow {
+
+void set_error(const char *fmt, ...);
+
+#define BF_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      bwaflow::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return -5; /* -EIO */                                                                    \
+    }                                                                                          \
+  } while (0)
+
+#define BF_REQUIRE(cond, code, ...)      \
+  do {                                   \
+    if (!(cond)) {                       \
+      bwaflow::set_error(__VA_ARGS__);   \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+// Index as the kernels see it (all pointers are device pointers into HBM).
+struct DevIndex {
+  uint64_t primary, seq_len;
+  uint64_t L2[5];
+  const uint4 *bwt;        // occ-interleaved BWT viewed as 16-byte quarters of the 64-byte blocks
+  const uint64_t *sa;
+  int sa_shift;            // log2(sa_intv)
+  int64_t l_pac;
+  const uint8_t *pac;
+  int n_seqs;
+  const int64_t *ctg_offset;
+  const int32_t *ctg_len;
+};
+
+// Scoring as the extension kernels see it.  Matrix row t (target base) as 5 packed int8: lo = q0..q3, hi = q4.
+struct DevScore {
+  int o_del, e_del, o_ins, e_ins, zdrop, smax;
+  uint32_t row_lo[5], row_hi[5];
+};
+
+struct Params {
+  bwaflow_opt_t opt;
+  DevScore sc;
+};
+
+} // namespace bwaflow
+
+struct bwaflow_ctx {
+  int device;
+  int n_sm;
+  bool has_index;
+  bwaflow::DevIndex ix;
+  bwaflow::Params par;
+  // owned device allocations
+  void *d_bwt, *d_sa, *d_pac, *d_ctg_off, *d_ctg_len;
+};
+
+namespace bwaflow {
+void fill_score(const bwaflow_opt_t &o, DevScore &s);
+
+struct Timer {
+  cudaEvent_t ev[4];
+  bool ok = false;
+  int init() {
+    for (int i = 0; i < 4; ++i) BF_CUDA(cudaEventCreate(&ev[i]));
+    ok = true; return 0;
+  }
+  void destroy() { if (ok) for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]); ok = false; }
+};
+} // namespace bwaflow

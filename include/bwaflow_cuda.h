@@ -1,0 +1,147 @@
+/* bwaflow_cuda.h -- C ABI of the B200 (sm_100a) backend for bwa-flow's per-read compute path.
+ *
+ * This is the boundary a `src/cuda` backend of falcon-computing/bwa-flow binds, in the same
+ * place `src/fpga` plugs in (kflow stage slots 2 and 4, src/main.cpp:302-335).  Every entry
+ * point cites the reference interface it replaces.  Plain pointers and sizes only; no C++,
+ * no torch, no reference headers needed.  All functions return 0 on success and a negative
+ * errno-style code on failure (message via bwaflow_last_error()); nothing throws across the
+ * ABI and there is NO CPU fallback: a missing GPU is an error.
+ *
+ * Shape of the interface = the FPGA batch interface it mirrors:
+ *   BWAOCLEnv ctor (src/fpga/BWAOCLEnv.h:67-216: upload pac + BWT once)   -> bwaflow_ctx_create
+ *   SMemTask{start,finish} (src/fpga/SMemTask.h:9-47)                     -> bwaflow_smem_{submit,collect}
+ *   SWTask{start,finish}   (src/fpga/SWTask.h:9-50)                       -> bwaflow_c2a_{submit,collect}
+ *                                                                            bwaflow_ext_{submit,collect}
+ * submit is asynchronous (H2D + kernels + D2H queued on the batch's own stream), collect blocks;
+ * a worker keeps two batch objects to double-buffer, exactly as FPGAPipeline.cpp:374-386 does.
+ */
+#ifndef BWAFLOW_CUDA_H
+#define BWAFLOW_CUDA_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- plain-data mirrors of the reference structs that cross the boundary ------------------ */
+
+/* bwtintv_t, bwa/bwt.h:60-62 (32 B): x[0] fwd SA start, x[1] rev-comp SA start, x[2] size, info = qbeg<<32|qend */
+typedef struct { uint64_t x[3], info; } bwaflow_intv_t;
+
+/* mem_seed_t, src/bwa_wrapper.h:64-68 (24 B) */
+typedef struct { int64_t rbeg; int32_t qbeg, len, score, _pad; } bwaflow_seed_t;
+
+/* the fields of mem_chain_t (src/bwa_wrapper.h:70-77) that mem_chain2aln reads, flattened:
+ * seeds of chain c are seeds[seed_off .. seed_off+n_seeds) of the batch-wide seed array.
+ * flags = w | kept<<29 | is_alt<<31 (carried, not interpreted). */
+typedef struct { int64_t pos; int32_t n_seeds, rid; float frac_rep; uint32_t flags; int64_t seed_off; } bwaflow_chain_t;
+
+/* mem_alnreg_t, bwa/bwamem.h:60-78 (88 B, identical layout; the device fills what mem_chain2aln
+ * fills -- rb re qb qe rid score truesc w seedcov seedlen0 frac_rep -- and zeroes the rest) */
+typedef struct {
+  int64_t rb, re; int32_t qb, qe, rid, score, truesc, sub, alt_sc, csub, sub_n, w, seedcov, secondary,
+  secondary_all, seedlen0; uint32_t n_comp_is_alt; float frac_rep; uint64_t hash;
+} bwaflow_alnreg_t;
+
+/* One ksw_extend2 call (bwa/ksw.c:380): query = qpool[q_off..+qlen) codes 0..4, target = tpool[t_off..+tlen)
+ * codes 0..3(4).  w is the caller's (unclamped) band; the clamp of ksw.c:399-407 happens on the device. */
+typedef struct { int32_t qlen, tlen, w, h0, end_bonus, zdrop; int64_t q_off, t_off; } bwaflow_ext_job_t;
+/* its six outputs: return value, *_qle, *_tle, *_gtle, *_gscore, *_max_off (bwa/ksw.c:473-478) */
+typedef struct { int32_t score, qle, tle, gtle, gscore, max_off; } bwaflow_ext_result_t;
+
+/* Index arrays exactly as bwa holds them in memory (bwt_t bwa/bwt.h:46-58, bntseq_t bwa/bntseq.h:56-64,
+ * bwaidx_t::pac bwa/bwa.h:22-30).  Host pointers; copied to HBM once by bwaflow_ctx_create. */
+typedef struct {
+  uint64_t primary, L2[5], seq_len, bwt_size; const uint32_t *bwt;   /* occ-interleaved BWT, bwt_size u32 words */
+  uint64_t n_sa; int64_t sa_intv; const uint64_t *sa;                /* sampled SA, sa[0] = (u64)-1 */
+  int64_t l_pac; const uint8_t *pac; int32_t n_seqs, _pad;           /* 2-bit forward reference, l_pac/4+1 bytes */
+  const int64_t *ctg_offset; const int32_t *ctg_len;                 /* bns->anns[i].offset / .len, n_seqs each */
+} bwaflow_index_t;
+
+/* The mem_opt_t fields the path reads (bwa/bwamem.h:26-58; defaults bwa/bwamem.c:48-84). */
+typedef struct {
+  int32_t a, b, o_del, e_del, o_ins, e_ins, pen_clip5, pen_clip3, w, zdrop;
+  int32_t min_seed_len, split_width, max_occ, max_mem_intv;
+  float split_factor; int8_t mat[25]; int8_t _pad[3];
+} bwaflow_opt_t;
+
+typedef struct bwaflow_ctx bwaflow_ctx_t;
+typedef struct bwaflow_ext_batch bwaflow_ext_batch_t;
+typedef struct bwaflow_c2a_batch bwaflow_c2a_batch_t;
+typedef struct bwaflow_smem_batch bwaflow_smem_batch_t;
+
+/* per-call device timings (CUDA events on the batch stream), milliseconds */
+typedef struct { float h2d_ms, kernel_ms, d2h_ms, total_ms; int32_t n_launches, _pad; double work_units; } bwaflow_timing_t;
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+const char *bwaflow_last_error(void);
+int bwaflow_device_count(void);
+void bwaflow_opt_default(bwaflow_opt_t *opt);                       /* mem_opt_init, bwa/bwamem.c:48-84 */
+
+/* replaces `new BWAOCLEnv()` (src/main.cpp:212, src/fpga/BWAOCLEnv.h:67-216).  idx may be NULL for a
+ * context that only runs raw extension jobs. */
+int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt_t *opt, bwaflow_ctx_t **out);
+void bwaflow_ctx_destroy(bwaflow_ctx_t *ctx);
+int bwaflow_ctx_set_opt(bwaflow_ctx_t *ctx, const bwaflow_opt_t *opt);
+
+/* pinned host staging memory (the FPGA tasks use clCreateBuffer+map for the same purpose, SWTask.cpp:30-60) */
+void *bwaflow_host_alloc(uint64_t bytes);
+void bwaflow_host_free(void *p);
+
+/* ---- extension jobs: one ksw_extend2 each (replaces the per-seed SW stream of SWTask, src/fpga/SWTask.h) */
+
+int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_qbytes, int64_t max_tbytes,
+                             bwaflow_ext_batch_t **out);
+void bwaflow_ext_batch_destroy(bwaflow_ext_batch_t *b);
+/* SWTask::start: async H2D of jobs+pools, device-side length binning, kernels, async D2H of results */
+int bwaflow_ext_submit(bwaflow_ext_batch_t *b, int64_t n_jobs, const bwaflow_ext_job_t *jobs,
+                       const uint8_t *qpool, int64_t qbytes, const uint8_t *tpool, int64_t tbytes);
+/* SWTask::finish: blocks; (*out)[n_jobs] in job order, pinned host memory owned by the batch, valid until
+ * its next submit */
+int bwaflow_ext_collect(bwaflow_ext_batch_t *b, const bwaflow_ext_result_t **out, bwaflow_timing_t *timing);
+/* device-resident re-run of the last submitted inputs (bench: inputs already in HBM); results stay on device
+ * until bwaflow_ext_collect.  */
+int bwaflow_ext_rerun(bwaflow_ext_batch_t *b);
+
+/* ---- stage 4: chains -> alignment regions (replaces ChainsToRegionsFPGA::compute, src/fpga/FPGAPipeline.cpp:367;
+ *      arithmetic = mem_chain2aln bwa/bwamem.c:641-795 incl. the containment skip the FPGA path drops) */
+
+int bwaflow_c2a_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_bases, int64_t max_chains,
+                             int64_t max_seeds, bwaflow_c2a_batch_t **out);
+void bwaflow_c2a_batch_destroy(bwaflow_c2a_batch_t *b);
+/* bases = nt4 codes of all reads concatenated (bseq1_t::seq after src/bwa_wrapper.cpp:124-125);
+ * read_off[n_reads+1]; chains of read r = chains[chain_off[r] .. chain_off[r+1]) in mem_chain_v order. */
+int bwaflow_c2a_submit(bwaflow_c2a_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off,
+                       const bwaflow_chain_t *chains, const int64_t *chain_off,
+                       const bwaflow_seed_t *seeds, int64_t n_seeds);
+/* blocks; regions of read r = (*regs)[(*reg_off)[r] .. (*reg_off)[r+1]) in the order mem_chain2aln appends them.
+ * The returned arrays are pinned host memory owned by the batch, valid until its next submit. */
+int bwaflow_c2a_collect(bwaflow_c2a_batch_t *b, const bwaflow_alnreg_t **regs, const int64_t **reg_off,
+                        int64_t *n_regs, bwaflow_timing_t *timing);
+int bwaflow_c2a_rerun(bwaflow_c2a_batch_t *b);
+
+/* ---- stage 2: reads -> SMEM intervals (replaces SeqsToChainsFPGA::compute, src/fpga/FPGAPipeline.cpp:582;
+ *      arithmetic = mem_collect_intv_new src/bwa_wrapper.cpp:207-246).  Output per read: bwtintv_t list sorted
+ *      by info, what ChainsPipe::compute (src/Pipeline.cpp:408) consumes with tag=0.  No per-read cap. */
+
+int bwaflow_smem_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_bases, bwaflow_smem_batch_t **out);
+void bwaflow_smem_batch_destroy(bwaflow_smem_batch_t *b);
+int bwaflow_smem_submit(bwaflow_smem_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off);
+int bwaflow_smem_collect(bwaflow_smem_batch_t *b, const bwaflow_intv_t **intv, const int64_t **intv_off,
+                         int64_t *n_intv, bwaflow_timing_t *timing);
+int bwaflow_smem_rerun(bwaflow_smem_batch_t *b);
+
+/* Seed positions for chaining (replaces the bwt_sa loop of mem_chain_postprocess, src/bwa_wrapper.cpp:281-291):
+ * for the intervals of the last collect, pos[] holds bwt_sa(x[0]+k) for k = 0, step, 2*step.. (count < max_occ)
+ * in interval order; pos_off[n_intv+1].  Pinned memory owned by the batch. */
+int bwaflow_smem_seed_positions(bwaflow_smem_batch_t *b, const int64_t **pos, const int64_t **pos_off,
+                                int64_t *n_pos, bwaflow_timing_t *timing);
+
+/* plain SA lookups (bwt_sa, bwa/bwt.c:86-96) */
+int bwaflow_sa_lookup(bwaflow_ctx_t *ctx, int64_t n, const uint64_t *k, uint64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
