@@ -1,0 +1,598 @@
+// Stage 4 on the device: chains -> alignment regions, exact mem_chain2aln semantics
+// (bwa/bwamem.c:641-795) for every chain of every read of a batch, including the containment skip
+// (:680-715) that the FPGA path drops.  Mirrors ChainsToRegionsFPGA::compute's role
+// (src/fpga/FPGAPipeline.cpp:367) behind a SWTask-like submit/collect pair.
+//
+// One lane owns one read at a time and walks its chains and seeds in the reference's order, because
+// whether seed k is extended depends on the regions earlier seeds (and earlier chains) of the same
+// read produced.  Each extension is run by the lane itself with the row-stepped engine in
+// ksw_lane.cuh (left flank, then right flank seeded with the left score, up to two band tries each).
+// The target is read straight from the 2-bit reference in HBM, the query from the read.
+//
+// Device pipeline per submit:
+//   c2a_chain_prep   per chain: reference window [lo,hi) (:651-668 + bns_fetch_seq clipping), sort keys
+//   cub scan + sort  seeds of each chain permuted into processing order (score descending, :671-676)
+//   c2a_read_prep    per read: LPT key (total seeds) and qlen class
+//   c2a_kernel       persistent lanes pulling reads from per-class queues
+//   scan + gather    compact the per-read region lists
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <string.h>
+#include <stdlib.h>
+#include "internal.cuh"
+#include "ksw_lane.cuh"
+
+namespace bwaflow {
+
+constexpr int C2A_NCLASS = 8;
+__constant__ int c_c2a_qmax[C2A_NCLASS] = {31, 63, 95, 127, 159, 255, 511, 1023};
+static const int h_c2a_qmax[C2A_NCLASS] = {31, 63, 95, 127, 159, 255, 511, 1023};
+static const int h_c2a_threads[C2A_NCLASS] = {64, 64, 64, 64, 64, 64, 64, 32};
+
+struct C2AOpt { int a, w, pen_clip5, pen_clip3, o_del, e_del, o_ins, e_ins; };
+
+struct C2AArgs {
+  const uint8_t *bases; const int64_t *read_off;
+  const bwaflow_chain_t *chains; const int64_t *chain_off;
+  const int64_t *sbase;              // [n_chains+1] exclusive prefix of n_seeds in chain order
+  const bwaflow_seed_t *sseeds;      // seeds in processing order, chain c at sbase[c]
+  const int64_t *win;                // [2*n_chains] reference window of each chain
+  uint8_t *skipped;                  // per seed (processing order): 1 = extension skipped (:710)
+  bwaflow_alnreg_t *regs;            // region slots, read r at sbase[chain_off[r]]
+  int *n_regs;                       // [n_reads]
+  const uint32_t *order; int *queue; int *err; unsigned long long *cells;
+  int cls, qmax, refill;
+  DevIndex ix; DevScore sc; C2AOpt o;
+};
+
+// cal_max_gap, bwa/bwamem.c:630-637 (integer-exact form of the double arithmetic, see gap_limit)
+__device__ __forceinline__ int max_gap(const C2AOpt &o, int qlen)
+{
+  const int l_del = gap_limit(qlen * o.a - o.o_del, o.e_del);
+  const int l_ins = gap_limit(qlen * o.a - o.o_ins, o.e_ins);
+  const int l = l_del > l_ins ? l_del : l_ins;
+  return l < o.w << 1 ? l : o.w << 1;
+}
+
+// base at coordinate p of the forward + reverse-complement text (bns_get_seq, bwa/bntseq.c:398-419)
+__device__ __forceinline__ int ref_base(const DevIndex &ix, int64_t p)
+{
+  const bool rev = p >= ix.l_pac;
+  const int64_t f = rev ? (ix.l_pac << 1) - 1 - p : p;
+  const int b = (__ldg(ix.pac + (f >> 2)) >> ((~f & 3) << 1)) & 3;
+  return rev ? 3 - b : b;
+}
+
+__global__ void c2a_chain_prep(const bwaflow_chain_t *chains, int64_t n_chains, const int64_t *chain_read,
+                               const int64_t *read_off, const bwaflow_seed_t *seeds, const int64_t *sbase,
+                               DevIndex ix, C2AOpt o, int64_t *win, uint64_t *keys, uint32_t *vals, int *err)
+{
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  const bwaflow_chain_t ch = chains[c];
+  const int64_t r = chain_read[c];
+  const int lq = (int)(read_off[r + 1] - read_off[r]);
+  const bwaflow_seed_t *sd = seeds + ch.seed_off;
+  const int64_t L = ix.l_pac;
+  int64_t lo = L << 1, hi = 0;
+  if ((uint64_t)c >= (1ull << 24) || ch.n_seeds >= (1 << 20)) atomicExch(err, 3);
+  for (int i = 0; i < ch.n_seeds; ++i) {
+    const bwaflow_seed_t s = sd[i];
+    const int tail = lq - s.qbeg - s.len;
+    const int64_t b = s.rbeg - (s.qbeg + max_gap(o, s.qbeg));
+    const int64_t e = s.rbeg + s.len + (tail + max_gap(o, tail));
+    lo = b < lo ? b : lo;
+    hi = e > hi ? e : hi;
+    if ((unsigned)s.score >= (1u << 20)) atomicExch(err, 3);
+    // ascending sort => chain-major, then (score, index) descending  (srt[] walked from the top, :671-676)
+    const uint64_t inner = ((uint64_t)(uint32_t)s.score << 20 | (uint32_t)i) ^ 0xFFFFFFFFFFull;
+    keys[sbase[c] + i] = (uint64_t)c << 40 | inner;
+    vals[sbase[c] + i] = (uint32_t)(ch.seed_off + i);
+  }
+  if (ch.n_seeds > 0) {
+    lo = lo > 0 ? lo : 0;
+    hi = hi < L << 1 ? hi : L << 1;
+    if (lo < L && L < hi) { if (sd[0].rbeg < L) hi = L; else lo = L; }
+    // bns_fetch_seq: clip to the contig of the first seed (bwa/bntseq.c:421-446)
+    int64_t fb = ix.ctg_offset[ch.rid], fe = fb + ix.ctg_len[ch.rid];
+    if (sd[0].rbeg >= L) { const int64_t t = fb; fb = (L << 1) - fe; fe = (L << 1) - t; }
+    lo = lo > fb ? lo : fb;
+    hi = hi < fe ? hi : fe;
+  }
+  win[2 * c] = lo; win[2 * c + 1] = hi;
+}
+
+__global__ void c2a_mark_reads(const int64_t *chain_off, int64_t n_reads, int64_t *chain_read)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  for (int64_t c = chain_off[r]; c < chain_off[r + 1]; ++c) chain_read[c] = r;
+}
+
+__global__ void c2a_nseeds(const bwaflow_chain_t *chains, int64_t n_chains, int64_t *out)
+{
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n_chains) out[c] = chains[c].n_seeds;
+  if (c == n_chains) out[c] = 0;
+}
+
+__global__ void c2a_gather_seeds(const bwaflow_seed_t *seeds, const uint32_t *vals, int64_t n, bwaflow_seed_t *out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = seeds[vals[i]];
+}
+
+__global__ void c2a_read_prep(const int64_t *read_off, const int64_t *chain_off, const int64_t *sbase, int64_t n_reads,
+                              uint32_t *keys, uint32_t *vals, int *hist, int *err)
+{
+  __shared__ int sh[C2A_NCLASS];
+  if (threadIdx.x < C2A_NCLASS) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_reads) {
+    const int64_t lq = read_off[r + 1] - read_off[r];
+    int c = 0;
+    while (c < C2A_NCLASS - 1 && lq > c_c2a_qmax[c]) ++c;
+    if (lq > c_c2a_qmax[C2A_NCLASS - 1]) atomicExch(err, 1);
+    int64_t est = sbase[chain_off[r + 1]] - sbase[chain_off[r]];
+    est = est > 0xFFFFFF ? 0xFFFFFF : est;
+    keys[r] = (uint32_t)c << 24 | (uint32_t)est;
+    vals[r] = (uint32_t)r;
+    atomicAdd(&sh[c], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < C2A_NCLASS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void c2a_ranges_kernel(const int *hist, int *queue)
+{
+  int pos = 0;
+  for (int c = C2A_NCLASS - 1; c >= 0; --c) { queue[c] = pos; pos += hist[c]; queue[C2A_NCLASS + c] = pos; }
+}
+
+enum { PH_NEXT_SEED = 0, PH_LEFT = 1, PH_RIGHT_START = 2, PH_RIGHT = 3 };
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) c2a_kernel(const C2AArgs a)
+{
+  extern __shared__ uint32_t s_rows[];
+  const int stride = THREADS;
+  uint32_t *col = s_rows + threadIdx.x;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int *head = a.queue + a.cls;
+  const int q_end = a.queue[C2A_NCLASS + a.cls];
+  const C2AOpt o = a.o;
+
+  KswLane k;
+  bool running = false, drained = false;
+  int r = -1;                         // read owned by this lane (-1: idle)
+  // read
+  int lq = 0; const uint8_t *rd = nullptr; int64_t ci = 0, c_end = 0; bwaflow_alnreg_t *av = nullptr; int n_av = 0;
+  // chain
+  int64_t s_base = 0, wlo = 0, whi = 0; int n_seeds = 0, p = 0, rid = 0; float frac_rep = 0.f;
+  // seed + region under construction
+  int64_t s_rbeg = 0, a_rb = 0, a_re = 0, tpos = 0;
+  int s_qbeg = 0, s_len = 0, a_score = 0, a_truesc = 0, a_qb = 0, a_qe = 0, aw0 = 0, aw1 = 0, sc0 = 0, prev = 0, tri = 0;
+  int phase = PH_NEXT_SEED, tstep = 1;
+  unsigned long long cells = 0;
+
+  for (;;) {
+    const unsigned stalled = __ballot_sync(full, !running);
+    if (stalled == full || __popc(stalled) >= a.refill) {
+      // ---- hand reads to idle lanes
+      const unsigned idle = __ballot_sync(full, r < 0);
+      if (idle && !drained) {
+        const int n_idle = __popc(idle);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(head, n_idle);
+        base = __shfl_sync(full, base, 0);
+        if (base + n_idle >= q_end) drained = true;
+        if (r < 0) {
+          const int slot = base + __popc(idle & ((1u << lane) - 1));
+          if (slot < q_end) {
+            r = (int)a.order[slot];
+            const int64_t ro = a.read_off[r];
+            lq = (int)(a.read_off[r + 1] - ro); rd = a.bases + ro;
+            ci = a.chain_off[r] - 1; c_end = a.chain_off[r + 1];
+            av = a.regs + a.sbase[a.chain_off[r]]; n_av = 0;
+            n_seeds = 0; p = 0; phase = PH_NEXT_SEED;
+            if (lq > a.qmax) { a.n_regs[r] = 0; r = -1; }           // reported through err by c2a_read_prep
+          }
+        }
+      }
+      // ---- driver: runs until this lane has an extension in flight or its read is finished
+      if (r >= 0 && !running) {
+        for (;;) {
+          if (phase == PH_LEFT || phase == PH_RIGHT) {            // an extension just finished
+            cells += k.cells;
+            const int score = k.best;
+            const int aw = phase == PH_LEFT ? aw0 : aw1;
+            if (!(tri == 1 || score == prev || k.max_off < (aw >> 1) + (aw >> 2))) {
+              // second band try (bwa/bwamem.c:732-743, 760-771)
+              prev = score; tri = 1;
+              int qlen, tlen, h0, eb;
+              if (phase == PH_LEFT) { aw0 = o.w << 1; qlen = s_qbeg; tlen = (int)(s_rbeg - wlo); h0 = s_len * o.a; eb = o.pen_clip5; tpos = s_rbeg - 1; tstep = -1; }
+              else { aw1 = o.w << 1; qlen = lq - (s_qbeg + s_len); tlen = (int)(whi - (s_rbeg + s_len)); h0 = sc0; eb = o.pen_clip3; tpos = s_rbeg + s_len; tstep = 1; }
+              const uint8_t *qp = phase == PH_LEFT ? rd + s_qbeg - 1 : rd + s_qbeg + s_len;
+              const int qs = tstep;
+              if (!k.begin(col, stride, a.sc, qlen, tlen, phase == PH_LEFT ? aw0 : aw1, h0, eb, [&](int j) { return (uint32_t)qp[j * qs]; })) atomicExch(a.err, 2);
+              if (tlen > 0) { running = true; break; }
+              continue;
+            }
+            if (phase == PH_LEFT) {                                  // :745-751
+              a_score = score;
+              if (k.gscore <= 0 || k.gscore <= a_score - o.pen_clip5) { a_qb = s_qbeg - (k.best_j + 1); a_rb = s_rbeg - (k.best_i + 1); a_truesc = a_score; }
+              else { a_qb = 0; a_rb = s_rbeg - (k.end_i + 1); a_truesc = k.gscore; }
+              phase = PH_RIGHT_START;
+            } else {                                                 // :773-779
+              a_score = score;
+              const int qe = s_qbeg + s_len;
+              if (k.gscore <= 0 || k.gscore <= a_score - o.pen_clip3) { a_qe = qe + k.best_j + 1; a_re = s_rbeg + s_len + k.best_i + 1; a_truesc += a_score - sc0; }
+              else { a_qe = lq; a_re = s_rbeg + s_len + k.end_i + 1; a_truesc += k.gscore - sc0; }
+              phase = -1;                                            // region complete
+            }
+          }
+          if (phase == PH_RIGHT_START) {
+            if (s_qbeg + s_len != lq) {                              // :755-771
+              sc0 = a_score; prev = a_score; tri = 0; aw1 = o.w;
+              const int qlen = lq - (s_qbeg + s_len), tlen = (int)(whi - (s_rbeg + s_len));
+              tpos = s_rbeg + s_len; tstep = 1;
+              const uint8_t *qp = rd + s_qbeg + s_len;
+              if (!k.begin(col, stride, a.sc, qlen, tlen, aw1, sc0, o.pen_clip3, [&](int j) { return (uint32_t)qp[j]; })) atomicExch(a.err, 2);
+              phase = PH_RIGHT;
+              if (tlen > 0) { running = true; break; }
+              continue;
+            }
+            a_qe = lq; a_re = s_rbeg + s_len;                        // :780
+            phase = -1;
+          }
+          if (phase == -1) {                                         // :783-792 append the region
+            const bwaflow_seed_t *sd = a.sseeds + s_base;
+            int cov = 0;
+            for (int i = 0; i < n_seeds; ++i) {
+              const bwaflow_seed_t t = sd[i];
+              if (t.qbeg >= a_qb && t.qbeg + t.len <= a_qe && t.rbeg >= a_rb && t.rbeg + t.len <= a_re) cov += t.len;
+            }
+            bwaflow_alnreg_t g;
+            memset(&g, 0, sizeof(g));
+            g.rb = a_rb; g.re = a_re; g.qb = a_qb; g.qe = a_qe; g.rid = rid; g.score = a_score; g.truesc = a_truesc;
+            g.w = aw0 > aw1 ? aw0 : aw1; g.seedcov = cov; g.seedlen0 = s_len; g.frac_rep = frac_rep;
+            av[n_av++] = g;
+            phase = PH_NEXT_SEED; ++p;
+          }
+          // ---- PH_NEXT_SEED: advance to the next seed that needs extending (:676-715)
+          while (p >= n_seeds) {
+            if (++ci >= c_end) break;
+            const bwaflow_chain_t ch = a.chains[ci];
+            n_seeds = ch.n_seeds; rid = ch.rid; frac_rep = ch.frac_rep; s_base = a.sbase[ci];
+            wlo = a.win[2 * ci]; whi = a.win[2 * ci + 1]; p = 0;
+          }
+          if (ci >= c_end) { a.n_regs[r] = n_av; r = -1; break; }    // read finished
+          {
+            const bwaflow_seed_t s = a.sseeds[s_base + p];
+            s_rbeg = s.rbeg; s_qbeg = s.qbeg; s_len = s.len;
+            int i;
+            for (i = 0; i < n_av; ++i) {                             // :680-696
+              const bwaflow_alnreg_t *q = &av[i];
+              const int64_t prb = q->rb, pre = q->re; const int pqb = q->qb, pqe = q->qe;
+              if (s_rbeg < prb || s_rbeg + s_len > pre || s_qbeg < pqb || s_qbeg + s_len > pqe) continue;
+              if ((double)(s_len - q->seedlen0) > .1 * lq) continue;
+              const int pw = q->w;
+              int qd = s_qbeg - pqb; int64_t rdd = s_rbeg - prb;
+              int mg = max_gap(o, qd < rdd ? qd : (int)rdd);
+              int w = mg < pw ? mg : pw;
+              if (qd - rdd < w && rdd - qd < w) break;
+              qd = pqe - (s_qbeg + s_len); rdd = pre - (s_rbeg + s_len);
+              mg = max_gap(o, qd < rdd ? qd : (int)rdd);
+              w = mg < pw ? mg : pw;
+              if (qd - rdd < w && rdd - qd < w) break;
+            }
+            if (i < n_av) {                                          // :697-712
+              const bwaflow_seed_t *sd = a.sseeds + s_base;
+              int e;
+              for (e = p - 1; e >= 0; --e) {
+                if (a.skipped[s_base + e]) continue;
+                const bwaflow_seed_t t = sd[e];
+                if ((double)t.len < s_len * .95) continue;
+                if (s_qbeg <= t.qbeg && s_qbeg + s_len - t.qbeg >= s_len >> 2 && t.qbeg - s_qbeg != t.rbeg - s_rbeg) break;
+                if (t.qbeg <= s_qbeg && t.qbeg + t.len - s_qbeg >= s_len >> 2 && s_qbeg - t.qbeg != s_rbeg - t.rbeg) break;
+              }
+              if (e < 0) { a.skipped[s_base + p] = 1; ++p; continue; }
+            }
+            aw0 = aw1 = o.w; a_score = a_truesc = -1;                // :717-721
+            if (s_qbeg) {                                            // :724-743
+              prev = -1; tri = 0;
+              const int tlen = (int)(s_rbeg - wlo);
+              tpos = s_rbeg - 1; tstep = -1;
+              const uint8_t *qp = rd + s_qbeg - 1;
+              if (!k.begin(col, stride, a.sc, s_qbeg, tlen, aw0, s_len * o.a, o.pen_clip5, [&](int j) { return (uint32_t)qp[-j]; })) atomicExch(a.err, 2);
+              phase = PH_LEFT;
+              if (tlen > 0) { running = true; break; }
+              continue;
+            }
+            a_score = a_truesc = s_len * o.a; a_qb = 0; a_rb = s_rbeg;   // :753
+            phase = PH_RIGHT_START;
+          }
+        }
+      }
+      if (drained && __ballot_sync(full, r >= 0) == 0) break;
+    }
+    if (running) {
+      const int t = ref_base(a.ix, tpos + (int64_t)k.i * tstep);
+      if (k.row(col, stride, a.sc, t)) running = false;
+    }
+  }
+  if (cells) atomicAdd(a.cells, cells);
+}
+
+__global__ void c2a_compact(const int64_t *chain_off, const int64_t *sbase, const int *n_regs, const int64_t *reg_off,
+                            int64_t n_reads, const bwaflow_alnreg_t *regs, bwaflow_alnreg_t *out)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const bwaflow_alnreg_t *src = regs + sbase[chain_off[r]];
+  bwaflow_alnreg_t *dst = out + reg_off[r];
+  for (int i = 0; i < n_regs[r]; ++i) dst[i] = src[i];
+}
+
+__global__ void c2a_widen(const int *n_regs, int64_t n, int64_t *out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = n_regs[i];
+  if (i == n) out[i] = 0;
+}
+
+} // namespace bwaflow
+
+using namespace bwaflow;
+
+struct bwaflow_c2a_batch {
+  bwaflow_ctx_t *ctx;
+  cudaStream_t stream;
+  Timer tm;
+  int64_t max_reads, max_bases, max_chains, max_seeds;
+  int64_t n_reads, n_chains, n_seeds;   // n_seeds = sum of chains[].n_seeds (seeds actually referenced)
+  uint8_t *d_bases; int64_t *d_read_off, *d_chain_off;
+  bwaflow_chain_t *d_chains; bwaflow_seed_t *d_seeds, *d_sseeds;
+  int64_t *d_nseeds, *d_sbase, *d_chain_read, *d_win;
+  uint64_t *d_skeys[2]; uint32_t *d_svals[2];
+  uint32_t *d_rkeys[2], *d_rvals[2];
+  void *d_tmp; size_t tmp_bytes;
+  uint8_t *d_skipped;
+  bwaflow_alnreg_t *d_regs, *d_regs_out, *h_regs;
+  int *d_nregs; int64_t *d_nregs64, *d_reg_off, *h_reg_off;
+  int *d_ctl, *h_ctl;               // hist[8] | queue[16] | err | pad | cells(u64)
+  int blocks[C2A_NCLASS];
+  int refill;
+  bool pending;
+};
+
+static size_t max3(size_t a, size_t b, size_t c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+
+static int c2a_launch(bwaflow_c2a_batch *b)
+{
+  const int64_t nr = b->n_reads, nc = b->n_chains, ns = b->n_seeds;
+  cudaStream_t st = b->stream;
+  int *hist = b->d_ctl, *queue = b->d_ctl + C2A_NCLASS, *err = b->d_ctl + 3 * C2A_NCLASS;
+  BF_CUDA(cudaMemsetAsync(b->d_ctl, 0, (3 * C2A_NCLASS + 4) * sizeof(int), st));
+  BF_CUDA(cudaMemsetAsync(b->d_reg_off, 0, (nr + 1) * sizeof(int64_t), st));
+  if (nr == 0) return 0;
+  const bwaflow_opt_t &op = b->ctx->par.opt;
+  C2AOpt o{op.a, op.w, op.pen_clip5, op.pen_clip3, op.o_del, op.e_del, op.o_ins, op.e_ins};
+  size_t tmp;
+  // per-chain seed prefix
+  c2a_nseeds<<<(unsigned)((nc + 1 + 255) / 256), 256, 0, st>>>(b->d_chains, nc, b->d_nseeds);
+  tmp = b->tmp_bytes;
+  BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_nseeds, b->d_sbase, (int)(nc + 1), st));
+  c2a_mark_reads<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(b->d_chain_off, nr, b->d_chain_read);
+  cub::DoubleBuffer<uint64_t> sk(b->d_skeys[0], b->d_skeys[1]);
+  cub::DoubleBuffer<uint32_t> sv(b->d_svals[0], b->d_svals[1]);
+  if (nc) {
+    c2a_chain_prep<<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(b->d_chains, nc, b->d_chain_read, b->d_read_off, b->d_seeds, b->d_sbase,
+                                                               b->ctx->ix, o, b->d_win, b->d_skeys[0], b->d_svals[0], err);
+    if (ns) {
+      tmp = b->tmp_bytes;
+      BF_CUDA(cub::DeviceRadixSort::SortPairs(b->d_tmp, tmp, sk, sv, (int)ns, 0, 64, st));
+      c2a_gather_seeds<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(b->d_seeds, sv.Current(), ns, b->d_sseeds);
+      BF_CUDA(cudaMemsetAsync(b->d_skipped, 0, ns, st));
+    }
+  }
+  // read queue
+  c2a_read_prep<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(b->d_read_off, b->d_chain_off, b->d_sbase, nr, b->d_rkeys[0], b->d_rvals[0], hist, err);
+  cub::DoubleBuffer<uint32_t> rk(b->d_rkeys[0], b->d_rkeys[1]), rv(b->d_rvals[0], b->d_rvals[1]);
+  tmp = b->tmp_bytes;
+  BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(b->d_tmp, tmp, rk, rv, (int)nr, 0, 27, st));
+  c2a_ranges_kernel<<<1, 1, 0, st>>>(hist, queue);
+  C2AArgs a;
+  a.bases = b->d_bases; a.read_off = b->d_read_off; a.chains = b->d_chains; a.chain_off = b->d_chain_off;
+  a.sbase = b->d_sbase; a.sseeds = b->d_sseeds; a.win = b->d_win; a.skipped = b->d_skipped; a.regs = b->d_regs;
+  a.n_regs = b->d_nregs; a.order = rv.Current(); a.queue = queue; a.err = err;
+  a.cells = (unsigned long long *)(b->d_ctl + 3 * C2A_NCLASS + 2);
+  a.refill = b->refill; a.ix = b->ctx->ix; a.sc = b->ctx->par.sc; a.o = o;
+  for (int c = C2A_NCLASS - 1; c >= 0; --c) {
+    a.cls = c; a.qmax = h_c2a_qmax[c];
+    const size_t smem = (size_t)h_c2a_threads[c] * (h_c2a_qmax[c] + 1) * sizeof(uint32_t);
+    if (h_c2a_threads[c] == 64) c2a_kernel<64><<<b->blocks[c], 64, smem, st>>>(a);
+    else c2a_kernel<32><<<b->blocks[c], 32, smem, st>>>(a);
+  }
+  // compact
+  c2a_widen<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(b->d_nregs, nr, b->d_nregs64);
+  tmp = b->tmp_bytes;
+  BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_nregs64, b->d_reg_off, (int)(nr + 1), st));
+  c2a_compact<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(b->d_chain_off, b->d_sbase, b->d_nregs, b->d_reg_off, nr, b->d_regs, b->d_regs_out);
+  BF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int bwaflow_c2a_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_bases, int64_t max_chains,
+                             int64_t max_seeds, bwaflow_c2a_batch_t **out)
+{
+  BF_REQUIRE(ctx && out, -22, "bwaflow_c2a_batch_create: null argument");
+  BF_REQUIRE(ctx->has_index, -22, "bwaflow_c2a_batch_create: the context has no index");
+  BF_REQUIRE(max_reads > 0 && max_reads < (1LL << 31) - 1 && max_chains < (1LL << 24) && max_seeds < (1LL << 31) - 1, -22,
+             "bwaflow_c2a_batch_create: capacity out of range (reads < 2^31, chains < 2^24, seeds < 2^31)");
+  BF_CUDA(cudaSetDevice(ctx->device));
+  bwaflow_c2a_batch *b = (bwaflow_c2a_batch *)calloc(1, sizeof(*b));
+  b->ctx = ctx; b->max_reads = max_reads; b->max_bases = max_bases; b->max_chains = max_chains; b->max_seeds = max_seeds;
+  b->refill = 8;
+  if (const char *s = getenv("BWAFLOW_C2A_REFILL")) b->refill = atoi(s) > 0 ? atoi(s) : 8;
+  BF_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  if (b->tm.init()) return -5;
+  const int64_t mc = max_chains + 1, ms = max_seeds + 1, mr = max_reads + 1;
+  BF_CUDA(cudaMalloc(&b->d_bases, max_bases + 16));
+  BF_CUDA(cudaMalloc(&b->d_read_off, mr * 8));
+  BF_CUDA(cudaMalloc(&b->d_chain_off, mr * 8));
+  BF_CUDA(cudaMalloc(&b->d_chains, mc * sizeof(bwaflow_chain_t)));
+  BF_CUDA(cudaMalloc(&b->d_seeds, ms * sizeof(bwaflow_seed_t)));
+  BF_CUDA(cudaMalloc(&b->d_sseeds, ms * sizeof(bwaflow_seed_t)));
+  BF_CUDA(cudaMalloc(&b->d_nseeds, (mc + 1) * 8));
+  BF_CUDA(cudaMalloc(&b->d_sbase, (mc + 1) * 8));
+  BF_CUDA(cudaMalloc(&b->d_chain_read, mc * 8));
+  BF_CUDA(cudaMalloc(&b->d_win, mc * 16));
+  for (int i = 0; i < 2; ++i) {
+    BF_CUDA(cudaMalloc(&b->d_skeys[i], ms * 8));
+    BF_CUDA(cudaMalloc(&b->d_svals[i], ms * 4));
+    BF_CUDA(cudaMalloc(&b->d_rkeys[i], mr * 4));
+    BF_CUDA(cudaMalloc(&b->d_rvals[i], mr * 4));
+  }
+  size_t t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+  {
+    cub::DoubleBuffer<uint64_t> sk(b->d_skeys[0], b->d_skeys[1]);
+    cub::DoubleBuffer<uint32_t> sv(b->d_svals[0], b->d_svals[1]), rk(b->d_rkeys[0], b->d_rkeys[1]), rv(b->d_rvals[0], b->d_rvals[1]);
+    BF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, sk, sv, (int)ms, 0, 64, b->stream));
+    BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, t2, rk, rv, (int)mr, 0, 27, b->stream));
+    BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t3, b->d_nseeds, b->d_sbase, (int)(mc + 1), b->stream));
+    BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t4, b->d_nseeds, b->d_sbase, (int)(mr + 1), b->stream));
+  }
+  b->tmp_bytes = max3(t1, t2, t3 > t4 ? t3 : t4) + 256;
+  BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
+  BF_CUDA(cudaMalloc(&b->d_skipped, ms));
+  BF_CUDA(cudaMalloc(&b->d_regs, ms * sizeof(bwaflow_alnreg_t)));
+  BF_CUDA(cudaMalloc(&b->d_regs_out, ms * sizeof(bwaflow_alnreg_t)));
+  BF_CUDA(cudaMallocHost(&b->h_regs, ms * sizeof(bwaflow_alnreg_t)));
+  BF_CUDA(cudaMalloc(&b->d_nregs, mr * 4));
+  BF_CUDA(cudaMalloc(&b->d_nregs64, (mr + 1) * 8));
+  BF_CUDA(cudaMalloc(&b->d_reg_off, (mr + 1) * 8));
+  BF_CUDA(cudaMallocHost(&b->h_reg_off, (mr + 1) * 8));
+  BF_CUDA(cudaMalloc(&b->d_ctl, (3 * C2A_NCLASS + 4) * sizeof(int)));
+  BF_CUDA(cudaMallocHost(&b->h_ctl, 4 * sizeof(int)));
+  for (int c = 0; c < C2A_NCLASS; ++c) {
+    const size_t smem = (size_t)h_c2a_threads[c] * (h_c2a_qmax[c] + 1) * sizeof(uint32_t);
+    int per_sm = 0;
+    if (h_c2a_threads[c] == 64) {
+      BF_CUDA(cudaFuncSetAttribute(c2a_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c2a_kernel<64>, 64, smem));
+    } else {
+      BF_CUDA(cudaFuncSetAttribute(c2a_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c2a_kernel<32>, 32, smem));
+    }
+    BF_REQUIRE(per_sm > 0, -12, "chain2aln kernel class %d does not fit on an SM", c);
+    b->blocks[c] = per_sm * ctx->n_sm;
+  }
+  *out = b;
+  return 0;
+}
+
+void bwaflow_c2a_batch_destroy(bwaflow_c2a_batch_t *b)
+{
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->stream);
+  cudaFree(b->d_bases); cudaFree(b->d_read_off); cudaFree(b->d_chain_off); cudaFree(b->d_chains); cudaFree(b->d_seeds);
+  cudaFree(b->d_sseeds); cudaFree(b->d_nseeds); cudaFree(b->d_sbase); cudaFree(b->d_chain_read); cudaFree(b->d_win);
+  for (int i = 0; i < 2; ++i) { cudaFree(b->d_skeys[i]); cudaFree(b->d_svals[i]); cudaFree(b->d_rkeys[i]); cudaFree(b->d_rvals[i]); }
+  cudaFree(b->d_tmp); cudaFree(b->d_skipped); cudaFree(b->d_regs); cudaFree(b->d_regs_out); cudaFreeHost(b->h_regs);
+  cudaFree(b->d_nregs); cudaFree(b->d_nregs64); cudaFree(b->d_reg_off); cudaFreeHost(b->h_reg_off);
+  cudaFree(b->d_ctl); cudaFreeHost(b->h_ctl);
+  b->tm.destroy();
+  cudaStreamDestroy(b->stream);
+  free(b);
+}
+
+static int c2a_finish_queue(bwaflow_c2a_batch *b)
+{
+  BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_reg_off, b->d_reg_off, (b->n_reads + 1) * 8, cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_ctl, b->d_ctl + 3 * C2A_NCLASS, 4 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  b->pending = true;
+  return 0;
+}
+
+int bwaflow_c2a_submit(bwaflow_c2a_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off,
+                       const bwaflow_chain_t *chains, const int64_t *chain_off,
+                       const bwaflow_seed_t *seeds, int64_t n_seeds)
+{
+  BF_REQUIRE(b && (n_reads == 0 || (bases && read_off && chain_off)), -22, "bwaflow_c2a_submit: null argument");
+  const int64_t n_bases = n_reads ? read_off[n_reads] : 0, n_chains = n_reads ? chain_off[n_reads] : 0;
+  BF_REQUIRE(n_reads >= 0 && n_reads <= b->max_reads && n_bases <= b->max_bases && n_chains <= b->max_chains && n_seeds <= b->max_seeds, -7,
+             "bwaflow_c2a_submit: batch capacity exceeded (%lld reads, %lld bases, %lld chains, %lld seeds)",
+             (long long)n_reads, (long long)n_bases, (long long)n_chains, (long long)n_seeds);
+  BF_REQUIRE(n_reads == 0 || (read_off[0] == 0 && chain_off[0] == 0), -22, "bwaflow_c2a_submit: offsets must start at 0");
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  int64_t used = 0;
+  for (int64_t c = 0; c < n_chains; ++c) {
+    BF_REQUIRE(chains[c].n_seeds >= 0 && chains[c].seed_off >= 0 && chains[c].seed_off + chains[c].n_seeds <= n_seeds, -22,
+               "bwaflow_c2a_submit: chain %lld references seeds outside [0,%lld)", (long long)c, (long long)n_seeds);
+    used += chains[c].n_seeds;
+  }
+  BF_REQUIRE(used <= b->max_seeds, -7, "bwaflow_c2a_submit: chains reference %lld seeds, capacity %lld", (long long)used, (long long)b->max_seeds);
+  b->n_reads = n_reads; b->n_chains = n_chains; b->n_seeds = used;
+  cudaStream_t st = b->stream;
+  BF_CUDA(cudaEventRecord(b->tm.ev[0], st));
+  if (n_reads) {
+    BF_CUDA(cudaMemcpyAsync(b->d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
+    BF_CUDA(cudaMemcpyAsync(b->d_read_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    BF_CUDA(cudaMemcpyAsync(b->d_chain_off, chain_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_chains) BF_CUDA(cudaMemcpyAsync(b->d_chains, chains, n_chains * sizeof(bwaflow_chain_t), cudaMemcpyHostToDevice, st));
+    if (n_seeds) BF_CUDA(cudaMemcpyAsync(b->d_seeds, seeds, n_seeds * sizeof(bwaflow_seed_t), cudaMemcpyHostToDevice, st));
+  }
+  BF_CUDA(cudaEventRecord(b->tm.ev[1], st));
+  int r = c2a_launch(b);
+  if (r) return r;
+  return c2a_finish_queue(b);
+}
+
+int bwaflow_c2a_rerun(bwaflow_c2a_batch_t *b)
+{
+  BF_REQUIRE(b, -22, "bwaflow_c2a_rerun: null batch");
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  BF_CUDA(cudaEventRecord(b->tm.ev[0], b->stream));
+  BF_CUDA(cudaEventRecord(b->tm.ev[1], b->stream));
+  int r = c2a_launch(b);
+  if (r) return r;
+  return c2a_finish_queue(b);
+}
+
+int bwaflow_c2a_collect(bwaflow_c2a_batch_t *b, const bwaflow_alnreg_t **regs, const int64_t **reg_off,
+                        int64_t *n_regs, bwaflow_timing_t *t)
+{
+  BF_REQUIRE(b && b->pending, -22, "bwaflow_c2a_collect: nothing submitted");
+  BF_CUDA(cudaStreamSynchronize(b->stream));
+  b->pending = false;
+  const int err = b->h_ctl[0];
+  BF_REQUIRE(err != 1, -34, "read longer than %d bases", h_c2a_qmax[C2A_NCLASS - 1]);
+  BF_REQUIRE(err != 2, -34, "extension whose scores may exceed %d (h0 + qlen*max_mat)", KSW_MAX_SCORE);
+  BF_REQUIRE(err != 3, -34, "chain/seed counts or seed scores exceed the sort-key fields (2^24 chains, 2^20 seeds per chain, score < 2^20)");
+  const int64_t total = b->n_reads ? b->h_reg_off[b->n_reads] : 0;
+  if (total) BF_CUDA(cudaMemcpyAsync(b->h_regs, b->d_regs_out, total * sizeof(bwaflow_alnreg_t), cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaEventRecord(b->tm.ev[3], b->stream));
+  BF_CUDA(cudaStreamSynchronize(b->stream));
+  if (t) {
+    memset(t, 0, sizeof(*t));
+    cudaEventElapsedTime(&t->h2d_ms, b->tm.ev[0], b->tm.ev[1]);
+    cudaEventElapsedTime(&t->kernel_ms, b->tm.ev[1], b->tm.ev[2]);
+    cudaEventElapsedTime(&t->d2h_ms, b->tm.ev[2], b->tm.ev[3]);
+    cudaEventElapsedTime(&t->total_ms, b->tm.ev[0], b->tm.ev[3]);
+    t->n_launches = b->n_reads ? 10 + C2A_NCLASS + 16 : 0;
+    t->work_units = (double)*(unsigned long long *)(b->h_ctl + 2);
+  }
+  if (regs) *regs = b->h_regs;
+  if (reg_off) *reg_off = b->h_reg_off;
+  if (n_regs) *n_regs = total;
+  return 0;
+}
+
+} // extern "C"

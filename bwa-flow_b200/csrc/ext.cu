@@ -29,6 +29,7 @@ struct ExtArgs {
   int *queue;                 // [EXT_NCLASS] heads, [EXT_NCLASS] ends
   bwaflow_ext_result_t *out;
   int *err;
+  unsigned long long *cells;
   int cls, qmax;
   int refill;                 // refill idle lanes once at least this many are idle
   DevScore sc;
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(THREADS) ext_kernel(const ExtArgs a)
     if (active) {
       if (k.row(col, stride, a.sc, (int)tp[k.i])) {
         a.out[job] = bwaflow_ext_result_t{k.best, k.best_j + 1, k.best_i + 1, k.end_i + 1, k.gscore, k.max_off};
+        atomicAdd(a.cells, (unsigned long long)k.cells);
         active = false;
       }
     }
@@ -134,9 +136,9 @@ struct bwaflow_ext_batch {
   uint8_t *d_q, *d_t;
   uint32_t *d_keys[2], *d_vals[2];
   void *d_tmp; size_t tmp_bytes;
-  int *d_ctl;                       // hist[8] | queue[16] | err
+  int *d_ctl;                       // hist[8] | queue[16] | err | pad | cells (u64)
   bwaflow_ext_result_t *d_out, *h_out;
-  int *h_err;
+  int *h_err;                       // err | pad | cells (u64)
   int blocks[EXT_NCLASS];
   int refill;
   bool pending;
@@ -147,7 +149,7 @@ static int ext_launch(bwaflow_ext_batch *b)
 {
   const int64_t n = b->n_jobs;
   int *hist = b->d_ctl, *queue = b->d_ctl + EXT_NCLASS, *err = b->d_ctl + 3 * EXT_NCLASS;
-  BF_CUDA(cudaMemsetAsync(b->d_ctl, 0, (3 * EXT_NCLASS + 1) * sizeof(int), b->stream));
+  BF_CUDA(cudaMemsetAsync(b->d_ctl, 0, (3 * EXT_NCLASS + 4) * sizeof(int), b->stream));
   if (n == 0) return 0;
   ext_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_jobs, n, b->d_keys[0], b->d_vals[0], hist, err);
   cub::DoubleBuffer<uint32_t> keys(b->d_keys[0], b->d_keys[1]), vals(b->d_vals[0], b->d_vals[1]);
@@ -156,7 +158,7 @@ static int ext_launch(bwaflow_ext_batch *b)
   ext_ranges_kernel<<<1, 1, 0, b->stream>>>(hist, queue);
   ExtArgs a;
   a.jobs = b->d_jobs; a.qpool = b->d_q; a.tpool = b->d_t; a.order = vals.Current(); a.queue = queue;
-  a.out = b->d_out; a.err = err; a.refill = b->refill; a.sc = b->ctx->par.sc;
+  a.out = b->d_out; a.err = err; a.cells = (unsigned long long *)(b->d_ctl + 3 * EXT_NCLASS + 2); a.refill = b->refill; a.sc = b->ctx->par.sc;
   for (int c = EXT_NCLASS - 1; c >= 0; --c) {
     a.cls = c; a.qmax = h_ext_qmax[c];
     const size_t smem = (size_t)h_ext_threads[c] * (h_ext_qmax[c] + 1) * sizeof(uint32_t);
@@ -191,10 +193,10 @@ int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_q
   cub::DoubleBuffer<uint32_t> keys(b->d_keys[0], b->d_keys[1]), vals(b->d_vals[0], b->d_vals[1]);
   BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, b->tmp_bytes, keys, vals, (int)max_jobs, 0, 27, b->stream));
   BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
-  BF_CUDA(cudaMalloc(&b->d_ctl, (3 * EXT_NCLASS + 1) * sizeof(int)));
+  BF_CUDA(cudaMalloc(&b->d_ctl, (3 * EXT_NCLASS + 4) * sizeof(int)));
   BF_CUDA(cudaMalloc(&b->d_out, max_jobs * sizeof(bwaflow_ext_result_t)));
   BF_CUDA(cudaMallocHost(&b->h_out, max_jobs * sizeof(bwaflow_ext_result_t)));
-  BF_CUDA(cudaMallocHost(&b->h_err, sizeof(int)));
+  BF_CUDA(cudaMallocHost(&b->h_err, 4 * sizeof(int)));
   for (int c = 0; c < EXT_NCLASS; ++c) {
     const size_t smem = (size_t)h_ext_threads[c] * (h_ext_qmax[c] + 1) * sizeof(uint32_t);
     int per_sm = 0;
@@ -230,7 +232,7 @@ static int ext_queue_d2h(bwaflow_ext_batch *b)
 {
   BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
   if (b->n_jobs) BF_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, b->n_jobs * sizeof(bwaflow_ext_result_t), cudaMemcpyDeviceToHost, b->stream));
-  BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_ctl + 3 * EXT_NCLASS, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_ctl + 3 * EXT_NCLASS, 4 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
   BF_CUDA(cudaEventRecord(b->tm.ev[3], b->stream));
   b->pending = true;
   return 0;
@@ -265,7 +267,7 @@ int bwaflow_ext_rerun(bwaflow_ext_batch_t *b)
   int r = ext_launch(b);
   if (r) return r;
   BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
-  BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_ctl + 3 * EXT_NCLASS, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_ctl + 3 * EXT_NCLASS, 4 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
   BF_CUDA(cudaEventRecord(b->tm.ev[3], b->stream));
   b->pending = true;
   return 0;
@@ -283,6 +285,7 @@ int bwaflow_ext_collect(bwaflow_ext_batch_t *b, const bwaflow_ext_result_t **out
     cudaEventElapsedTime(&t->d2h_ms, b->tm.ev[2], b->tm.ev[3]);
     cudaEventElapsedTime(&t->total_ms, b->tm.ev[0], b->tm.ev[3]);
     t->n_launches = b->n_jobs ? 3 + EXT_NCLASS + 7 : 0;   // key + ranges + 8 class kernels + cub passes
+    t->work_units = (double)*(unsigned long long *)(b->h_err + 2);   // DP cells executed
   }
   BF_REQUIRE(*b->h_err != 1, -34, "extension job with qlen > %d (or negative length)", h_ext_qmax[EXT_NCLASS - 1]);
   BF_REQUIRE(*b->h_err != 2, -34, "extension job whose scores may exceed %d (h0 + qlen*max_mat) or with h0 <= 0", KSW_MAX_SCORE);

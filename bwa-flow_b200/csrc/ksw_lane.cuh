@@ -36,6 +36,7 @@ struct KswLane {
   int qlen, tlen, w, h0;
   int i, lo, hi;
   int best, best_i, best_j, end_i, gscore, max_off;
+  unsigned cells;              // DP cells executed (ksw.c:424-448 iterations) since begin()
 
   // Sets up row -1 (ksw.c:395-397) and the clamped band (ksw.c:399-407).  qf(j) yields query base j.
   // Returns false when the job cannot be represented in the packed row state.
@@ -49,7 +50,7 @@ struct KswLane {
     lim = gap_limit(qlen * sc.smax + end_bonus - sc.o_del, sc.e_del);
     w = w < lim ? w : lim;
     i = 0; lo = 0; hi = qlen;
-    best = h0; best_i = best_j = -1; end_i = -1; gscore = -1; max_off = 0;
+    best = h0; best_i = best_j = -1; end_i = -1; gscore = -1; max_off = 0; cells = 0;
     if (h0 + qlen * sc.smax > KSW_MAX_SCORE || h0 <= 0) return false;
     const int gi = sc.o_ins + sc.e_ins;
     uint32_t *p = col;
@@ -89,6 +90,7 @@ struct KswLane {
       left = h;
     }
     const int jend = lo < hi ? hi : lo;
+    cells += (unsigned)(jend - lo);
     p = col + hi * stride;
     *p = (*p & KSW_QMASK) | (uint32_t)left;              // eh[end] = {h1, 0}   ksw.c:449
     if (jend == qlen) {                                  // ksw.c:450-453

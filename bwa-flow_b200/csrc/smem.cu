@@ -1,0 +1,636 @@
+// Stage 2 on the device: reads -> SMEM intervals, exact mem_collect_intv_new semantics
+// (src/bwa_wrapper.cpp:207-246: bwt_smem1a_new :325-450, pass-2 re-seeding, bwt_seed_strategy1
+// bwa/bwt.c:358-379, final sort by info), plus SA lookups (bwt_sa, bwa/bwt.c:86-96).
+// Mirrors SeqsToChainsFPGA::compute's role (src/fpga/FPGAPipeline.cpp:582) behind an SMemTask-like
+// submit/collect pair; there is no 256-interval cap and no CPU redo (:706-714) -- a full per-read
+// slot is detected on the device and the batch is re-run with larger slots.
+//
+// The FM-index (occ-interleaved BWT, 64-byte blocks = 4 x u64 counts + 128 two-bit symbols,
+// bwa/bwt.h:72-73) is resident in HBM; an occurrence lookup is four 128-bit loads of one block.
+// Seeding is a chain of dependent random block reads, so the kernel keeps one read per lane and many
+// lanes in flight, and the irregular control flow of bwt_smem1a_new is written as a per-lane flow
+// machine whose ONLY expensive operation -- bwt_extend (bwa/bwt.c:262-275) -- sits at one convergent
+// call site: every trip of the warp loop performs one interval extension for every live lane.
+#include <cub/device/device_scan.cuh>
+#include <string.h>
+#include <stdlib.h>
+#include "internal.cuh"
+
+namespace bwaflow {
+
+struct Intv { uint64_t x0, x1, x2; };
+
+// counts of A,C,G,T among symbols [0, n) of a 64-byte occ block whose symbol words are w0..w3 (u64, MSB first)
+__device__ __forceinline__ void block_count(const uint4 s0, const uint4 s1, int n, uint64_t cnt[4])
+{
+  const uint64_t W[4] = {(uint64_t)s0.x << 32 | s0.y, (uint64_t)s0.z << 32 | s0.w,
+                         (uint64_t)s1.x << 32 | s1.y, (uint64_t)s1.z << 32 | s1.w};
+  int c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = n - 32 * i;                       // symbols of this word that count
+    m = m < 0 ? 0 : (m > 32 ? 32 : m);
+    const uint64_t keep = m ? (~0ull << (64 - 2 * m)) & 0x5555555555555555ull : 0ull;
+    const uint64_t lo = W[i], hi = W[i] >> 1;
+    c1 += __popcll(~hi & lo & keep);
+    c2 += __popcll(hi & ~lo & keep);
+    c3 += __popcll(hi & lo & keep);
+  }
+  cnt[0] += (uint64_t)(n - c1 - c2 - c3); cnt[1] += (uint64_t)c1; cnt[2] += (uint64_t)c2; cnt[3] += (uint64_t)c3;
+}
+
+// Occ(., k) for all four bases: bwt_occ4, bwa/bwt.c:169-186
+__device__ __forceinline__ void occ4(const DevIndex &ix, uint64_t k, uint64_t cnt[4], unsigned long long *blocks)
+{
+  if (k == (uint64_t)-1) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; return; }
+  k -= (k >= ix.primary);
+  const uint4 *b = ix.bwt + ((k >> 7) << 2);
+  const uint4 c0 = __ldg(b), c1 = __ldg(b + 1), s0 = __ldg(b + 2), s1 = __ldg(b + 3);
+  cnt[0] = (uint64_t)c0.y << 32 | c0.x; cnt[1] = (uint64_t)c0.w << 32 | c0.z;
+  cnt[2] = (uint64_t)c1.y << 32 | c1.x; cnt[3] = (uint64_t)c1.w << 32 | c1.z;
+  block_count(s0, s1, (int)(k & 127) + 1, cnt);
+  ++*blocks;
+}
+
+// ok[c] of bwt_extend (bwa/bwt.c:262-275) for the one base c the caller wants.  The two Occ lookups share the
+// block load when both ends fall in the same 128-symbol interval (bwt_2occ4, bwa/bwt.c:189-220).
+__device__ __forceinline__ Intv extend1(const DevIndex &ix, const Intv ik, int is_back, int c, unsigned long long *blocks)
+{
+  const uint64_t xf = is_back ? ik.x0 : ik.x1, xg = is_back ? ik.x1 : ik.x0;
+  const uint64_t k = xf - 1, l = xf - 1 + ik.x2;
+  uint64_t tk[4], tl[4];
+  const uint64_t _k = k - (k >= ix.primary), _l = l - (l >= ix.primary);
+  if (k != (uint64_t)-1 && (_k >> 7) == (_l >> 7)) {
+    const uint4 *b = ix.bwt + ((_k >> 7) << 2);
+    const uint4 c0 = __ldg(b), c1 = __ldg(b + 1), s0 = __ldg(b + 2), s1 = __ldg(b + 3);
+    tk[0] = (uint64_t)c0.y << 32 | c0.x; tk[1] = (uint64_t)c0.w << 32 | c0.z;
+    tk[2] = (uint64_t)c1.y << 32 | c1.x; tk[3] = (uint64_t)c1.w << 32 | c1.z;
+    tl[0] = tk[0]; tl[1] = tk[1]; tl[2] = tk[2]; tl[3] = tk[3];
+    block_count(s0, s1, (int)(_k & 127) + 1, tk);
+    block_count(s0, s1, (int)(_l & 127) + 1, tl);
+    ++*blocks;
+  } else {
+    occ4(ix, k, tk, blocks);
+    occ4(ix, l, tl, blocks);
+  }
+  Intv o;
+  uint64_t acc = xg + (xf <= ix.primary && xf + ik.x2 - 1 >= ix.primary);
+  for (int b = 3; b > c; --b) acc += tl[b] - tk[b];
+  const uint64_t nf = ix.L2[c] + 1 + tk[c];
+  o.x2 = tl[c] - tk[c];
+  if (is_back) { o.x0 = nf; o.x1 = acc; } else { o.x1 = nf; o.x0 = acc; }
+  return o;
+}
+
+__device__ __forceinline__ Intv set_intv(const DevIndex &ix, int c)
+{ // bwt_set_intv, bwa/bwt.h:80
+  Intv ik; ik.x0 = ix.L2[c] + 1; ik.x2 = ix.L2[c + 1] - ix.L2[c]; ik.x1 = ix.L2[3 - c] + 1; return ik;
+}
+
+struct SmemArgs {
+  const uint8_t *bases; const int64_t *read_off; int64_t n_reads;
+  bwaflow_intv_t *slots; int cap;            // per-read output slot of `cap` intervals
+  int *counts;                               // per-read interval count (or cap+1 on overflow)
+  int *ctl;                                  // [0] queue head, [1] overflow flag, [2] too-long flag
+  unsigned long long *blocks;                // occ-block touches (64 B each)
+  DevIndex ix;
+  int min_seed_len, split_len, split_width, max_mem_intv;
+};
+
+// program counter of the per-lane flow machine
+enum { PC_FETCH, PC_NEXT, PC_F_HEAD, PC_F_DONE, PC_B_HEAD, PC_BE_HEAD, PC_BE_DONE, PC_FE_K, PC_FE_M, PC_B_NEXT, PC_SMEM_DONE,
+       PC_P3_HEAD, PC_FINISH, PC_EXTEND, PC_EXIT };
+enum { ST_F, ST_BE, ST_FE, ST_P3 };
+
+template <int MAXL>
+__global__ void __launch_bounds__(128) smem_kernel(const SmemArgs a)
+{
+  // per-lane lists of bwt_smem1a_new: forward matches (interval + end) and the leftward trail of one of them
+  uint64_t f0[MAXL], f1[MAXL], f2[MAXL]; int fend[MAXL];
+  uint64_t b0[MAXL], b1[MAXL], b2[MAXL];
+  const DevIndex &ix = a.ix;
+  const unsigned full = 0xffffffffu;
+  const int msl = a.min_seed_len;
+
+  int pc = PC_FETCH, st = ST_F;
+  // read
+  int64_t r = -1; int len = 0; const uint8_t *q = nullptr; bwaflow_intv_t *mem = nullptr; int n_mem = 0;
+  int pass = 1, x = 0, k2 = 0, old_n = 0;
+  // one bwt_smem1a_new call
+  int sx = 0, mi = 1, i = 0, fwd_n = 0, back_n = 0, fi = 0, start = 0, stop = 0, kb = 0, bk = 0, m = 0, ret = 0, px = 0;
+  Intv ik = {0, 0, 0}; int ik_beg = 0, ik_end = 0;
+  Intv cand = {0, 0, 0}; int cand_beg = 0, cand_end = 0;
+  int ext_back = 0, ext_c = 0;
+  unsigned long long blocks = 0;
+
+  auto push_mem = [&](const Intv &v, int beg, int end) {
+    if (n_mem < a.cap) {
+      bwaflow_intv_t o; o.x[0] = v.x0; o.x[1] = v.x1; o.x[2] = v.x2; o.info = (uint64_t)(uint32_t)beg << 32 | (uint32_t)end;
+      mem[n_mem] = o;
+    }
+    ++n_mem;
+  };
+
+  for (;;) {
+    // ---- flow machine: run until this lane needs one interval extension (or has no more reads)
+    while (pc != PC_EXTEND && pc != PC_EXIT) {
+      switch (pc) {
+      case PC_FETCH: {
+        r = (int64_t)atomicAdd(a.ctl, 1);
+        if (r >= a.n_reads) { pc = PC_EXIT; break; }
+        const int64_t ro = a.read_off[r];
+        len = (int)(a.read_off[r + 1] - ro); q = a.bases + ro;
+        mem = a.slots + r * a.cap; n_mem = 0; pass = 1; x = 0;
+        if (len >= MAXL) { atomicExch(a.ctl + 2, 1); a.counts[r] = 0; pc = PC_FETCH; break; }
+        if (len < msl) { pc = PC_FINISH; break; }            // src/bwa_wrapper.cpp:150
+        pc = PC_NEXT;
+        break;
+      }
+      case PC_NEXT:                                          // mem_collect_intv_new's three loops
+        if (pass == 1) {                                     // :214-218
+          while (x < len && q[x] > 3) ++x;
+          if (x < len) { sx = x; mi = 1; pc = PC_F_HEAD; fwd_n = back_n = 0; ik = set_intv(ix, q[sx]); ik_end = sx + 1; i = sx + 1; }
+          else { pass = 2; old_n = n_mem < a.cap ? n_mem : a.cap; k2 = 0; }
+        } else if (pass == 2) {                              // :220-226
+          pc = PC_NEXT;
+          bool go = false;
+          while (k2 < old_n) {
+            const bwaflow_intv_t p = mem[k2++];
+            const int s = (int)(p.info >> 32), e = (int)(uint32_t)p.info;
+            if (e - s < a.split_len || p.x[2] > (uint64_t)a.split_width) continue;
+            sx = (s + e) >> 1; mi = (int)p.x[2] + 1; go = true;
+            break;
+          }
+          if (go) {
+            if (q[sx] > 3) break;                            // bwt_smem1a_new :338 (cannot happen inside an SMEM)
+            fwd_n = back_n = 0; ik = set_intv(ix, q[sx]); ik_end = sx + 1; i = sx + 1; pc = PC_F_HEAD;
+          } else { pass = 3; x = 0; if (a.max_mem_intv <= 0) pc = PC_FINISH; }
+        } else {                                             // :228-243
+          while (x < len && q[x] > 3) ++x;
+          if (x < len) { px = x; ik = set_intv(ix, q[x]); i = x + 1; pc = PC_P3_HEAD; }
+          else pc = PC_FINISH;
+        }
+        break;
+      case PC_F_HEAD:                                        // forward sweep, src/bwa_wrapper.cpp:346-363
+        if (i < len && q[i] < 4) { ext_back = 0; ext_c = 3 - q[i]; st = ST_F; pc = PC_EXTEND; break; }
+        f0[fwd_n] = ik.x0; f1[fwd_n] = ik.x1; f2[fwd_n] = ik.x2; fend[fwd_n] = ik_end; ++fwd_n;   // N or end of read
+        pc = PC_F_DONE;
+        break;
+      case PC_F_DONE:
+        ret = fend[fwd_n - 1]; start = sx; stop = sx; fi = 0;
+        pc = PC_B_HEAD;
+        break;
+      case PC_B_HEAD:                                        // :367-371
+        if (fi >= fwd_n) { pc = PC_SMEM_DONE; break; }
+        ik.x0 = f0[fi]; ik.x1 = f1[fi]; ik.x2 = f2[fi]; ik_end = fend[fi]; ik_beg = sx;
+        if (back_n == 0 || stop - start >= 3) {
+          b0[0] = ik.x0; b1[0] = ik.x1; b2[0] = ik.x2; back_n = 1;
+          kb = sx - 1; pc = PC_BE_HEAD;
+        } else { stop = fend[fi]; bk = back_n - 1; pc = PC_FE_K; }
+        break;
+      case PC_BE_HEAD:                                       // back-enlarge, :374-386
+        if (kb >= 0 && q[kb] < 4) { ext_back = 1; ext_c = q[kb]; st = ST_BE; pc = PC_EXTEND; }
+        else pc = PC_BE_DONE;
+        break;
+      case PC_BE_DONE:                                       // :387-400
+        start = fend[fi]; stop = fi == fwd_n - 1 ? len : fend[fi + 1];
+        if (fi > 0 && ik_beg > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+        cand = ik; cand_beg = ik_beg; cand_end = ik_end;
+        pc = PC_B_NEXT;
+        break;
+      case PC_FE_K:                                          // forward-enlarge, :404-429
+        if (bk < 0) { pc = PC_B_NEXT; break; }
+        ik.x0 = b0[bk]; ik.x1 = b1[bk]; ik.x2 = b2[bk]; m = start + 1;
+        pc = PC_FE_M;
+        break;
+      case PC_FE_M:
+        if (m <= stop) { ext_back = 0; ext_c = 3 - q[m - 1]; st = ST_FE; pc = PC_EXTEND; }
+        else { --bk; pc = PC_FE_K; }
+        break;
+      case PC_B_NEXT:                                        // :431-443
+        ++fi;
+        if (fi < fwd_n) {
+          int max_len = cand_beg + fend[fi];
+          while (max_len < msl && fi < fwd_n) {
+            ++fi;
+            if (fi < fwd_n) stop = fend[fi];
+            max_len = cand_beg + stop;
+          }
+        }
+        if (fi >= fwd_n && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+        pc = PC_B_HEAD;
+        break;
+      case PC_SMEM_DONE:
+        if (pass == 1) x = ret;
+        pc = PC_NEXT;
+        break;
+      case PC_P3_HEAD:                                       // bwt_seed_strategy1, bwa/bwt.c:366-378
+        if (i < len) {
+          if (q[i] > 3) { x = i + 1; pc = PC_NEXT; }
+          else { ext_back = 0; ext_c = 3 - q[i]; st = ST_P3; pc = PC_EXTEND; }
+        } else { x = len; pc = PC_NEXT; }
+        break;
+      case PC_FINISH: {                                      // ks_introsort by info (:245); equal keys are equal elements
+        const int n = n_mem < a.cap ? n_mem : a.cap;
+        for (int u = 1; u < n; ++u) {
+          const bwaflow_intv_t v = mem[u];
+          int t = u - 1;
+          while (t >= 0 && mem[t].info > v.info) { mem[t + 1] = mem[t]; --t; }
+          mem[t + 1] = v;
+        }
+        a.counts[r] = n_mem;
+        if (n_mem > a.cap) atomicExch(a.ctl + 1, 1);
+        pc = PC_FETCH;
+        break;
+      }
+      }
+    }
+    if (__ballot_sync(full, pc == PC_EXTEND) == 0) break;
+    if (pc == PC_EXTEND) {
+      // ---- the one convergent call site of bwt_extend
+      const Intv o = extend1(ix, ik, ext_back, ext_c, &blocks);
+      switch (st) {
+      case ST_F:                                             // :353-357
+        if (o.x2 != ik.x2) {
+          f0[fwd_n] = ik.x0; f1[fwd_n] = ik.x1; f2[fwd_n] = ik.x2; fend[fwd_n] = ik_end; ++fwd_n;
+          if (o.x2 < (uint64_t)mi) { pc = PC_F_DONE; break; }
+        }
+        ik = o; ik_end = i + 1; ++i; pc = PC_F_HEAD;
+        break;
+      case ST_BE:                                            // :377-381
+        if (o.x2 < (uint64_t)mi) { pc = PC_BE_DONE; break; }
+        ik = o; ik_beg = kb;
+        b0[back_n] = ik.x0; b1[back_n] = ik.x1; b2[back_n] = ik.x2; ++back_n;
+        --kb; pc = PC_BE_HEAD;
+        break;
+      case ST_FE:                                            // :409-427
+        if (o.x2 < (uint64_t)mi) { --bk; pc = PC_FE_K; break; }
+        ik = o;
+        if (m == stop) {
+          ik_end = fend[fi]; ik_beg = sx - bk;
+          if (ik_beg > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+          cand = ik; cand_beg = ik_beg; cand_end = ik_end;
+          pc = PC_B_NEXT;
+        } else { ++m; pc = PC_FE_M; }
+        break;
+      case ST_P3:                                            // bwa/bwt.c:370-375
+        if (o.x2 < (uint64_t)a.max_mem_intv && i - px >= msl) {
+          if (o.x2 > 0) push_mem(o, px, i + 1);
+          x = i + 1; pc = PC_NEXT;
+        } else { ik = o; ++i; pc = PC_P3_HEAD; }
+        break;
+      }
+    }
+  }
+  if (blocks) atomicAdd(a.blocks, blocks);
+}
+
+// ---- SA -----------------------------------------------------------------------------------------
+
+// bwt_sa, bwa/bwt.c:86-96 with bwt_invPsi :53-59 (symbol and its Occ come from the same block)
+__device__ __forceinline__ uint64_t sa_lookup(const DevIndex &ix, uint64_t k, unsigned long long *blocks)
+{
+  uint64_t steps = 0;
+  const uint64_t mask = (1ull << ix.sa_shift) - 1;
+  while (k & mask) {
+    ++steps;
+    if (k == ix.primary) { k = 0; continue; }
+    const uint64_t x = k - (k > ix.primary);
+    const uint4 *b = ix.bwt + ((x >> 7) << 2);
+    const uint4 c0 = __ldg(b), c1 = __ldg(b + 1), s0 = __ldg(b + 2), s1 = __ldg(b + 3);
+    const int r = (int)(x & 127);
+    const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    uint32_t word = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) word = (r >> 4) == t ? sw[t] : word;
+    const int c = (word >> ((~r & 15) << 1)) & 3;
+    uint64_t cnt[4];
+    cnt[0] = (uint64_t)c0.y << 32 | c0.x; cnt[1] = (uint64_t)c0.w << 32 | c0.z;
+    cnt[2] = (uint64_t)c1.y << 32 | c1.x; cnt[3] = (uint64_t)c1.w << 32 | c1.z;
+    block_count(s0, s1, r + 1, cnt);
+    k = ix.L2[c] + cnt[c];
+    ++*blocks;
+  }
+  return steps + ix.sa[k >> ix.sa_shift];
+}
+
+__global__ void sa_kernel(DevIndex ix, int64_t n, const uint64_t *k, uint64_t *out, unsigned long long *blocks)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long nb = 0;
+  if (i < n) out[i] = sa_lookup(ix, k[i], &nb);
+  if (nb) atomicAdd(blocks, nb);
+}
+
+__global__ void smem_compact_counts(const int *counts, int64_t n, int cap, int64_t *out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = counts[i] < cap ? counts[i] : cap;
+  if (i == n) out[i] = 0;
+}
+
+__global__ void smem_compact(const bwaflow_intv_t *slots, int cap, const int64_t *off, int64_t n_reads, bwaflow_intv_t *out)
+{ // one warp per read, 32-byte intervals copied as uint4 halves
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_reads) return;
+  const int64_t lo = off[r], n = off[r + 1] - lo;
+  const uint4 *src = (const uint4 *)(slots + r * cap);
+  uint4 *dst = (uint4 *)(out + lo);
+  for (int64_t t = lane; t < 2 * n; t += 32) dst[t] = src[t];
+}
+
+// number of SA rows sampled per interval: the loop of src/bwa_wrapper.cpp:286-287 visits min(x2, max_occ) rows
+__global__ void seedpos_counts(const bwaflow_intv_t *intv, int64_t n, int max_occ, int64_t *out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = intv[i].x[2] < (uint64_t)max_occ ? (int64_t)intv[i].x[2] : max_occ;
+  if (i == n) out[i] = 0;
+}
+
+__global__ void seedpos_kernel(DevIndex ix, const bwaflow_intv_t *intv, int64_t n_intv, const int64_t *off, int64_t total,
+                               int max_occ, int64_t *pos, unsigned long long *blocks)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long nb = 0;
+  if (t < total) {
+    int64_t lo = 0, hi = n_intv;                       // last interval with off[iv] <= t
+    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
+    const bwaflow_intv_t p = intv[lo];
+    const uint64_t step = p.x[2] > (uint64_t)max_occ ? p.x[2] / max_occ : 1;
+    pos[t] = (int64_t)sa_lookup(ix, p.x[0] + (uint64_t)(t - off[lo]) * step, &nb);
+  }
+  if (nb) atomicAdd(blocks, nb);
+}
+
+} // namespace bwaflow
+
+using namespace bwaflow;
+
+struct bwaflow_smem_batch {
+  bwaflow_ctx_t *ctx;
+  cudaStream_t stream;
+  Timer tm;
+  int64_t max_reads, max_bases, n_reads, max_len;
+  uint8_t *d_bases; int64_t *d_read_off;
+  bwaflow_intv_t *d_slots; int cap; int64_t slots_cap;
+  int *d_counts; int64_t *d_cnt64, *d_off, *h_off;
+  bwaflow_intv_t *d_out, *h_out; int64_t out_cap;
+  int *d_ctl, *h_ctl;               // head | overflow | too-long | pad | blocks(u64)
+  void *d_tmp; size_t tmp_bytes;
+  int64_t n_intv;
+  // seed positions
+  int64_t *d_pcnt, *d_poff, *h_poff, *d_pos, *h_pos; int64_t pos_cap;
+  int blocks_per_launch;
+  bool pending;
+};
+
+static int smem_alloc_slots(bwaflow_smem_batch *b, int cap)
+{
+  if (b->d_slots) cudaFree(b->d_slots);
+  b->cap = cap; b->slots_cap = b->max_reads * cap;
+  BF_CUDA(cudaMalloc(&b->d_slots, b->slots_cap * sizeof(bwaflow_intv_t)));
+  return 0;
+}
+
+static int smem_launch(bwaflow_smem_batch *b)
+{
+  const int64_t nr = b->n_reads;
+  cudaStream_t st = b->stream;
+  BF_CUDA(cudaMemsetAsync(b->d_ctl, 0, 8 * sizeof(int), st));
+  BF_CUDA(cudaMemsetAsync(b->d_off, 0, (nr + 1) * 8, st));
+  if (nr == 0) return 0;
+  const bwaflow_opt_t &o = b->ctx->par.opt;
+  SmemArgs a;
+  a.bases = b->d_bases; a.read_off = b->d_read_off; a.n_reads = nr; a.slots = b->d_slots; a.cap = b->cap;
+  a.counts = b->d_counts; a.ctl = b->d_ctl; a.blocks = (unsigned long long *)(b->d_ctl + 4); a.ix = b->ctx->ix;
+  a.min_seed_len = o.min_seed_len; a.split_len = (int)(o.min_seed_len * o.split_factor + .499);
+  a.split_width = o.split_width; a.max_mem_intv = o.max_mem_intv;
+  int64_t want = (nr + 127) / 128;
+  const int grid = (int)(want < b->blocks_per_launch ? want : b->blocks_per_launch);
+  if (b->max_len < 160) smem_kernel<160><<<grid, 128, 0, st>>>(a);
+  else if (b->max_len < 256) smem_kernel<256><<<grid, 128, 0, st>>>(a);
+  else smem_kernel<1024><<<grid, 128, 0, st>>>(a);
+  smem_compact_counts<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(b->d_counts, nr, b->cap, b->d_cnt64);
+  size_t tmp = b->tmp_bytes;
+  BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_cnt64, b->d_off, (int)(nr + 1), st));
+  BF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int bwaflow_smem_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_bases, bwaflow_smem_batch_t **out)
+{
+  BF_REQUIRE(ctx && out, -22, "bwaflow_smem_batch_create: null argument");
+  BF_REQUIRE(ctx->has_index, -22, "bwaflow_smem_batch_create: the context has no index");
+  BF_REQUIRE(max_reads > 0 && max_reads < (1LL << 31) - 1, -22, "max_reads out of range");
+  BF_CUDA(cudaSetDevice(ctx->device));
+  bwaflow_smem_batch *b = (bwaflow_smem_batch *)calloc(1, sizeof(*b));
+  b->ctx = ctx; b->max_reads = max_reads; b->max_bases = max_bases;
+  BF_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  if (b->tm.init()) return -5;
+  BF_CUDA(cudaMalloc(&b->d_bases, max_bases + 16));
+  BF_CUDA(cudaMalloc(&b->d_read_off, (max_reads + 1) * 8));
+  BF_CUDA(cudaMalloc(&b->d_counts, (max_reads + 1) * 4));
+  BF_CUDA(cudaMalloc(&b->d_cnt64, (max_reads + 2) * 8));
+  BF_CUDA(cudaMalloc(&b->d_off, (max_reads + 2) * 8));
+  BF_CUDA(cudaMallocHost(&b->h_off, (max_reads + 2) * 8));
+  BF_CUDA(cudaMalloc(&b->d_ctl, 8 * sizeof(int)));
+  BF_CUDA(cudaMallocHost(&b->h_ctl, 8 * sizeof(int)));
+  int r = smem_alloc_slots(b, 32);
+  if (r) return r;
+  b->out_cap = max_reads * 16;
+  BF_CUDA(cudaMalloc(&b->d_out, b->out_cap * sizeof(bwaflow_intv_t)));
+  BF_CUDA(cudaMallocHost(&b->h_out, b->out_cap * sizeof(bwaflow_intv_t)));
+  BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b->tmp_bytes, b->d_cnt64, b->d_off, (int)(b->out_cap + 1), b->stream));
+  b->tmp_bytes += 256;
+  BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
+  BF_CUDA(cudaMalloc(&b->d_pcnt, (b->out_cap + 2) * 8));
+  BF_CUDA(cudaMalloc(&b->d_poff, (b->out_cap + 2) * 8));
+  BF_CUDA(cudaMallocHost(&b->h_poff, (b->out_cap + 2) * 8));
+  b->pos_cap = 0; b->d_pos = 0; b->h_pos = 0;
+  int per_sm = 0;
+  BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smem_kernel<256>, 128, 0));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  if (const char *s = getenv("BWAFLOW_SMEM_BLOCKS_PER_SM")) per_sm = atoi(s) > 0 ? atoi(s) : per_sm;
+  b->blocks_per_launch = per_sm * ctx->n_sm;
+  *out = b;
+  return 0;
+}
+
+void bwaflow_smem_batch_destroy(bwaflow_smem_batch_t *b)
+{
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->stream);
+  cudaFree(b->d_bases); cudaFree(b->d_read_off); cudaFree(b->d_counts); cudaFree(b->d_cnt64); cudaFree(b->d_off);
+  cudaFreeHost(b->h_off); cudaFree(b->d_ctl); cudaFreeHost(b->h_ctl); cudaFree(b->d_slots); cudaFree(b->d_out);
+  cudaFreeHost(b->h_out); cudaFree(b->d_tmp); cudaFree(b->d_pcnt); cudaFree(b->d_poff); cudaFreeHost(b->h_poff);
+  cudaFree(b->d_pos); cudaFreeHost(b->h_pos);
+  b->tm.destroy();
+  cudaStreamDestroy(b->stream);
+  free(b);
+}
+
+static int smem_queue_tail(bwaflow_smem_batch *b)
+{
+  BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_off, b->d_off, (b->n_reads + 1) * 8, cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_ctl, b->d_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  b->pending = true;
+  return 0;
+}
+
+int bwaflow_smem_submit(bwaflow_smem_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off)
+{
+  BF_REQUIRE(b && (n_reads == 0 || (bases && read_off)), -22, "bwaflow_smem_submit: null argument");
+  const int64_t n_bases = n_reads ? read_off[n_reads] : 0;
+  BF_REQUIRE(n_reads >= 0 && n_reads <= b->max_reads && n_bases <= b->max_bases, -7,
+             "bwaflow_smem_submit: batch capacity exceeded (%lld reads, %lld bases)", (long long)n_reads, (long long)n_bases);
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  int64_t max_len = 0;
+  for (int64_t i = 0; i < n_reads; ++i) { const int64_t l = read_off[i + 1] - read_off[i]; max_len = l > max_len ? l : max_len; }
+  BF_REQUIRE(max_len < 1024, -34, "read of %lld bases: the seeding kernel supports reads shorter than 1024", (long long)max_len);
+  b->n_reads = n_reads; b->max_len = max_len;
+  BF_CUDA(cudaEventRecord(b->tm.ev[0], b->stream));
+  if (n_reads) {
+    BF_CUDA(cudaMemcpyAsync(b->d_bases, bases, n_bases, cudaMemcpyHostToDevice, b->stream));
+    BF_CUDA(cudaMemcpyAsync(b->d_read_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, b->stream));
+  }
+  BF_CUDA(cudaEventRecord(b->tm.ev[1], b->stream));
+  int r = smem_launch(b);
+  if (r) return r;
+  return smem_queue_tail(b);
+}
+
+int bwaflow_smem_rerun(bwaflow_smem_batch_t *b)
+{
+  BF_REQUIRE(b, -22, "bwaflow_smem_rerun: null batch");
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  BF_CUDA(cudaEventRecord(b->tm.ev[0], b->stream));
+  BF_CUDA(cudaEventRecord(b->tm.ev[1], b->stream));
+  int r = smem_launch(b);
+  if (r) return r;
+  return smem_queue_tail(b);
+}
+
+int bwaflow_smem_collect(bwaflow_smem_batch_t *b, const bwaflow_intv_t **intv, const int64_t **intv_off,
+                         int64_t *n_intv, bwaflow_timing_t *t)
+{
+  BF_REQUIRE(b && b->pending, -22, "bwaflow_smem_collect: nothing submitted");
+  BF_CUDA(cudaStreamSynchronize(b->stream));
+  while (b->h_ctl[1]) {                      // some read filled its slot: grow the slots and redo the batch on the GPU
+    BF_REQUIRE(b->cap < 4096, -34, "a read produced more than 4096 intervals");
+    int r = smem_alloc_slots(b, b->cap * 4);
+    if (r) return r;
+    if ((r = smem_launch(b))) return r;
+    if ((r = smem_queue_tail(b))) return r;
+    BF_CUDA(cudaStreamSynchronize(b->stream));
+  }
+  b->pending = false;
+  const int64_t total = b->n_reads ? b->h_off[b->n_reads] : 0;
+  if (total > b->out_cap) {
+    cudaFree(b->d_out); cudaFreeHost(b->h_out); cudaFree(b->d_pcnt); cudaFree(b->d_poff); cudaFreeHost(b->h_poff); cudaFree(b->d_tmp);
+    b->out_cap = total + total / 4;
+    BF_CUDA(cudaMalloc(&b->d_out, b->out_cap * sizeof(bwaflow_intv_t)));
+    BF_CUDA(cudaMallocHost(&b->h_out, b->out_cap * sizeof(bwaflow_intv_t)));
+    BF_CUDA(cudaMalloc(&b->d_pcnt, (b->out_cap + 2) * 8));
+    BF_CUDA(cudaMalloc(&b->d_poff, (b->out_cap + 2) * 8));
+    BF_CUDA(cudaMallocHost(&b->h_poff, (b->out_cap + 2) * 8));
+    BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b->tmp_bytes, b->d_cnt64, b->d_off, (int)(b->out_cap + 1), b->stream));
+    b->tmp_bytes += 256;
+    BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
+  }
+  if (total) {
+    smem_compact<<<(unsigned)((b->n_reads * 32 + 255) / 256), 256, 0, b->stream>>>(b->d_slots, b->cap, b->d_off, b->n_reads, b->d_out);
+    BF_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, total * sizeof(bwaflow_intv_t), cudaMemcpyDeviceToHost, b->stream));
+  }
+  BF_CUDA(cudaEventRecord(b->tm.ev[3], b->stream));
+  BF_CUDA(cudaStreamSynchronize(b->stream));
+  b->n_intv = total;
+  if (t) {
+    memset(t, 0, sizeof(*t));
+    cudaEventElapsedTime(&t->h2d_ms, b->tm.ev[0], b->tm.ev[1]);
+    cudaEventElapsedTime(&t->kernel_ms, b->tm.ev[1], b->tm.ev[2]);
+    cudaEventElapsedTime(&t->d2h_ms, b->tm.ev[2], b->tm.ev[3]);
+    cudaEventElapsedTime(&t->total_ms, b->tm.ev[0], b->tm.ev[3]);
+    t->n_launches = b->n_reads ? 5 : 0;
+    t->work_units = (double)*(unsigned long long *)(b->h_ctl + 4);   // occ blocks touched (64 B each)
+  }
+  BF_REQUIRE(!b->h_ctl[2], -34, "a read is too long for the seeding kernel instance chosen for this batch");
+  if (intv) *intv = b->h_out;
+  if (intv_off) *intv_off = b->h_off;
+  if (n_intv) *n_intv = total;
+  return 0;
+}
+
+int bwaflow_smem_seed_positions(bwaflow_smem_batch_t *b, const int64_t **pos, const int64_t **pos_off,
+                                int64_t *n_pos, bwaflow_timing_t *t)
+{
+  BF_REQUIRE(b && !b->pending, -22, "bwaflow_smem_seed_positions: collect the batch first");
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  cudaStream_t st = b->stream;
+  const int64_t ni = b->n_intv;
+  const int max_occ = b->ctx->par.opt.max_occ;
+  BF_CUDA(cudaEventRecord(b->tm.ev[0], st));
+  BF_CUDA(cudaMemsetAsync(b->d_ctl + 4, 0, 8, st));
+  BF_CUDA(cudaMemsetAsync(b->d_poff, 0, (ni + 1) * 8, st));
+  if (ni) {
+    seedpos_counts<<<(unsigned)((ni + 1 + 255) / 256), 256, 0, st>>>(b->d_out, ni, max_occ, b->d_pcnt);
+    size_t tmp = b->tmp_bytes;
+    BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_pcnt, b->d_poff, (int)(ni + 1), st));
+  }
+  BF_CUDA(cudaMemcpyAsync(b->h_poff, b->d_poff, (ni + 1) * 8, cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaStreamSynchronize(st));
+  const int64_t total = b->h_poff[ni];
+  if (total > b->pos_cap) {
+    cudaFree(b->d_pos); cudaFreeHost(b->h_pos);
+    b->pos_cap = total + total / 4 + 1024;
+    BF_CUDA(cudaMalloc(&b->d_pos, b->pos_cap * 8));
+    BF_CUDA(cudaMallocHost(&b->h_pos, b->pos_cap * 8));
+  }
+  BF_CUDA(cudaEventRecord(b->tm.ev[1], st));
+  if (total) {
+    seedpos_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(b->ctx->ix, b->d_out, ni, b->d_poff, total, max_occ, b->d_pos,
+                                                                      (unsigned long long *)(b->d_ctl + 4));
+    BF_CUDA(cudaGetLastError());
+  }
+  BF_CUDA(cudaEventRecord(b->tm.ev[2], st));
+  if (total) BF_CUDA(cudaMemcpyAsync(b->h_pos, b->d_pos, total * 8, cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaMemcpyAsync(b->h_ctl, b->d_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaEventRecord(b->tm.ev[3], st));
+  BF_CUDA(cudaStreamSynchronize(st));
+  if (t) {
+    memset(t, 0, sizeof(*t));
+    cudaEventElapsedTime(&t->h2d_ms, b->tm.ev[0], b->tm.ev[1]);
+    cudaEventElapsedTime(&t->kernel_ms, b->tm.ev[1], b->tm.ev[2]);
+    cudaEventElapsedTime(&t->d2h_ms, b->tm.ev[2], b->tm.ev[3]);
+    cudaEventElapsedTime(&t->total_ms, b->tm.ev[0], b->tm.ev[3]);
+    t->n_launches = total ? 3 : 0;
+    t->work_units = (double)*(unsigned long long *)(b->h_ctl + 4);
+  }
+  if (pos) *pos = b->h_pos;
+  if (pos_off) *pos_off = b->h_poff;
+  if (n_pos) *n_pos = total;
+  return 0;
+}
+
+int bwaflow_sa_lookup(bwaflow_ctx_t *ctx, int64_t n, const uint64_t *k, uint64_t *out)
+{
+  BF_REQUIRE(ctx && ctx->has_index && (n == 0 || (k && out)), -22, "bwaflow_sa_lookup: bad argument");
+  BF_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return 0;
+  uint64_t *dk = 0, *dout = 0; unsigned long long *db = 0;
+  BF_CUDA(cudaMalloc(&dk, n * 8)); BF_CUDA(cudaMalloc(&dout, n * 8)); BF_CUDA(cudaMalloc(&db, 8));
+  BF_CUDA(cudaMemset(db, 0, 8));
+  BF_CUDA(cudaMemcpy(dk, k, n * 8, cudaMemcpyHostToDevice));
+  sa_kernel<<<(unsigned)((n + 127) / 128), 128>>>(ctx->ix, n, dk, dout, db);
+  BF_CUDA(cudaGetLastError());
+  BF_CUDA(cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dk); cudaFree(dout); cudaFree(db);
+  return 0;
+}
+
+} // extern "C"

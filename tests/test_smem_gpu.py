@@ -1,0 +1,123 @@
+"""GPU parity: stage 2 (reads -> sorted bwtintv_t lists) and SA lookups through the C ABI vs the golden vectors of the
+compiled reference (mem_collect_intv_new src/bwa_wrapper.cpp:207-246, bwt_sa bwa/bwt.c:86-96) and the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(ix, **opt_over):
+    from bwaflow_b200 import capi
+    index, keep = capi.make_index(ix.ref.view, ix.ref.ctg_off, ix.ref.ctg_len)
+    opt = capi.default_opt()
+    for k, v in opt_over.items():
+        setattr(opt, k, v)
+    return capi.Context(0, index, opt, keepalive=keep)
+
+
+@pytest.mark.parametrize("case", ["c1", "c5"])
+def test_smem_matches_golden(case, request):
+    from bwaflow_b200 import capi
+    ix = request.getfixturevalue("index_" + case)
+    g = request.getfixturevalue("golden_" + case)
+    ctx = _ctx(ix)
+    nt4 = ix.reads.nt4()
+    b = capi.SmemBatch(ctx, ix.reads.n, len(nt4))
+    b.submit(nt4, ix.reads.offsets)
+    intv, off, t = b.collect()
+    assert (off == g["intv_off"]).all(), np.nonzero(off != g["intv_off"])[0][:5]
+    assert intv.tobytes() == g["intv"].tobytes()
+    assert t.work_units > 0
+    # seed positions = bwt_sa over each interval exactly as mem_chain_postprocess samples them
+    pos, poff, _ = b.seed_positions()
+    max_occ = ctx.opt.max_occ
+    rng = np.random.default_rng(1)
+    for i in rng.integers(0, len(intv), 300):
+        x0, x2 = int(intv["x0"][i]), int(intv["x2"][i])
+        step = x2 // max_occ if x2 > max_occ else 1
+        ks = [x0 + k for k in range(0, x2, step)][:max_occ]
+        exp = [ix.ref.bwt_sa(k) for k in ks]
+        assert list(pos[poff[i]:poff[i + 1]]) == exp
+    b.rerun()
+    intv2, off2, _ = b.collect()
+    assert intv2.tobytes() == g["intv"].tobytes() and (off2 == off).all()
+    b.close()
+    ctx.close()
+
+
+def test_sa_lookup_known_answers(index_c1, golden_c1):
+    ctx = _ctx(index_c1)
+    got = ctx.sa_lookup(golden_c1["sa_k"])
+    assert (got == golden_c1["sa_v"]).all()
+    ctx.close()
+
+
+def test_smem_edge_reads(index_c1):
+    """All-N reads, reads shorter than min_seed_len, N-riddled reads, exact reference substrings (both strands),
+    a highly repetitive read, mixed lengths in one batch; checked against the oracle restatement."""
+    from bwaflow_b200 import capi
+    from oracle import api
+    ix = index_c1
+    O = api.Oracle.from_ref(ix.ref)
+    rng = np.random.default_rng(11)
+    pac = ix.ref.pac_array()
+    L = ix.ref.view.l_pac
+
+    def refsub(p, n):
+        idx = np.arange(p, p + n)
+        return ((pac[idx >> 2] >> ((~idx & 3) << 1)) & 3).astype(np.uint8)
+
+    reads = [np.full(60, 4, np.uint8), np.zeros(10, np.uint8), np.zeros(18, np.uint8), np.zeros(19, np.uint8)]
+    for _ in range(40):
+        n = int(rng.integers(19, 250))
+        p = int(rng.integers(0, L - n))
+        s = refsub(p, n)
+        if rng.random() < 0.5:
+            s = (3 - s)[::-1].copy()
+        k = rng.random()
+        if k < 0.3:
+            s[rng.random(n) < 0.1] = 4
+        elif k < 0.6:
+            m = rng.random(n) < 0.05
+            s[m] = (s[m] + 1) & 3
+        reads.append(s)
+    reads.append(np.tile(np.array([0, 1], np.uint8), 70))
+    reads.append(np.zeros(150, np.uint8))
+    off = np.zeros(len(reads) + 1, np.int64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    bases = np.concatenate(reads)
+    ctx = _ctx(ix)
+    b = capi.SmemBatch(ctx, len(reads), len(bases))
+    b.submit(bases, off)
+    intv, ioff, _ = b.collect()
+    for i, r in enumerate(reads):
+        exp = O.collect_intv(r)
+        got = intv[ioff[i]:ioff[i + 1]]
+        assert got.tobytes() == exp.tobytes(), (i, len(r), got, exp)
+    b.close()
+    ctx.close()
+
+
+def test_smem_slot_overflow_regrows(index_c1, golden_c1):
+    """Seeding knobs that make every read emit many intervals: the per-read slot overflows and the batch is redone
+    on the GPU with larger slots (no CPU redo as in FPGAPipeline.cpp:706-714)."""
+    from bwaflow_b200 import capi
+    from oracle import api
+    ix = index_c1
+    ctx = _ctx(ix, min_seed_len=5, max_mem_intv=1000000)
+    oo = ix.ref.orc_opt()
+    oo.min_seed_len = 5
+    oo.max_mem_intv = 1000000
+    O = api.Oracle(ix.ref.view, oo, ix.ref.ctg_off, ix.ref.ctg_len, keepalive=ix.ref)
+    nt4 = ix.reads.nt4()
+    n = 64
+    off = ix.reads.offsets[:n + 1]
+    b = capi.SmemBatch(ctx, n, int(off[-1]))
+    b.submit(nt4[:off[-1]], off)
+    intv, ioff, _ = b.collect()
+    assert (np.diff(ioff) > 32).any()
+    for i in range(n):
+        exp = O.collect_intv(nt4[off[i]:off[i + 1]])
+        assert intv[ioff[i]:ioff[i + 1]].tobytes() == exp.tobytes(), i
+    b.close()
+    ctx.close()
