@@ -38,6 +38,11 @@ class Opt(C.Structure):
                [("split_factor", C.c_float), ("mat", C.c_int8 * 25), ("_pad", C.c_int8 * 3)]
 
 
+class ChainOpt(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("w", "max_chain_gap", "min_chain_weight", "max_chain_extend", "min_seed_len", "max_occ")] + \
+               [("mask_level", C.c_float), ("drop_ratio", C.c_float)]
+
+
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("n_launches", C.c_int32), ("_pad", C.c_int32), ("work_units", C.c_double)]
@@ -87,6 +92,12 @@ def lib():
             L.bwaflow_smem_rerun.argtypes = [C.c_void_p]
             L.bwaflow_smem_seed_positions.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Timing)]
             L.bwaflow_sa_lookup.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.bwaflow_chain_opt_default.argtypes = [C.POINTER(ChainOpt)]
+        L.bwaflow_chain_build.argtypes = [C.POINTER(ChainOpt), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.bwaflow_chain_result_view.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                                C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]
+        L.bwaflow_chain_result_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -286,3 +297,35 @@ class SmemBatch:
         if self.h:
             self.L.bwaflow_smem_batch_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def default_chain_opt():
+    o = ChainOpt()
+    lib().bwaflow_chain_opt_default(C.byref(o))
+    return o
+
+
+def chain_build(l_pac, ctg_off, ctg_len, read_off, intv, intv_off, pos, pos_off, opt: ChainOpt | None = None, ctg_alt=None,
+                n_threads=0, copy=True):
+    """Host chaining (ChainsPipe's role): intervals + device-computed SA positions -> (chains, seeds, chain_off)."""
+    L = lib()
+    opt = opt if opt is not None else default_chain_opt()
+    ctg_off = np.ascontiguousarray(ctg_off, dtype=np.int64)
+    ctg_len = np.ascontiguousarray(ctg_len, dtype=np.int32)
+    alt = np.ascontiguousarray(ctg_alt, dtype=np.int32) if ctg_alt is not None else None
+    read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+    intv_off = np.ascontiguousarray(intv_off, dtype=np.int64)
+    pos_off = np.ascontiguousarray(pos_off, dtype=np.int64)
+    intv = np.ascontiguousarray(intv)
+    pos = np.ascontiguousarray(pos, dtype=np.int64)
+    res = C.c_void_p()
+    check(L.bwaflow_chain_build(C.byref(opt), int(l_pac), len(ctg_off), _p(ctg_off), _p(ctg_len), _p(alt) if alt is not None else None,
+                                len(read_off) - 1, _p(read_off), _p(intv), _p(intv_off), _p(pos), _p(pos_off), int(n_threads), C.byref(res)))
+    ch, sd, co = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    nc, ns = C.c_int64(), C.c_int64()
+    L.bwaflow_chain_result_view(res, C.byref(ch), C.byref(nc), C.byref(sd), C.byref(ns), C.byref(co))
+    chains = _view(ch.value, nc.value, CHAIN).copy()
+    seeds = _view(sd.value, ns.value, SEED).copy()
+    off = _view(co.value, len(read_off), np.dtype("<i8")).copy()
+    L.bwaflow_chain_result_free(res)
+    return chains, seeds, off

@@ -141,6 +141,27 @@ int bwaflow_smem_seed_positions(bwaflow_smem_batch_t *b, const int64_t **pos, co
 /* plain SA lookups (bwt_sa, bwa/bwt.c:86-96) */
 int bwaflow_sa_lookup(bwaflow_ctx_t *ctx, int64_t n, const uint64_t *k, uint64_t *out);
 
+/* ---- host chaining between the two device stages (the role of ChainsPipe::compute, src/Pipeline.cpp:408-438:
+ *      mem_chain_postprocess src/bwa_wrapper.cpp:248-323 with the bwt_sa results supplied by
+ *      bwaflow_smem_seed_positions, then mem_chain_flt bwa/bwamem.c:336-394).  CPU code, multi-threaded over
+ *      reads; offered so that a backend can go reads -> regions without the reference's host objects.  A drop-in
+ *      integration may keep using the reference's own ChainsPipe instead (tag=0 records). */
+typedef struct {
+  int32_t w, max_chain_gap, min_chain_weight, max_chain_extend, min_seed_len, max_occ;
+  float mask_level, drop_ratio;
+} bwaflow_chain_opt_t;
+typedef struct bwaflow_chain_result bwaflow_chain_result_t;
+void bwaflow_chain_opt_default(bwaflow_chain_opt_t *opt);
+int bwaflow_chain_build(const bwaflow_chain_opt_t *opt, int64_t l_pac, int32_t n_seqs, const int64_t *ctg_offset,
+                        const int32_t *ctg_len, const int32_t *ctg_is_alt /* may be NULL */,
+                        int64_t n_reads, const int64_t *read_off,
+                        const bwaflow_intv_t *intv, const int64_t *intv_off, const int64_t *pos, const int64_t *pos_off,
+                        int n_threads /* <1: all cores */, bwaflow_chain_result_t **out);
+/* chains of read r = chains[chain_off[r] .. chain_off[r+1]); seed_off indexes `seeds`; mem_chain_v order */
+void bwaflow_chain_result_view(const bwaflow_chain_result_t *r, const bwaflow_chain_t **chains, int64_t *n_chains,
+                               const bwaflow_seed_t **seeds, int64_t *n_seeds, const int64_t **chain_off);
+void bwaflow_chain_result_free(bwaflow_chain_result_t *r);
+
 #ifdef __cplusplus
 }
 #endif
