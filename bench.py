@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- hot-path throughput of the B200 backend (and, with --impl reference, of the reference's own CPU path).
+
+Metric: read pairs/s of the BWA-MEM per-read compute path (SMEM seeding -> chaining -> banded extension, i.e. kflow
+stages 2..4: reads in, mem_alnreg_t lists out) on BASELINE.json config[2]'s shape: a synthetic chr20-scale (64 Mbp)
+reference and 2x150 bp pairs at 1% substitutions.  One step = one pass of the hot path over one device batch
+(16 kflow records of 10 Mbp = 533,344 pairs by default).  Per rank the work is fixed (weak scaling): the index is
+replicated per GPU and every rank processes its own read shard; there is no data-path collective.
+
+  value  = pairs/s with the reads already resident in HBM when the timed region starts
+  e2e    = pairs/s through the public stage API from pinned HOST buffers (H2D of the reads and D2H of the regions inside)
+  roofline      for the dominant kernel of the step (seeding: 64-byte occ-block touches vs measured HBM GB/s)
+  roofline_ext  extension kernel: executed DP cells (GCUPS) vs the measured DPX issue peak / 5 lane-instr per cell
+  cpu_baseline  the compiled reference (oracle/_ref) on this box's host cores over a bounded sample of the same reads
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 under torchrun (one rank per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "read pairs/s, BWA-MEM per-read compute path (SMEM seeding + chaining + ksw_extend2 extension; reads -> mem_alnreg_t)"
+KFLOW_BATCH_BP = 10_000_000            # src/Pipeline.cpp:146
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-mbp", type=float, default=64.0)
+    ap.add_argument("--contigs", type=int, default=4)
+    ap.add_argument("--kflow-batches", type=int, default=16, help="10 Mbp records per device batch (= one step)")
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--sub-rate", type=float, default=0.01)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(args, rank):
+    from bwaflow_b200 import synth
+    ref = synth.make_reference(int(args.ref_mbp * 1e6), n_contigs=args.contigs, seed=64)
+    pairs_per_record = -(-KFLOW_BATCH_BP // (2 * args.read_len))           # getKseqBatch: stop at >= 10 Mbp, even count
+    n_pairs = pairs_per_record * args.kflow_batches
+    reads = synth.simulate_pairs(ref, n_pairs, args.read_len, args.sub_rate, seed=3 + rank, first_id=rank * n_pairs)
+    return ref, reads, n_pairs, pairs_per_record
+
+
+def shared_dir(args):
+    d = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(),
+                     "bwaflow_bench_%d_%d_%d" % (int(args.ref_mbp * 1000), args.contigs, os.getuid()))
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def barrier_max(x, world):
+    """max over ranks (torch.distributed is only used for this and the barrier; nothing crosses ranks on the data path)"""
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def cpu_hot_path(R, reads, lo, hi):
+    """stages 2 and 4 of the reference on reads [lo,hi): SeqsToChains::compute + ChainsToRegions::compute"""
+    b = R.batch(reads.slice(lo, hi), lo)
+    b.seq2chains()
+    b.chains2regions()
+    b.free()
+
+
+def run_reference_cpu(args, ref, reads, n_pairs_sample, built=None):
+    """Times the compiled reference's hot path (oracle/_ref) with one thread per host core over a bounded sample."""
+    from oracle import api
+    from concurrent.futures import ThreadPoolExecutor
+    td = tempfile.mkdtemp(prefix="bwaflow_ref_")
+    prefix = os.path.join(td, "ref")
+    if built is not None:
+        v = built.view
+        api.write_index_files(prefix, v.primary, list(v.L2), v.seq_len, built.bwt_array(), built.sa_array(), v.sa_intv,
+                              built.pac_array(), v.l_pac, ref.names, [int(x) for x in ref.lengths])
+    else:
+        ref.write_fasta(prefix + ".fa")
+        api.build_index(prefix + ".fa", prefix)
+    R = api.Ref(prefix, paired=True)
+    cores = os.cpu_count() or 1
+    n_reads = 2 * n_pairs_sample
+    chunk = max(2, (n_reads // (cores * 4)) & ~1)
+    cuts = list(range(0, n_reads, chunk)) + [n_reads]
+
+    def one_pass():
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            list(ex.map(lambda i: cpu_hot_path(R, reads, cuts[i], cuts[i + 1]), range(len(cuts) - 1)))
+        return time.perf_counter() - t0
+    return R, one_pass, cores
+
+
+def main():
+    args = parse()
+    rank, world, local = dist_env()
+    if world > 1 and args.impl == "ours":
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.impl == "reference" and rank != 0:
+        return
+    ref, reads, n_pairs, pairs_per_record = make_workload(args, rank)
+    workload = {"workload": "C3 shape: synthetic %.0f Mbp reference (%d contigs, FM-index replicated per GPU), 2x%dbp pairs @%.0f%% subst"
+                            % (args.ref_mbp, args.contigs, args.read_len, args.sub_rate * 100),
+                "pairs_per_step_per_gpu": n_pairs, "kflow_records_per_step": args.kflow_batches,
+                "l2": "inputs larger than L2: %.0f MB of reads per step plus >1 GB of per-step interval/region scratch rewritten every step "
+                      "(the %.0f MB FM-index itself is smaller than the 126 MB L2, as it would be in a real run on this reference)"
+                      % (2 * n_pairs * args.read_len / 1e6, args.ref_mbp * 1.5)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = args.cpu_sample_pairs or min(n_pairs, 50_000)
+        R, one_pass, cores = run_reference_cpu(args, ref, reads, sample)
+        for _ in range(min(args.warmup, 1)):
+            one_pass()
+        ts = [one_pass() for _ in range(args.steps)]
+        sec = float(np.mean(ts))
+        val = sample / sec
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload,
+                "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "reference",
+                                 "sample": "%d pairs per step, stages 2+4 of the compiled reference (oracle/_ref), one thread per core" % sample},
+                "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    from bwaflow_b200 import capi, stages
+    sd = shared_dir(args)
+    t0 = time.time()
+    built = None
+    codes = ref.concat()
+    built = capi.BuiltIndex(codes, ref.lengths) if (world == 1 or rank == 0) else None
+    if world > 1:
+        # rank 0 builds, the others read the arrays from shared memory (replication, not sharding)
+        if rank == 0:
+            np.save(os.path.join(sd, "bwt.npy"), built.bwt_array())
+            np.save(os.path.join(sd, "sa.npy"), built.sa_array())
+            np.save(os.path.join(sd, "pac.npy"), built.pac_array())
+            v = built.view
+            json.dump({"primary": v.primary, "L2": list(v.L2), "seq_len": v.seq_len, "sa_intv": v.sa_intv, "l_pac": v.l_pac},
+                      open(os.path.join(sd, "meta.json"), "w"))
+        barrier(world)
+    if built is not None:
+        index, ctg_off, ctg_len, keep = built.index(), built.ctg_off, built.ctg_len, built
+    else:
+        meta = json.load(open(os.path.join(sd, "meta.json")))
+        bwt = np.load(os.path.join(sd, "bwt.npy"), mmap_mode="r")
+        sa = np.load(os.path.join(sd, "sa.npy"), mmap_mode="r")
+        pac = np.load(os.path.join(sd, "pac.npy"), mmap_mode="r")
+        bwt, sa, pac = np.ascontiguousarray(bwt), np.ascontiguousarray(sa), np.ascontiguousarray(pac)
+        index = capi.Index()
+        index.primary, index.seq_len, index.bwt_size, index.bwt = meta["primary"], meta["seq_len"], len(bwt), bwt.ctypes.data
+        for i in range(5):
+            index.L2[i] = meta["L2"][i]
+        index.n_sa, index.sa_intv, index.sa = len(sa), meta["sa_intv"], sa.ctypes.data
+        index.l_pac, index.pac, index.n_seqs = meta["l_pac"], pac.ctypes.data, len(ref.lengths)
+        ctg_off = np.ascontiguousarray(ref.offsets, dtype=np.int64)
+        ctg_len = np.ascontiguousarray(ref.lengths, dtype=np.int32)
+        index.ctg_offset, index.ctg_len = ctg_off.ctypes.data, ctg_len.ctypes.data
+        keep = (bwt, sa, pac, ctg_off, ctg_len)
+    t_index = time.time() - t0
+    ctx = capi.Context(local, index, keepalive=keep)
+    nt4_np = reads.nt4()
+    bases = capi.pinned(nt4_np.shape, np.uint8)
+    bases[:] = nt4_np
+    read_off = capi.pinned((reads.n + 1,), np.int64)
+    read_off[:] = reads.offsets
+    threads = max(1, (os.cpu_count() or 1) // world)
+    hp = stages.HotPath(ctx, index, ctg_off, ctg_len, reads.n, len(bases), n_threads=threads)
+    sw = capi.Stopwatch(ctx)
+    rec = stages.seqs_record(rank * reads.n, bases, read_off)
+
+    def step_e2e():
+        return hp.run(rec)
+
+    def step_resident():
+        # reads already in HBM (both device stages keep the bases of their previous submit)
+        s2, s4 = hp.s2.batch, hp.s4.batch
+        s2.rerun()
+        intv, intv_off, t1 = s2.collect()
+        pos, pos_off, t2 = s2.seed_positions()
+        t = time.perf_counter()
+        chains, seeds, chain_off = capi.chain_build(hp.hop.l_pac, ctg_off, ctg_len, read_off, intv, intv_off, pos, pos_off,
+                                                    n_threads=threads)
+        t_chain = (time.perf_counter() - t) * 1e3
+        regrown = hp.s4._fit(len(chains), len(seeds))
+        hp.s4.batch.submit(bases if regrown else None, read_off, chains, chain_off, seeds)
+        regs, reg_off, t3 = hp.s4.batch.collect()
+        return {"smem": t1, "seedpos": t2, "chain_ms": t_chain, "c2a": t3, "n_regs": len(regs), "n_intv": len(intv), "n_pos": len(pos),
+                "n_chains": len(chains), "n_seeds": len(seeds)}
+
+    out = step_e2e()                       # first touch: allocations, local-memory setup, capacity growth
+    n_regs = len(out["alnreg"])
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local)
+    barrier(world)
+    clocks.start()
+    sw.start()
+    parts = []
+    for _ in range(args.steps):
+        parts.append(step_resident())
+    ms_res = sw.stop()
+    barrier(world)
+    ms_res = barrier_max(ms_res, world)
+    # e2e leg
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier(world)
+    sw.start()
+    for _ in range(args.steps):
+        step_e2e()
+    ms_e2e = sw.stop()
+    clk = clocks.stop()
+    barrier(world)
+    ms_e2e = barrier_max(ms_e2e, world)
+
+    total_pairs = n_pairs * world
+    ms_step = ms_res / args.steps
+    value = total_pairs / (ms_step * 1e-3)
+    e2e_val = total_pairs / (ms_e2e / args.steps * 1e-3)
+    if rank != 0:
+        return
+    # per-kernel means over the timed steps (CUDA events on each batch's stream)
+    k_smem = float(np.mean([p["smem"].kernel_ms for p in parts]))
+    k_pos = float(np.mean([p["seedpos"].kernel_ms for p in parts]))
+    k_c2a = float(np.mean([p["c2a"].kernel_ms for p in parts]))
+    t_chain = float(np.mean([p["chain_ms"] for p in parts]))
+    blocks_smem = parts[-1]["smem"].work_units
+    blocks_pos = parts[-1]["seedpos"].work_units
+    cells = parts[-1]["c2a"].work_units
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    smem_gbs = blocks_smem * 64 / (k_smem * 1e-3) / 1e9
+    roofline = {"kernel": "smem_kernel", "bound": "hbm", "achieved": smem_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": smem_gbs / hbm_peak,
+                "traffic": traffic.get("smem_kernel"), "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback",
+                "algorithmic_bytes_per_launch": blocks_smem * 64, "kernel_ms": k_smem, "share_of_step": k_smem / ms_step}
+    dpx16, dpx32 = ctx.dpx_peak()
+    gcups = cells / (k_c2a * 1e-3) / 1e9
+    peak_gcups = dpx16 / 5.0 / 1e9
+    roofline_ext = {"kernel": "c2a_kernel", "bound": "int-alu/dpx", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": gcups / peak_gcups,
+                    "cells_per_launch": cells, "kernel_ms": k_c2a, "share_of_step": k_c2a / ms_step,
+                    "peak_source": "measured DPX s16x2 issue rate %.3g lane-instr/s / 5 lane-instr per cell (SURVEY 8d); s32 rate %.3g" % (dpx16, dpx32)}
+    h2d = int(bases.nbytes + read_off.nbytes)
+    d2h = int(n_regs * 88 + (reads.n + 1) * 8)
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": workload, "clocks": clk,
+            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(args.steps * (parts[-1]["smem"].n_launches + parts[-1]["seedpos"].n_launches + parts[-1]["c2a"].n_launches)),
+            "roofline": roofline, "roofline_ext": roofline_ext,
+            "breakdown_ms": {"smem_kernel": k_smem, "seedpos_kernel": k_pos, "host_chaining": t_chain, "c2a_kernels": k_c2a,
+                             "step": ms_step, "e2e_step": ms_e2e / args.steps, "index_build_s": t_index},
+            "counts": {k: parts[-1][k] for k in ("n_intv", "n_pos", "n_chains", "n_seeds", "n_regs")},
+            "seedpos_gbs": blocks_pos * 64 / (k_pos * 1e-3) / 1e9 if k_pos > 0 else None}
+    if world == 1 and not args.no_cpu_baseline:
+        sample = args.cpu_sample_pairs or min(n_pairs, 50_000)
+        R, one_pass, cores = run_reference_cpu(args, ref, reads, sample, built=built)
+        sec = one_pass()
+        line["cpu_baseline"] = {"value": sample / sec, "unit": "pairs/s", "cores": cores, "kind": "reference",
+                                "sample": "%d pairs, stages 2+4 of the compiled reference (oracle/_ref: bwa/*.c + src/bwa_wrapper.cpp), "
+                                          "one thread per core, %.1f s" % (sample, sec)}
+    print(json.dumps(line))
+    hp.close()
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -92,6 +92,16 @@ def lib():
             L.bwaflow_smem_rerun.argtypes = [C.c_void_p]
             L.bwaflow_smem_seed_positions.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Timing)]
             L.bwaflow_sa_lookup.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.bwaflow_stopwatch_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.bwaflow_stopwatch_start.argtypes = [C.c_void_p]
+        L.bwaflow_stopwatch_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.bwaflow_stopwatch_destroy.argtypes = [C.c_void_p]
+        L.bwaflow_ctx_sync.argtypes = [C.c_void_p]
+        L.bwaflow_dpx_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.bwaflow_index_build.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.bwaflow_built_index_view.restype = C.POINTER(Index)
+        L.bwaflow_built_index_view.argtypes = [C.c_void_p]
+        L.bwaflow_built_index_free.argtypes = [C.c_void_p]
         L.bwaflow_chain_opt_default.argtypes = [C.POINTER(ChainOpt)]
         L.bwaflow_chain_build.argtypes = [C.POINTER(ChainOpt), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
@@ -172,6 +182,12 @@ class Context:
             self.L.bwaflow_ctx_destroy(self.h)
             self.h = C.c_void_p()
 
+    def dpx_peak(self):
+        """(packed s16x2, scalar s32) DPX lane-instructions per second, measured."""
+        a, b = C.c_double(), C.c_double()
+        check(self.L.bwaflow_dpx_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def sa_lookup(self, k):
         k = np.ascontiguousarray(k, dtype=np.uint64)
         out = np.zeros(len(k), dtype=np.uint64)
@@ -241,7 +257,8 @@ class C2ABatch:
         chain_off = np.ascontiguousarray(chain_off, dtype=np.int64)
         self._keep = (bases, read_off, chains, chain_off, seeds)
         self.n = len(read_off) - 1
-        check(self.L.bwaflow_c2a_submit(self.h, self.n, _p(bases), _p(read_off), _p(chains), _p(chain_off), _p(seeds), len(seeds)))
+        check(self.L.bwaflow_c2a_submit(self.h, self.n, _p(bases) if bases is not None else None, _p(read_off), _p(chains),
+                                        _p(chain_off), _p(seeds), len(seeds)))
 
     def rerun(self):
         check(self.L.bwaflow_c2a_rerun(self.h))
@@ -329,3 +346,56 @@ def chain_build(l_pac, ctg_off, ctg_len, read_off, intv, intv_off, pos, pos_off,
     off = _view(co.value, len(read_off), np.dtype("<i8")).copy()
     L.bwaflow_chain_result_free(res)
     return chains, seeds, off
+
+
+class BuiltIndex:
+    """FM-index of a synthetic reference built by the library (same arrays as `bwa index` + bwa_idx_load)."""
+
+    def __init__(self, codes, contig_len, n_threads=0):
+        self.L = lib()
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        cl = np.ascontiguousarray(contig_len, dtype=np.int64)
+        self.h = C.c_void_p()
+        check(self.L.bwaflow_index_build(_p(codes), len(codes), len(cl), _p(cl), int(n_threads), C.byref(self.h)))
+        self.view = self.L.bwaflow_built_index_view(self.h).contents
+        self.ctg_off = np.concatenate([[0], np.cumsum(cl)])[:-1].astype(np.int64)
+        self.ctg_len = cl.astype(np.int32)
+
+    def index(self):
+        return self.view
+
+    def bwt_array(self):
+        return np.frombuffer((C.c_uint32 * self.view.bwt_size).from_address(self.view.bwt), dtype=np.uint32)
+
+    def sa_array(self):
+        return np.frombuffer((C.c_uint64 * self.view.n_sa).from_address(self.view.sa), dtype=np.uint64)
+
+    def pac_array(self):
+        return np.frombuffer((C.c_uint8 * (self.view.l_pac // 4 + 1)).from_address(self.view.pac), dtype=np.uint8)
+
+    def close(self):
+        if self.h:
+            self.L.bwaflow_built_index_free(self.h)
+            self.h = C.c_void_p()
+
+
+class Stopwatch:
+    """CUDA-event stopwatch on the context's device (bwaflow_stopwatch_*)."""
+
+    def __init__(self, ctx: Context):
+        self.L = ctx.L
+        self.h = C.c_void_p()
+        check(self.L.bwaflow_stopwatch_create(ctx.h, C.byref(self.h)))
+
+    def start(self):
+        check(self.L.bwaflow_stopwatch_start(self.h))
+
+    def stop(self):
+        ms = C.c_float()
+        check(self.L.bwaflow_stopwatch_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.h:
+            self.L.bwaflow_stopwatch_destroy(self.h)
+            self.h = C.c_void_p()

@@ -525,7 +525,7 @@ int bwaflow_c2a_submit(bwaflow_c2a_batch_t *b, int64_t n_reads, const uint8_t *b
                        const bwaflow_chain_t *chains, const int64_t *chain_off,
                        const bwaflow_seed_t *seeds, int64_t n_seeds)
 {
-  BF_REQUIRE(b && (n_reads == 0 || (bases && read_off && chain_off)), -22, "bwaflow_c2a_submit: null argument");
+  BF_REQUIRE(b && (n_reads == 0 || (read_off && chain_off)), -22, "bwaflow_c2a_submit: null argument");
   const int64_t n_bases = n_reads ? read_off[n_reads] : 0, n_chains = n_reads ? chain_off[n_reads] : 0;
   BF_REQUIRE(n_reads >= 0 && n_reads <= b->max_reads && n_bases <= b->max_bases && n_chains <= b->max_chains && n_seeds <= b->max_seeds, -7,
              "bwaflow_c2a_submit: batch capacity exceeded (%lld reads, %lld bases, %lld chains, %lld seeds)",
@@ -543,8 +543,10 @@ int bwaflow_c2a_submit(bwaflow_c2a_batch_t *b, int64_t n_reads, const uint8_t *b
   cudaStream_t st = b->stream;
   BF_CUDA(cudaEventRecord(b->tm.ev[0], st));
   if (n_reads) {
-    BF_CUDA(cudaMemcpyAsync(b->d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
-    BF_CUDA(cudaMemcpyAsync(b->d_read_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (bases) {   // bases == NULL: the reads of the previous submit are still resident and are reused
+      BF_CUDA(cudaMemcpyAsync(b->d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
+      BF_CUDA(cudaMemcpyAsync(b->d_read_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    }
     BF_CUDA(cudaMemcpyAsync(b->d_chain_off, chain_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n_chains) BF_CUDA(cudaMemcpyAsync(b->d_chains, chains, n_chains * sizeof(bwaflow_chain_t), cudaMemcpyHostToDevice, st));
     if (n_seeds) BF_CUDA(cudaMemcpyAsync(b->d_seeds, seeds, n_seeds * sizeof(bwaflow_seed_t), cudaMemcpyHostToDevice, st));

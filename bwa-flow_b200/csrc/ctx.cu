@@ -35,7 +35,56 @@ void fill_score(const bwaflow_opt_t &o, DevScore &s)
 
 using namespace bwaflow;
 
+// dependency-free DPX issue-rate probe: 8 independent accumulator chains per thread
+template <int PACKED>
+__global__ void dpx_peak_kernel(unsigned *out, int iters, unsigned seed)
+{
+  unsigned a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u, a4 = a0 * 11u, a5 = a0 * 13u, a6 = a0 * 17u, a7 = a0 * 19u;
+  const unsigned b = seed * 2654435761u, c = seed ^ 0x01010101u;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (PACKED) {
+        a0 = __vimax3_s16x2(a0, b, c); a1 = __viaddmax_s16x2_relu(a1, b, c); a2 = __vimax3_s16x2(a2, b, c); a3 = __viaddmax_s16x2_relu(a3, b, c);
+        a4 = __vimax3_s16x2(a4, b, c); a5 = __viaddmax_s16x2_relu(a5, b, c); a6 = __vimax3_s16x2(a6, b, c); a7 = __viaddmax_s16x2_relu(a7, b, c);
+      } else {
+        a0 = __vimax3_s32(a0, b, c); a1 = __viaddmax_s32_relu(a1, b, c); a2 = __vimax3_s32(a2, b, c); a3 = __viaddmax_s32_relu(a3, b, c);
+        a4 = __vimax3_s32(a4, b, c); a5 = __viaddmax_s32_relu(a5, b, c); a6 = __vimax3_s32(a6, b, c); a7 = __viaddmax_s32_relu(a7, b, c);
+      }
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
 extern "C" {
+
+int bwaflow_dpx_peak(bwaflow_ctx_t *ctx, double *packed, double *scalar)
+{
+  BF_REQUIRE(ctx, -22, "bwaflow_dpx_peak: null context");
+  BF_CUDA(cudaSetDevice(ctx->device));
+  const int threads = 256, blocks = ctx->n_sm * 8, iters = 4096;
+  unsigned *d = 0;
+  BF_CUDA(cudaMalloc(&d, (size_t)threads * blocks * 4));
+  cudaEvent_t e0, e1;
+  BF_CUDA(cudaEventCreate(&e0)); BF_CUDA(cudaEventCreate(&e1));
+  for (int mode = 0; mode < 2; ++mode) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      BF_CUDA(cudaEventRecord(e0, 0));
+      if (mode == 0) dpx_peak_kernel<1><<<blocks, threads>>>(d, iters, 12345u + rep);
+      else dpx_peak_kernel<0><<<blocks, threads>>>(d, iters, 12345u + rep);
+      BF_CUDA(cudaEventRecord(e1, 0));
+      BF_CUDA(cudaEventSynchronize(e1));
+      float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+      if (rep > 0 && ms < best) best = ms;
+    }
+    const double ops = (double)threads * blocks * iters * 64.0 / (best * 1e-3);
+    if (mode == 0) { if (packed) *packed = ops; } else if (scalar) *scalar = ops;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  BF_CUDA(cudaGetLastError());
+  return 0;
+}
 
 const char *bwaflow_last_error(void) { return g_err; }
 
@@ -126,6 +175,47 @@ int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt
     c->has_index = true;
   }
   *out = c;
+  return 0;
+}
+
+struct bwaflow_stopwatch { int device; cudaEvent_t a, b; };
+
+int bwaflow_stopwatch_create(bwaflow_ctx_t *ctx, bwaflow_stopwatch_t **out)
+{
+  BF_REQUIRE(ctx && out, -22, "bwaflow_stopwatch_create: null argument");
+  BF_CUDA(cudaSetDevice(ctx->device));
+  bwaflow_stopwatch *w = (bwaflow_stopwatch *)calloc(1, sizeof(*w));
+  w->device = ctx->device;
+  BF_CUDA(cudaEventCreate(&w->a)); BF_CUDA(cudaEventCreate(&w->b));
+  *out = w;
+  return 0;
+}
+int bwaflow_stopwatch_start(bwaflow_stopwatch_t *w)
+{
+  BF_CUDA(cudaSetDevice(w->device));
+  BF_CUDA(cudaDeviceSynchronize());
+  BF_CUDA(cudaEventRecord(w->a, 0));
+  return 0;
+}
+int bwaflow_stopwatch_stop(bwaflow_stopwatch_t *w, float *ms)
+{
+  BF_CUDA(cudaSetDevice(w->device));
+  BF_CUDA(cudaDeviceSynchronize());
+  BF_CUDA(cudaEventRecord(w->b, 0));
+  BF_CUDA(cudaEventSynchronize(w->b));
+  BF_CUDA(cudaEventElapsedTime(ms, w->a, w->b));
+  return 0;
+}
+void bwaflow_stopwatch_destroy(bwaflow_stopwatch_t *w)
+{
+  if (!w) return;
+  cudaEventDestroy(w->a); cudaEventDestroy(w->b); free(w);
+}
+int bwaflow_ctx_sync(bwaflow_ctx_t *ctx)
+{
+  BF_REQUIRE(ctx, -22, "bwaflow_ctx_sync: null context");
+  BF_CUDA(cudaSetDevice(ctx->device));
+  BF_CUDA(cudaDeviceSynchronize());
   return 0;
 }
 

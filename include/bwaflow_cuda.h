@@ -89,6 +89,17 @@ int bwaflow_ctx_set_opt(bwaflow_ctx_t *ctx, const bwaflow_opt_t *opt);
 void *bwaflow_host_alloc(uint64_t bytes);
 void bwaflow_host_free(void *p);
 
+/* device-side stopwatch (CUDA events on the context's device) for callers that time whole steps */
+typedef struct bwaflow_stopwatch bwaflow_stopwatch_t;
+int bwaflow_stopwatch_create(bwaflow_ctx_t *ctx, bwaflow_stopwatch_t **out);
+int bwaflow_stopwatch_start(bwaflow_stopwatch_t *w);          /* device sync + event record */
+int bwaflow_stopwatch_stop(bwaflow_stopwatch_t *w, float *ms); /* device sync + event record + elapsed */
+void bwaflow_stopwatch_destroy(bwaflow_stopwatch_t *w);
+int bwaflow_ctx_sync(bwaflow_ctx_t *ctx);
+/* Measured integer peak for the extension roofline: chip-wide issue rate of dependency-free packed
+ * DPX instructions (VIMNMX3.S16x2 / VIADDMNMX.S16x2.RELU), in lane-instructions per second, and of their 32-bit forms. */
+int bwaflow_dpx_peak(bwaflow_ctx_t *ctx, double *s16x2_lane_ops_per_s, double *s32_lane_ops_per_s);
+
 /* ---- extension jobs: one ksw_extend2 each (replaces the per-seed SW stream of SWTask, src/fpga/SWTask.h) */
 
 int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_qbytes, int64_t max_tbytes,
@@ -111,7 +122,8 @@ int bwaflow_c2a_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_
                              int64_t max_seeds, bwaflow_c2a_batch_t **out);
 void bwaflow_c2a_batch_destroy(bwaflow_c2a_batch_t *b);
 /* bases = nt4 codes of all reads concatenated (bseq1_t::seq after src/bwa_wrapper.cpp:124-125);
- * read_off[n_reads+1]; chains of read r = chains[chain_off[r] .. chain_off[r+1]) in mem_chain_v order. */
+ * read_off[n_reads+1]; chains of read r = chains[chain_off[r] .. chain_off[r+1]) in mem_chain_v order.
+ * bases may be NULL to reuse the reads already resident from the previous submit (same read_off). */
 int bwaflow_c2a_submit(bwaflow_c2a_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off,
                        const bwaflow_chain_t *chains, const int64_t *chain_off,
                        const bwaflow_seed_t *seeds, int64_t n_seeds);
@@ -161,6 +173,14 @@ int bwaflow_chain_build(const bwaflow_chain_opt_t *opt, int64_t l_pac, int32_t n
 void bwaflow_chain_result_view(const bwaflow_chain_result_t *r, const bwaflow_chain_t **chains, int64_t *n_chains,
                                const bwaflow_seed_t **seeds, int64_t *n_seeds, const int64_t **chain_off);
 void bwaflow_chain_result_free(bwaflow_chain_result_t *r);
+
+/* ---- index construction for synthetic references (workload preparation; the arrays equal what `bwa index`
+ *      + bwa_idx_load leave in memory, bwa/bwtindex.c:256-324).  codes: 0..3 = ACGT, >=4 = N, contigs concatenated. */
+typedef struct bwaflow_built_index bwaflow_built_index_t;
+int bwaflow_index_build(const uint8_t *codes, int64_t n_bases, int32_t n_contigs, const int64_t *contig_len,
+                        int n_threads /* <1: all cores */, bwaflow_built_index_t **out);
+const bwaflow_index_t *bwaflow_built_index_view(const bwaflow_built_index_t *b);
+void bwaflow_built_index_free(bwaflow_built_index_t *b);
 
 #ifdef __cplusplus
 }

@@ -370,3 +370,42 @@ def orc_ksw_extend2(query, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus
     out = np.zeros(6, dtype=np.int32)
     orc_lib().orc_ksw_extend2(len(q), _p(q), len(t), _p(t), _p(m), o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, _p(out))
     return out
+
+
+def write_index_files(prefix, primary, L2, seq_len, bwt, sa, sa_intv, pac, l_pac, names, ctg_len, codes=None):
+    """Write bwa's on-disk index (.bwt .sa .pac .ann .amb; formats of bwt_dump_bwt/bwt_dump_sa bwa/bwt.c:385-407,
+    bns_dump bwa/bntseq.c:66-97, .pac trailer bwa/bntseq.c:309-318) from in-memory arrays, so that the compiled reference
+    can bwa_idx_load an index it did not have to rebuild.  `codes` (0..4 per base) adds the N holes to .amb/.ann."""
+    L2 = [int(x) for x in L2]
+    with open(prefix + ".bwt", "wb") as f:
+        np.array([primary] + L2[1:5], dtype="<u8").tofile(f)
+        np.ascontiguousarray(bwt, dtype="<u4").tofile(f)
+    with open(prefix + ".sa", "wb") as f:
+        np.array([primary] + L2[1:5] + [sa_intv, seq_len], dtype="<u8").tofile(f)
+        np.ascontiguousarray(sa, dtype="<u8")[1:].tofile(f)
+    with open(prefix + ".pac", "wb") as f:
+        n = l_pac // 4 + (1 if l_pac % 4 else 0)
+        np.ascontiguousarray(pac, dtype=np.uint8)[:n].tofile(f)
+        if l_pac % 4 == 0:
+            f.write(b"\0")
+        f.write(bytes([l_pac % 4]))
+    offs = np.concatenate([[0], np.cumsum(ctg_len)])
+    holes = []
+    if codes is not None:
+        isn = np.concatenate([[0], (np.asarray(codes) > 3).astype(np.int8), [0]])
+        d = np.diff(isn)
+        starts, ends = np.nonzero(d == 1)[0], np.nonzero(d == -1)[0]
+        for s, e in zip(starts, ends):          # a run never spans contigs in bwa (lasts resets per sequence)
+            cuts = [s] + [int(o) for o in offs[1:-1] if s < o < e] + [e]
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                holes.append((int(a), int(b - a)))
+    with open(prefix + ".ann", "w") as f:
+        f.write("%d %d %u\n" % (l_pac, len(names), 11))
+        for i, nm in enumerate(names):
+            f.write("0 %s\n" % nm)
+            na = sum(1 for h in holes if offs[i] <= h[0] < offs[i + 1])
+            f.write("%d %d %d\n" % (offs[i], ctg_len[i], na))
+    with open(prefix + ".amb", "w") as f:
+        f.write("%d %d %u\n" % (l_pac, len(names), len(holes)))
+        for o, ln in holes:
+            f.write("%d %d N\n" % (o, ln))
