@@ -51,6 +51,15 @@ class Timing(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
 
 
+class HotTiming(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("h2d_ms", "smem_ms", "seedpos_ms", "chain_ms", "c2a_ms", "d2h_ms", "total_ms")] + \
+               [("n_launches", C.c_int32), ("smem_blocks", C.c_double), ("seedpos_blocks", C.c_double), ("cells", C.c_double)] + \
+               [(k, C.c_int64) for k in ("n_intv", "n_pos", "n_chains", "n_seeds")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class BwaflowError(RuntimeError):
     pass
 
@@ -92,6 +101,11 @@ def lib():
             L.bwaflow_smem_rerun.argtypes = [C.c_void_p]
             L.bwaflow_smem_seed_positions.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Timing)]
             L.bwaflow_sa_lookup.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.bwaflow_hot_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ChainOpt), C.c_void_p, C.POINTER(C.c_void_p)]
+        L.bwaflow_hot_batch_destroy.argtypes = [C.c_void_p]
+        L.bwaflow_hot_submit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.bwaflow_hot_rerun.argtypes = [C.c_void_p]
+        L.bwaflow_hot_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(HotTiming)]
         L.bwaflow_stopwatch_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.bwaflow_stopwatch_start.argtypes = [C.c_void_p]
         L.bwaflow_stopwatch_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -398,4 +412,38 @@ class Stopwatch:
     def close(self):
         if self.h:
             self.L.bwaflow_stopwatch_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class HotBatch:
+    """Fused reads -> regions batch (bwaflow_hot_*): every intermediate stays in HBM."""
+
+    def __init__(self, ctx: Context, max_reads, max_bases, chain_opt: ChainOpt | None = None, ctg_alt=None):
+        self.L = ctx.L
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        alt = np.ascontiguousarray(ctg_alt, dtype=np.int32) if ctg_alt is not None else None
+        check(self.L.bwaflow_hot_batch_create(ctx.h, max_reads, max_bases, C.byref(chain_opt) if chain_opt is not None else None,
+                                              _p(alt) if alt is not None else None, C.byref(self.h)))
+        self.n = 0
+
+    def submit(self, bases, read_off):
+        read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        self._keep = (bases, read_off)
+        self.n = len(read_off) - 1
+        check(self.L.bwaflow_hot_submit(self.h, self.n, _p(bases), _p(read_off)))
+
+    def rerun(self):
+        check(self.L.bwaflow_hot_rerun(self.h))
+
+    def collect(self):
+        regs, off = C.c_void_p(), C.c_void_p()
+        n = C.c_int64()
+        t = HotTiming()
+        check(self.L.bwaflow_hot_collect(self.h, C.byref(regs), C.byref(off), C.byref(n), C.byref(t)))
+        return _view(regs.value, n.value, ALNREG), _view(off.value, self.n + 1, np.dtype("<i8")), t
+
+    def close(self):
+        if self.h:
+            self.L.bwaflow_hot_batch_destroy(self.h)
             self.h = C.c_void_p()

@@ -1,0 +1,56 @@
+// Batch objects of the device stages (shared by smem.cu, chain2aln.cu, chain_dev.cu and hotpath.cu).
+#pragma once
+#include "internal.cuh"
+
+namespace bwaflow {
+constexpr int C2A_NCLASS = 8;
+}
+
+struct bwaflow_smem_batch {
+  bwaflow_ctx_t *ctx;
+  cudaStream_t stream;
+  bwaflow::Timer tm;
+  int64_t max_reads, max_bases, n_reads, max_len;
+  uint8_t *d_bases; int64_t *d_read_off;
+  bwaflow_intv_t *d_slots; int cap; int64_t slots_cap;
+  int *d_counts; int64_t *d_cnt64, *d_off, *h_off;
+  bwaflow_intv_t *d_out, *h_out; int64_t out_cap;
+  int *d_ctl, *h_ctl;               // head | overflow | too-long | pad | blocks(u64)
+  void *d_tmp; size_t tmp_bytes;
+  int64_t n_intv;
+  // seed positions
+  int64_t *d_pcnt, *d_poff, *h_poff, *d_pos, *h_pos; int64_t pos_cap, hpos_cap;
+  int blocks_per_launch;
+  bool pending;
+};
+
+struct bwaflow_c2a_batch {
+  bwaflow_ctx_t *ctx;
+  cudaStream_t stream, own_stream;   // own_stream: saved while the fused hot path runs this batch on its stream
+  bwaflow::Timer tm;
+  int64_t max_reads, max_bases, max_chains, max_seeds;
+  int64_t n_reads, n_chains, n_seeds;   // n_seeds = sum of chains[].n_seeds (seeds actually referenced)
+  uint8_t *d_bases; int64_t *d_read_off, *d_chain_off;
+  bwaflow_chain_t *d_chains; bwaflow_seed_t *d_seeds, *d_sseeds;
+  int64_t *d_nseeds, *d_sbase, *d_chain_read, *d_win;
+  uint64_t *d_skeys[2]; uint32_t *d_svals[2];
+  uint32_t *d_rkeys[2], *d_rvals[2];
+  void *d_tmp; size_t tmp_bytes;
+  uint8_t *d_skipped;
+  bwaflow_alnreg_t *d_regs, *d_regs_out, *h_regs;
+  int *d_nregs; int64_t *d_nregs64, *d_reg_off, *h_reg_off;
+  int *d_ctl, *h_ctl;               // hist[8] | queue[16] | err | pad | cells(u64)
+  int blocks[bwaflow::C2A_NCLASS];
+  int refill;
+  bool pending;
+};
+
+namespace bwaflow {
+// smem.cu: device-side halves of submit/collect (no interval D2H); used by the fused hot path
+int smem_launch(bwaflow_smem_batch *b);
+int smem_finish_device(bwaflow_smem_batch *b);                 // waits, regrows slots on overflow, compacts into d_out/d_off; sets n_intv
+int smem_seedpos_device(bwaflow_smem_batch *b, int64_t *total); // d_pos/d_poff for the current intervals
+// chain2aln.cu
+int c2a_launch(bwaflow_c2a_batch *b);
+int c2a_finish_queue(bwaflow_c2a_batch *b);
+} // namespace bwaflow

@@ -21,10 +21,10 @@
 #include <stdlib.h>
 #include "internal.cuh"
 #include "ksw_lane.cuh"
+#include "batches.cuh"
 
 namespace bwaflow {
 
-constexpr int C2A_NCLASS = 8;
 __constant__ int c_c2a_qmax[C2A_NCLASS] = {31, 63, 95, 127, 159, 255, 511, 1023};
 static const int h_c2a_qmax[C2A_NCLASS] = {31, 63, 95, 127, 159, 255, 511, 1023};
 static const int h_c2a_threads[C2A_NCLASS] = {64, 64, 64, 64, 64, 64, 64, 32};
@@ -347,30 +347,10 @@ __global__ void c2a_widen(const int *n_regs, int64_t n, int64_t *out)
 
 using namespace bwaflow;
 
-struct bwaflow_c2a_batch {
-  bwaflow_ctx_t *ctx;
-  cudaStream_t stream;
-  Timer tm;
-  int64_t max_reads, max_bases, max_chains, max_seeds;
-  int64_t n_reads, n_chains, n_seeds;   // n_seeds = sum of chains[].n_seeds (seeds actually referenced)
-  uint8_t *d_bases; int64_t *d_read_off, *d_chain_off;
-  bwaflow_chain_t *d_chains; bwaflow_seed_t *d_seeds, *d_sseeds;
-  int64_t *d_nseeds, *d_sbase, *d_chain_read, *d_win;
-  uint64_t *d_skeys[2]; uint32_t *d_svals[2];
-  uint32_t *d_rkeys[2], *d_rvals[2];
-  void *d_tmp; size_t tmp_bytes;
-  uint8_t *d_skipped;
-  bwaflow_alnreg_t *d_regs, *d_regs_out, *h_regs;
-  int *d_nregs; int64_t *d_nregs64, *d_reg_off, *h_reg_off;
-  int *d_ctl, *h_ctl;               // hist[8] | queue[16] | err | pad | cells(u64)
-  int blocks[C2A_NCLASS];
-  int refill;
-  bool pending;
-};
 
 static size_t max3(size_t a, size_t b, size_t c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 
-static int c2a_launch(bwaflow_c2a_batch *b)
+int bwaflow::c2a_launch(bwaflow_c2a_batch *b)
 {
   const int64_t nr = b->n_reads, nc = b->n_chains, ns = b->n_seeds;
   cudaStream_t st = b->stream;
@@ -422,6 +402,15 @@ static int c2a_launch(bwaflow_c2a_batch *b)
   BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_nregs64, b->d_reg_off, (int)(nr + 1), st));
   c2a_compact<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(b->d_chain_off, b->d_sbase, b->d_nregs, b->d_reg_off, nr, b->d_regs, b->d_regs_out);
   BF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bwaflow::c2a_finish_queue(bwaflow_c2a_batch *b)
+{
+  BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_reg_off, b->d_reg_off, (b->n_reads + 1) * 8, cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_ctl, b->d_ctl + 3 * C2A_NCLASS, 4 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  b->pending = true;
   return 0;
 }
 
@@ -512,14 +501,6 @@ void bwaflow_c2a_batch_destroy(bwaflow_c2a_batch_t *b)
   free(b);
 }
 
-static int c2a_finish_queue(bwaflow_c2a_batch *b)
-{
-  BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
-  BF_CUDA(cudaMemcpyAsync(b->h_reg_off, b->d_reg_off, (b->n_reads + 1) * 8, cudaMemcpyDeviceToHost, b->stream));
-  BF_CUDA(cudaMemcpyAsync(b->h_ctl, b->d_ctl + 3 * C2A_NCLASS, 4 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-  b->pending = true;
-  return 0;
-}
 
 int bwaflow_c2a_submit(bwaflow_c2a_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off,
                        const bwaflow_chain_t *chains, const int64_t *chain_off,

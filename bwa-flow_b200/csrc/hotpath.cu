@@ -1,0 +1,304 @@
+// Fused hot path: reads -> alignment regions with every intermediate resident in HBM.
+//   stage 2   smem_kernel + seedpos_kernel                         (smem.cu)
+//   chaining  chain_kernel: mem_chain_postprocess + mem_chain_flt  (chain_core.h, one read per thread)
+//   stage 4   c2a_kernel                                            (chain2aln.cu)
+// In kflow terms this is SeqsToChainsCUDA producing tag=1 records whose chains stay on the device, ChainsPipe passing
+// them through (src/Pipeline.cpp:409), and ChainsToRegionsCUDA consuming them.  Only the reads go
+// up and only the regions come down; the host sees three tiny size read-backs per batch.
+#include <cub/device/device_scan.cuh>
+#include <string.h>
+#include <stdlib.h>
+#include "internal.cuh"
+#include "batches.cuh"
+#include "chain_core.h"
+
+namespace bwaflow {
+
+using namespace chain;
+
+struct ChainArgs {
+  int64_t n_reads; const int64_t *read_off;
+  const bwaflow_intv_t *intv; const int64_t *intv_off; const int64_t *pos; const int64_t *pos_off;
+  // per-read scratch, carved by the read's first position index
+  SeedNode *seeds; Chain *chains; Chain *sorted; int *order; int *kept; Node *nodes;
+  int64_t *n_chains, *n_seeds; float *frac_rep; int *err;
+  bwaflow_chain_opt_t opt; Ctg ctg;
+};
+
+__device__ __forceinline__ Scratch read_scratch(const ChainArgs &a, int64_t r)
+{
+  const int64_t pbase = a.pos_off[a.intv_off[r]], e = pbase + r;       // P_r + 1 entries per read
+  Scratch S;
+  S.seeds = a.seeds + e; S.chains = a.chains + e; S.sorted = a.sorted + e; S.order = a.order + e; S.kept = a.kept + e;
+  S.nodes = a.nodes + (pbase / 4 + 4 * r);
+  S.n_seeds = S.n_chains = S.n_nodes = 0; S.root = 0;
+  return S;
+}
+
+__global__ void __launch_bounds__(128) chain_kernel(const ChainArgs a)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n_reads) return;
+  const int len = (int)(a.read_off[r + 1] - a.read_off[r]);
+  if (len >= a.opt.min_seed_len && needs_seed_rescoring(a.opt, len)) { atomicExch(a.err, 1); a.n_chains[r] = 0; a.n_seeds[r] = 0; return; }
+  Scratch S = read_scratch(a, r);
+  const int64_t i0 = a.intv_off[r], i1 = a.intv_off[r + 1];
+  float fr;
+  const int n = chain_read(S, a.opt, a.ctg, len, a.intv + i0, i1 - i0, a.pos, a.pos_off + i0, &fr);
+  int ns = 0;
+  for (int c = 0; c < n; ++c) ns += S.sorted[c].n;
+  a.n_chains[r] = n; a.n_seeds[r] = ns; a.frac_rep[r] = fr;
+}
+
+// second pass: flat chains/seeds in the layout stage 4 takes (chains of read r at chain_off[r], seeds contiguous per chain)
+__global__ void __launch_bounds__(128) chain_emit_kernel(const ChainArgs a, const int64_t *chain_off, const int64_t *seed_off,
+                                                         bwaflow_chain_t *chains, bwaflow_seed_t *seeds)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n_reads) return;
+  const Scratch S = read_scratch(a, r);
+  const int n = (int)a.n_chains[r];
+  int64_t so = seed_off[r];
+  const float fr = a.frac_rep[r];
+  for (int c = 0; c < n; ++c) {
+    const Chain ch = S.sorted[c];
+    bwaflow_chain_t f; f.pos = ch.pos; f.n_seeds = ch.n; f.rid = ch.rid; f.frac_rep = fr;
+    f.flags = (uint32_t)ch.w | (uint32_t)ch.kept << 29 | (uint32_t)ch.is_alt << 31; f.seed_off = so;
+    chains[chain_off[r] + c] = f;
+    for (int j = ch.head; j >= 0; j = S.seeds[j].next) seeds[so++] = S.seeds[j].s;
+  }
+}
+
+__global__ void fill_last_zero(int64_t *a, int64_t n) { if (threadIdx.x == 0 && blockIdx.x == 0) a[n] = 0; }
+
+} // namespace bwaflow
+
+using namespace bwaflow;
+
+struct bwaflow_hot_batch {
+  bwaflow_ctx_t *ctx;
+  bwaflow_smem_batch *s;
+  bwaflow_c2a_batch *c;
+  cudaStream_t stream;
+  cudaEvent_t ev[6];
+  int64_t max_reads, max_bases;
+  // chaining scratch
+  int64_t scr_entries, scr_nodes;
+  chain::SeedNode *d_seeds; chain::Chain *d_chains, *d_sorted; int *d_order, *d_kept; chain::Node *d_nodes;
+  int64_t *d_nch, *d_nsd, *d_choff, *d_sdoff, *h_tot; float *d_frac; int *d_err, *h_err;
+  void *d_tmp; size_t tmp_bytes;
+  int32_t *d_ctg_alt;
+  bwaflow_chain_opt_t copt;
+  int64_t n_intv, n_pos, n_chains, n_seeds;
+  float ms_smem, ms_seedpos, ms_chain, ms_c2a, ms_h2d;
+  double blocks_smem, blocks_pos;
+  bool pending;
+};
+
+static int hot_grow_scratch(bwaflow_hot_batch *b, int64_t entries, int64_t nodes)
+{
+  if (entries > b->scr_entries) {
+    cudaFree(b->d_seeds); cudaFree(b->d_chains); cudaFree(b->d_sorted); cudaFree(b->d_order); cudaFree(b->d_kept);
+    b->scr_entries = entries + entries / 4;
+    BF_CUDA(cudaMalloc(&b->d_seeds, b->scr_entries * sizeof(chain::SeedNode)));
+    BF_CUDA(cudaMalloc(&b->d_chains, b->scr_entries * sizeof(chain::Chain)));
+    BF_CUDA(cudaMalloc(&b->d_sorted, b->scr_entries * sizeof(chain::Chain)));
+    BF_CUDA(cudaMalloc(&b->d_order, b->scr_entries * sizeof(int)));
+    BF_CUDA(cudaMalloc(&b->d_kept, b->scr_entries * sizeof(int)));
+  }
+  if (nodes > b->scr_nodes) {
+    cudaFree(b->d_nodes);
+    b->scr_nodes = nodes + nodes / 4;
+    BF_CUDA(cudaMalloc(&b->d_nodes, b->scr_nodes * sizeof(chain::Node)));
+  }
+  return 0;
+}
+
+// (re)creates the stage-4 batch with room for n_chains/n_seeds and points it at the stage-2 batch's resident reads
+static int hot_make_c2a(bwaflow_hot_batch *b, int64_t max_chains, int64_t max_seeds)
+{
+  if (b->c) {
+    b->c->d_bases = nullptr; b->c->d_read_off = nullptr;           // aliases, not owned
+    b->c->stream = b->c->own_stream;
+    bwaflow_c2a_batch_destroy(b->c);
+    b->c = nullptr;
+  }
+  int r = bwaflow_c2a_batch_create(b->ctx, b->max_reads, 16, max_chains, max_seeds, &b->c);
+  if (r) return r;
+  cudaFree(b->c->d_bases); cudaFree(b->c->d_read_off);
+  b->c->d_bases = b->s->d_bases; b->c->d_read_off = b->s->d_read_off;
+  b->c->own_stream = b->c->stream;
+  b->c->stream = b->stream;                                         // everything runs in order on the stage-2 stream
+  return 0;
+}
+
+static int hot_run(bwaflow_hot_batch *b)
+{
+  bwaflow_smem_batch *s = b->s;
+  cudaStream_t st = b->stream;
+  const int64_t nr = s->n_reads;
+  int r;
+  // ---- stage 2
+  BF_CUDA(cudaEventRecord(b->ev[1], st));
+  if ((r = smem_launch(s))) return r;
+  BF_CUDA(cudaMemcpyAsync(s->h_off, s->d_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaMemcpyAsync(s->h_ctl, s->d_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  s->pending = true;
+  if ((r = smem_finish_device(s))) return r;
+  b->blocks_smem = (double)*(unsigned long long *)(s->h_ctl + 4);
+  BF_CUDA(cudaEventRecord(b->ev[2], st));
+  int64_t n_pos = 0;
+  if ((r = smem_seedpos_device(s, &n_pos))) return r;
+  b->n_intv = s->n_intv; b->n_pos = n_pos;
+  BF_CUDA(cudaMemcpyAsync(b->h_tot + 2, s->d_ctl + 4, 8, cudaMemcpyDeviceToHost, st));   // occ blocks touched by the SA walks
+  BF_CUDA(cudaEventRecord(b->ev[3], st));
+  // ---- chaining
+  if ((r = hot_grow_scratch(b, n_pos + nr + 8, n_pos / 4 + 4 * nr + 8))) return r;
+  ChainArgs a;
+  a.n_reads = nr; a.read_off = s->d_read_off; a.intv = s->d_out; a.intv_off = s->d_off; a.pos = s->d_pos; a.pos_off = s->d_poff;
+  a.seeds = b->d_seeds; a.chains = b->d_chains; a.sorted = b->d_sorted; a.order = b->d_order; a.kept = b->d_kept; a.nodes = b->d_nodes;
+  a.n_chains = b->d_nch; a.n_seeds = b->d_nsd; a.frac_rep = b->d_frac; a.err = b->d_err; a.opt = b->copt;
+  a.ctg = chain::Ctg{b->ctx->ix.n_seqs, b->ctx->ix.ctg_offset, b->ctx->ix.ctg_len, b->d_ctg_alt, b->ctx->ix.l_pac};
+  BF_CUDA(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
+  BF_CUDA(cudaMemsetAsync(b->d_choff, 0, (nr + 1) * 8, st));
+  BF_CUDA(cudaMemsetAsync(b->d_sdoff, 0, (nr + 1) * 8, st));
+  if (nr) {
+    const unsigned grid = (unsigned)((nr + 127) / 128);
+    chain_kernel<<<grid, 128, 0, st>>>(a);
+    fill_last_zero<<<1, 1, 0, st>>>(b->d_nch, nr);
+    fill_last_zero<<<1, 1, 0, st>>>(b->d_nsd, nr);
+    size_t tmp = b->tmp_bytes;
+    BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_nch, b->d_choff, (int)(nr + 1), st));
+    tmp = b->tmp_bytes;
+    BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_nsd, b->d_sdoff, (int)(nr + 1), st));
+  }
+  BF_CUDA(cudaMemcpyAsync(b->h_tot, b->d_choff + nr, 8, cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaMemcpyAsync(b->h_tot + 1, b->d_sdoff + nr, 8, cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaStreamSynchronize(st));
+  BF_REQUIRE(!*b->h_err, -34, "read too long for chaining: mem_flt_chained_seeds (bwa/bwamem.c:607) would rescore its seeds");
+  const int64_t n_chains = b->h_tot[0], n_seeds = b->h_tot[1];
+  b->n_chains = n_chains; b->n_seeds = n_seeds;
+  if (!b->c || n_chains > b->c->max_chains || n_seeds > b->c->max_seeds)
+    if ((r = hot_make_c2a(b, n_chains + n_chains / 4 + 1024, n_seeds + n_seeds / 4 + 1024))) return r;
+  bwaflow_c2a_batch *c = b->c;
+  if (nr) {
+    const unsigned grid = (unsigned)((nr + 127) / 128);
+    chain_emit_kernel<<<grid, 128, 0, st>>>(a, b->d_choff, b->d_sdoff, c->d_chains, c->d_seeds);
+    BF_CUDA(cudaMemcpyAsync(c->d_chain_off, b->d_choff, (nr + 1) * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  BF_CUDA(cudaEventRecord(b->ev[4], st));
+  // ---- stage 4 on the resident chains
+  c->n_reads = nr; c->n_chains = n_chains; c->n_seeds = n_seeds;
+  BF_CUDA(cudaEventRecord(c->tm.ev[0], st));
+  BF_CUDA(cudaEventRecord(c->tm.ev[1], st));
+  if ((r = c2a_launch(c))) return r;
+  if ((r = c2a_finish_queue(c))) return r;
+  BF_CUDA(cudaEventRecord(b->ev[5], st));
+  b->pending = true;
+  return 0;
+}
+
+extern "C" {
+
+int bwaflow_hot_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_bases, const bwaflow_chain_opt_t *copt,
+                             const int32_t *ctg_is_alt, bwaflow_hot_batch_t **out)
+{
+  BF_REQUIRE(ctx && out && ctx->has_index, -22, "bwaflow_hot_batch_create: bad argument");
+  BF_CUDA(cudaSetDevice(ctx->device));
+  bwaflow_hot_batch *b = (bwaflow_hot_batch *)calloc(1, sizeof(*b));
+  b->ctx = ctx; b->max_reads = max_reads; b->max_bases = max_bases;
+  if (copt) b->copt = *copt; else bwaflow_chain_opt_default(&b->copt);
+  int r = bwaflow_smem_batch_create(ctx, max_reads, max_bases, &b->s);
+  if (r) return r;
+  b->stream = b->s->stream;
+  for (int i = 0; i < 6; ++i) BF_CUDA(cudaEventCreate(&b->ev[i]));
+  BF_CUDA(cudaMalloc(&b->d_nch, (max_reads + 2) * 8));
+  BF_CUDA(cudaMalloc(&b->d_nsd, (max_reads + 2) * 8));
+  BF_CUDA(cudaMalloc(&b->d_choff, (max_reads + 2) * 8));
+  BF_CUDA(cudaMalloc(&b->d_sdoff, (max_reads + 2) * 8));
+  BF_CUDA(cudaMalloc(&b->d_frac, (max_reads + 2) * 4));
+  BF_CUDA(cudaMalloc(&b->d_err, 16));
+  BF_CUDA(cudaMallocHost(&b->h_tot, 32));
+  BF_CUDA(cudaMallocHost(&b->h_err, 16));
+  BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b->tmp_bytes, b->d_nch, b->d_choff, (int)(max_reads + 1), b->stream));
+  b->tmp_bytes += 256;
+  BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
+  if (ctg_is_alt) {
+    BF_CUDA(cudaMalloc(&b->d_ctg_alt, ctx->ix.n_seqs * 4));
+    BF_CUDA(cudaMemcpy(b->d_ctg_alt, ctg_is_alt, ctx->ix.n_seqs * 4, cudaMemcpyHostToDevice));
+  }
+  if ((r = hot_make_c2a(b, 4 * max_reads + 1024, 12 * max_reads + 1024))) return r;
+  *out = b;
+  return 0;
+}
+
+void bwaflow_hot_batch_destroy(bwaflow_hot_batch_t *b)
+{
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->stream);
+  if (b->c) { b->c->d_bases = nullptr; b->c->d_read_off = nullptr; b->c->stream = b->c->own_stream; bwaflow_c2a_batch_destroy(b->c); }
+  bwaflow_smem_batch_destroy(b->s);
+  cudaFree(b->d_seeds); cudaFree(b->d_chains); cudaFree(b->d_sorted); cudaFree(b->d_order); cudaFree(b->d_kept); cudaFree(b->d_nodes);
+  cudaFree(b->d_nch); cudaFree(b->d_nsd); cudaFree(b->d_choff); cudaFree(b->d_sdoff); cudaFree(b->d_frac); cudaFree(b->d_err);
+  cudaFreeHost(b->h_tot); cudaFreeHost(b->h_err); cudaFree(b->d_tmp); cudaFree(b->d_ctg_alt);
+  for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
+  free(b);
+}
+
+int bwaflow_hot_submit(bwaflow_hot_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off)
+{
+  BF_REQUIRE(b && (n_reads == 0 || (bases && read_off)), -22, "bwaflow_hot_submit: null argument");
+  bwaflow_smem_batch *s = b->s;
+  const int64_t n_bases = n_reads ? read_off[n_reads] : 0;
+  BF_REQUIRE(n_reads >= 0 && n_reads <= s->max_reads && n_bases <= s->max_bases, -7,
+             "bwaflow_hot_submit: batch capacity exceeded (%lld reads, %lld bases)", (long long)n_reads, (long long)n_bases);
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  int64_t max_len = 0;
+  for (int64_t i = 0; i < n_reads; ++i) { const int64_t l = read_off[i + 1] - read_off[i]; max_len = l > max_len ? l : max_len; }
+  BF_REQUIRE(max_len < 1024, -34, "read of %lld bases: the device path supports reads shorter than 1024", (long long)max_len);
+  s->n_reads = n_reads; s->max_len = max_len;
+  BF_CUDA(cudaEventRecord(b->ev[0], b->stream));
+  if (n_reads) {
+    BF_CUDA(cudaMemcpyAsync(s->d_bases, bases, n_bases, cudaMemcpyHostToDevice, b->stream));
+    BF_CUDA(cudaMemcpyAsync(s->d_read_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, b->stream));
+  }
+  return hot_run(b);
+}
+
+int bwaflow_hot_rerun(bwaflow_hot_batch_t *b)
+{
+  BF_REQUIRE(b, -22, "bwaflow_hot_rerun: null batch");
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  BF_CUDA(cudaEventRecord(b->ev[0], b->stream));
+  return hot_run(b);
+}
+
+int bwaflow_hot_collect(bwaflow_hot_batch_t *b, const bwaflow_alnreg_t **regs, const int64_t **reg_off, int64_t *n_regs,
+                        bwaflow_hot_timing_t *t)
+{
+  BF_REQUIRE(b && b->pending, -22, "bwaflow_hot_collect: nothing submitted");
+  bwaflow_timing_t ct;
+  int r = bwaflow_c2a_collect(b->c, regs, reg_off, n_regs, &ct);
+  b->pending = false;
+  if (r) return r;
+  if (t) {
+    memset(t, 0, sizeof(*t));
+    cudaEventElapsedTime(&t->h2d_ms, b->ev[0], b->ev[1]);
+    cudaEventElapsedTime(&t->smem_ms, b->ev[1], b->ev[2]);
+    cudaEventElapsedTime(&t->seedpos_ms, b->ev[2], b->ev[3]);
+    cudaEventElapsedTime(&t->chain_ms, b->ev[3], b->ev[4]);
+    cudaEventElapsedTime(&t->c2a_ms, b->ev[4], b->ev[5]);
+    t->d2h_ms = ct.d2h_ms;
+    cudaEventElapsedTime(&t->total_ms, b->ev[0], b->c->tm.ev[3]);
+    t->smem_blocks = b->blocks_smem;
+    t->seedpos_blocks = (double)(unsigned long long)b->h_tot[2];
+    t->cells = ct.work_units;
+    t->n_intv = b->n_intv; t->n_pos = b->n_pos; t->n_chains = b->n_chains; t->n_seeds = b->n_seeds;
+    t->n_launches = 5 + 3 + 8 + ct.n_launches;
+  }
+  return 0;
+}
+
+} // extern "C"

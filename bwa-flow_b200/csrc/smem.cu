@@ -15,40 +15,59 @@
 #include <string.h>
 #include <stdlib.h>
 #include "internal.cuh"
+#include "batches.cuh"
 
 namespace bwaflow {
 
 struct Intv { uint64_t x0, x1, x2; };
 
-// counts of A,C,G,T among symbols [0, n) of a 64-byte occ block whose symbol words are w0..w3 (u64, MSB first)
-__device__ __forceinline__ void block_count(const uint4 s0, const uint4 s1, int n, uint64_t cnt[4])
+// Among the first n symbols of a 64-byte occ block (symbol words as u64, 32 symbols each, MSB first): how many equal
+// base c (*eq) and how many are greater than c (*gt).  POPC runs on the narrow XU pipe, so the masks of two words
+// (which only use even bit positions) are interleaved into one word before counting: 4 popcounts per call.
+__device__ __forceinline__ void prefix_counts(const uint4 s0, const uint4 s1, int n, int c, int *eq, int *gt)
 {
   const uint64_t W[4] = {(uint64_t)s0.x << 32 | s0.y, (uint64_t)s0.z << 32 | s0.w,
                          (uint64_t)s1.x << 32 | s1.y, (uint64_t)s1.z << 32 | s1.w};
-  int c1 = 0, c2 = 0, c3 = 0;
+  const uint64_t ODD = 0x5555555555555555ull;
+  const uint64_t cpat = (uint64_t)c * ODD;                       // c in every 2-bit field
+  const uint64_t g_or = c == 0 ? ~0ull : 0ull, g_hi = c == 1 ? ~0ull : 0ull, g_and = c == 2 ? ~0ull : 0ull;
+  uint64_t e[4], g[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    int m = n - 32 * i;                       // symbols of this word that count
+    int m = n - 32 * i;                                          // symbols of this word that count
     m = m < 0 ? 0 : (m > 32 ? 32 : m);
-    const uint64_t keep = m ? (~0ull << (64 - 2 * m)) & 0x5555555555555555ull : 0ull;
-    const uint64_t lo = W[i], hi = W[i] >> 1;
-    c1 += __popcll(~hi & lo & keep);
-    c2 += __popcll(hi & ~lo & keep);
-    c3 += __popcll(hi & lo & keep);
+    const uint64_t keep = m ? (~0ull << (64 - 2 * m)) & ODD : 0ull;
+    const uint64_t x = W[i] ^ cpat, lo = W[i], hi = W[i] >> 1;
+    e[i] = ~(x | x >> 1) & keep;
+    g[i] = (((hi | lo) & g_or) | (hi & g_hi) | (hi & lo & g_and)) & keep;
   }
-  cnt[0] += (uint64_t)(n - c1 - c2 - c3); cnt[1] += (uint64_t)c1; cnt[2] += (uint64_t)c2; cnt[3] += (uint64_t)c3;
+  *eq = __popcll(e[0] | e[1] << 1) + __popcll(e[2] | e[3] << 1);
+  *gt = __popcll(g[0] | g[1] << 1) + __popcll(g[2] | g[3] << 1);
 }
 
-// Occ(., k) for all four bases: bwt_occ4, bwa/bwt.c:169-186
-__device__ __forceinline__ void occ4(const DevIndex &ix, uint64_t k, uint64_t cnt[4], unsigned long long *blocks)
+__device__ __forceinline__ uint64_t hdr_count(const uint4 c0, const uint4 c1, int b)
+{ // running count of base b stored at the head of the block (4 x u64)
+  const uint32_t lo = b == 0 ? c0.x : b == 1 ? c0.z : b == 2 ? c1.x : c1.z;
+  const uint32_t hi = b == 0 ? c0.y : b == 1 ? c0.w : b == 2 ? c1.y : c1.w;
+  return (uint64_t)hi << 32 | lo;
+}
+__device__ __forceinline__ uint64_t hdr_count_gt(const uint4 c0, const uint4 c1, int c)
+{ // sum of the running counts of all bases greater than c
+  const uint64_t n1 = (uint64_t)c0.w << 32 | c0.z, n2 = (uint64_t)c1.y << 32 | c1.x, n3 = (uint64_t)c1.w << 32 | c1.z;
+  return (c < 1 ? n1 : 0) + (c < 2 ? n2 : 0) + (c < 3 ? n3 : 0);
+}
+
+// Occ of base c and of all bases > c among BWT rows [0,k]: the part of bwt_occ4 (bwa/bwt.c:169-186) that one
+// interval extension needs.  k == -1 cannot occur here (interval starts are >= 1).
+__device__ __forceinline__ void occ_eq_gt(const DevIndex &ix, uint64_t k, int c, uint64_t *eq, uint64_t *gt, unsigned long long *blocks)
 {
-  if (k == (uint64_t)-1) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; return; }
   k -= (k >= ix.primary);
   const uint4 *b = ix.bwt + ((k >> 7) << 2);
   const uint4 c0 = __ldg(b), c1 = __ldg(b + 1), s0 = __ldg(b + 2), s1 = __ldg(b + 3);
-  cnt[0] = (uint64_t)c0.y << 32 | c0.x; cnt[1] = (uint64_t)c0.w << 32 | c0.z;
-  cnt[2] = (uint64_t)c1.y << 32 | c1.x; cnt[3] = (uint64_t)c1.w << 32 | c1.z;
-  block_count(s0, s1, (int)(k & 127) + 1, cnt);
+  int e, g;
+  prefix_counts(s0, s1, (int)(k & 127) + 1, c, &e, &g);
+  *eq = hdr_count(c0, c1, c) + (uint64_t)e;
+  *gt = hdr_count_gt(c0, c1, c) + (uint64_t)g;
   ++*blocks;
 }
 
@@ -58,26 +77,25 @@ __device__ __forceinline__ Intv extend1(const DevIndex &ix, const Intv ik, int i
 {
   const uint64_t xf = is_back ? ik.x0 : ik.x1, xg = is_back ? ik.x1 : ik.x0;
   const uint64_t k = xf - 1, l = xf - 1 + ik.x2;
-  uint64_t tk[4], tl[4];
   const uint64_t _k = k - (k >= ix.primary), _l = l - (l >= ix.primary);
-  if (k != (uint64_t)-1 && (_k >> 7) == (_l >> 7)) {
+  uint64_t ek, gk, el, gl;
+  if ((_k >> 7) == (_l >> 7)) {
     const uint4 *b = ix.bwt + ((_k >> 7) << 2);
     const uint4 c0 = __ldg(b), c1 = __ldg(b + 1), s0 = __ldg(b + 2), s1 = __ldg(b + 3);
-    tk[0] = (uint64_t)c0.y << 32 | c0.x; tk[1] = (uint64_t)c0.w << 32 | c0.z;
-    tk[2] = (uint64_t)c1.y << 32 | c1.x; tk[3] = (uint64_t)c1.w << 32 | c1.z;
-    tl[0] = tk[0]; tl[1] = tk[1]; tl[2] = tk[2]; tl[3] = tk[3];
-    block_count(s0, s1, (int)(_k & 127) + 1, tk);
-    block_count(s0, s1, (int)(_l & 127) + 1, tl);
+    int e0, g0, e1, g1;
+    prefix_counts(s0, s1, (int)(_k & 127) + 1, c, &e0, &g0);
+    prefix_counts(s0, s1, (int)(_l & 127) + 1, c, &e1, &g1);
+    const uint64_t he = hdr_count(c0, c1, c), hg = hdr_count_gt(c0, c1, c);
+    ek = he + (uint64_t)e0; el = he + (uint64_t)e1; gk = hg + (uint64_t)g0; gl = hg + (uint64_t)g1;
     ++*blocks;
   } else {
-    occ4(ix, k, tk, blocks);
-    occ4(ix, l, tl, blocks);
+    occ_eq_gt(ix, k, c, &ek, &gk, blocks);
+    occ_eq_gt(ix, l, c, &el, &gl, blocks);
   }
   Intv o;
-  uint64_t acc = xg + (xf <= ix.primary && xf + ik.x2 - 1 >= ix.primary);
-  for (int b = 3; b > c; --b) acc += tl[b] - tk[b];
-  const uint64_t nf = ix.L2[c] + 1 + tk[c];
-  o.x2 = tl[c] - tk[c];
+  const uint64_t acc = xg + (xf <= ix.primary && xf + ik.x2 - 1 >= ix.primary) + (gl - gk);
+  const uint64_t nf = ix.L2[c] + 1 + ek;
+  o.x2 = el - ek;
   if (is_back) { o.x0 = nf; o.x1 = acc; } else { o.x1 = nf; o.x0 = acc; }
   return o;
 }
@@ -97,62 +115,57 @@ struct SmemArgs {
   int min_seed_len, split_len, split_width, max_mem_intv;
 };
 
-// program counter of the per-lane flow machine
-enum { PC_FETCH, PC_NEXT, PC_F_HEAD, PC_F_DONE, PC_B_HEAD, PC_BE_HEAD, PC_BE_DONE, PC_FE_K, PC_FE_M, PC_B_NEXT, PC_SMEM_DONE,
-       PC_P3_HEAD, PC_FINISH, PC_EXTEND, PC_EXIT };
-enum { ST_F, ST_BE, ST_FE, ST_P3 };
+// One list entry of bwt_smem1a_new packed into 16 bytes: three 39-bit interval fields and an 11-bit query coordinate
+// (seq_len < 2^39, reads < 2^11); a single 128-bit local-memory access instead of four.
+__device__ __forceinline__ uint4 pack_entry(const Intv &v, int pos)
+{
+  const uint64_t lo = v.x0 | v.x1 << 39, hi = v.x1 >> 25 | v.x2 << 14 | (uint64_t)pos << 53;
+  return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+}
+__device__ __forceinline__ Intv unpack_entry(const uint4 e, int *pos)
+{
+  const uint64_t lo = (uint64_t)e.y << 32 | e.x, hi = (uint64_t)e.w << 32 | e.z, m = (1ull << 39) - 1;
+  Intv v; v.x0 = lo & m; v.x1 = (lo >> 39 | hi << 25) & m; v.x2 = (hi >> 14) & m; *pos = (int)(hi >> 53);
+  return v;
+}
+__device__ __forceinline__ int entry_pos(const uint4 e) { return (int)(e.w >> 21); }
 
+// One read per lane, written the way the reference is (nested loops); lanes of a warp diverge across the loops and the
+// hardware interleaves the divergent groups while they wait on their index loads.
 template <int MAXL>
 __global__ void __launch_bounds__(128) smem_kernel(const SmemArgs a)
 {
-  // per-lane lists of bwt_smem1a_new: forward matches (interval + end) and the leftward trail of one of them
-  uint64_t f0[MAXL], f1[MAXL], f2[MAXL]; int fend[MAXL];
-  uint64_t b0[MAXL], b1[MAXL], b2[MAXL];
+  uint4 fwd[MAXL], back[MAXL];          // forward matches (interval, end) and the leftward trail of one of them
   const DevIndex &ix = a.ix;
-  const unsigned full = 0xffffffffu;
   const int msl = a.min_seed_len;
-
-  int pc = PC_FETCH, st = ST_F;
-  // read
-  int64_t r = -1; int len = 0; const uint8_t *q = nullptr; bwaflow_intv_t *mem = nullptr; int n_mem = 0;
-  int pass = 1, x = 0, k2 = 0, old_n = 0;
-  // one bwt_smem1a_new call
-  int sx = 0, mi = 1, i = 0, fwd_n = 0, back_n = 0, fi = 0, start = 0, stop = 0, kb = 0, bk = 0, m = 0, ret = 0, px = 0;
-  Intv ik = {0, 0, 0}; int ik_beg = 0, ik_end = 0;
-  Intv cand = {0, 0, 0}; int cand_beg = 0, cand_end = 0;
-  int ext_back = 0, ext_c = 0;
   unsigned long long blocks = 0;
 
-  auto push_mem = [&](const Intv &v, int beg, int end) {
-    if (n_mem < a.cap) {
-      bwaflow_intv_t o; o.x[0] = v.x0; o.x[1] = v.x1; o.x[2] = v.x2; o.info = (uint64_t)(uint32_t)beg << 32 | (uint32_t)end;
-      mem[n_mem] = o;
-    }
-    ++n_mem;
-  };
-
   for (;;) {
-    // ---- flow machine: run until this lane needs one interval extension (or has no more reads)
-    while (pc != PC_EXTEND && pc != PC_EXIT) {
-      switch (pc) {
-      case PC_FETCH: {
-        r = (int64_t)atomicAdd(a.ctl, 1);
-        if (r >= a.n_reads) { pc = PC_EXIT; break; }
-        const int64_t ro = a.read_off[r];
-        len = (int)(a.read_off[r + 1] - ro); q = a.bases + ro;
-        mem = a.slots + r * a.cap; n_mem = 0; pass = 1; x = 0;
-        if (len >= MAXL) { atomicExch(a.ctl + 2, 1); a.counts[r] = 0; pc = PC_FETCH; break; }
-        if (len < msl) { pc = PC_FINISH; break; }            // src/bwa_wrapper.cpp:150
-        pc = PC_NEXT;
-        break;
+    const int64_t r = (int64_t)atomicAdd(a.ctl, 1);
+    if (r >= a.n_reads) break;
+    const int64_t ro = a.read_off[r];
+    const int len = (int)(a.read_off[r + 1] - ro);
+    const uint8_t *q = a.bases + ro;
+    bwaflow_intv_t *mem = a.slots + r * a.cap;
+    int n_mem = 0;
+    auto push_mem = [&](const Intv &v, int beg, int end) {
+      if (n_mem < a.cap) {
+        bwaflow_intv_t o; o.x[0] = v.x0; o.x[1] = v.x1; o.x[2] = v.x2; o.info = (uint64_t)(uint32_t)beg << 32 | (uint32_t)end;
+        mem[n_mem] = o;
       }
-      case PC_NEXT:                                          // mem_collect_intv_new's three loops
-        if (pass == 1) {                                     // :214-218
+      ++n_mem;
+    };
+    if (len >= MAXL) { atomicExch(a.ctl + 2, 1); a.counts[r] = 0; continue; }
+    if (len >= msl) {                                          // src/bwa_wrapper.cpp:150
+      // ---- passes 1 and 2 (src/bwa_wrapper.cpp:214-226): a sequence of bwt_smem1a_new(sx, mi) calls
+      int pass = 1, x = 0, k2 = 0, old_n = 0;
+      for (;;) {
+        int sx, mi;
+        if (pass == 1) {
           while (x < len && q[x] > 3) ++x;
-          if (x < len) { sx = x; mi = 1; pc = PC_F_HEAD; fwd_n = back_n = 0; ik = set_intv(ix, q[sx]); ik_end = sx + 1; i = sx + 1; }
-          else { pass = 2; old_n = n_mem < a.cap ? n_mem : a.cap; k2 = 0; }
-        } else if (pass == 2) {                              // :220-226
-          pc = PC_NEXT;
+          if (x >= len) { pass = 2; old_n = n_mem < a.cap ? n_mem : a.cap; continue; }
+          sx = x; mi = 1;
+        } else {
           bool go = false;
           while (k2 < old_n) {
             const bwaflow_intv_t p = mem[k2++];
@@ -161,125 +174,103 @@ __global__ void __launch_bounds__(128) smem_kernel(const SmemArgs a)
             sx = (s + e) >> 1; mi = (int)p.x[2] + 1; go = true;
             break;
           }
-          if (go) {
-            if (q[sx] > 3) break;                            // bwt_smem1a_new :338 (cannot happen inside an SMEM)
-            fwd_n = back_n = 0; ik = set_intv(ix, q[sx]); ik_end = sx + 1; i = sx + 1; pc = PC_F_HEAD;
-          } else { pass = 3; x = 0; if (a.max_mem_intv <= 0) pc = PC_FINISH; }
-        } else {                                             // :228-243
-          while (x < len && q[x] > 3) ++x;
-          if (x < len) { px = x; ik = set_intv(ix, q[x]); i = x + 1; pc = PC_P3_HEAD; }
-          else pc = PC_FINISH;
+          if (!go) break;
+          if (q[sx] > 3) continue;                             // bwt_smem1a_new :338
         }
-        break;
-      case PC_F_HEAD:                                        // forward sweep, src/bwa_wrapper.cpp:346-363
-        if (i < len && q[i] < 4) { ext_back = 0; ext_c = 3 - q[i]; st = ST_F; pc = PC_EXTEND; break; }
-        f0[fwd_n] = ik.x0; f1[fwd_n] = ik.x1; f2[fwd_n] = ik.x2; fend[fwd_n] = ik_end; ++fwd_n;   // N or end of read
-        pc = PC_F_DONE;
-        break;
-      case PC_F_DONE:
-        ret = fend[fwd_n - 1]; start = sx; stop = sx; fi = 0;
-        pc = PC_B_HEAD;
-        break;
-      case PC_B_HEAD:                                        // :367-371
-        if (fi >= fwd_n) { pc = PC_SMEM_DONE; break; }
-        ik.x0 = f0[fi]; ik.x1 = f1[fi]; ik.x2 = f2[fi]; ik_end = fend[fi]; ik_beg = sx;
-        if (back_n == 0 || stop - start >= 3) {
-          b0[0] = ik.x0; b1[0] = ik.x1; b2[0] = ik.x2; back_n = 1;
-          kb = sx - 1; pc = PC_BE_HEAD;
-        } else { stop = fend[fi]; bk = back_n - 1; pc = PC_FE_K; }
-        break;
-      case PC_BE_HEAD:                                       // back-enlarge, :374-386
-        if (kb >= 0 && q[kb] < 4) { ext_back = 1; ext_c = q[kb]; st = ST_BE; pc = PC_EXTEND; }
-        else pc = PC_BE_DONE;
-        break;
-      case PC_BE_DONE:                                       // :387-400
-        start = fend[fi]; stop = fi == fwd_n - 1 ? len : fend[fi + 1];
-        if (fi > 0 && ik_beg > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
-        cand = ik; cand_beg = ik_beg; cand_end = ik_end;
-        pc = PC_B_NEXT;
-        break;
-      case PC_FE_K:                                          // forward-enlarge, :404-429
-        if (bk < 0) { pc = PC_B_NEXT; break; }
-        ik.x0 = b0[bk]; ik.x1 = b1[bk]; ik.x2 = b2[bk]; m = start + 1;
-        pc = PC_FE_M;
-        break;
-      case PC_FE_M:
-        if (m <= stop) { ext_back = 0; ext_c = 3 - q[m - 1]; st = ST_FE; pc = PC_EXTEND; }
-        else { --bk; pc = PC_FE_K; }
-        break;
-      case PC_B_NEXT:                                        // :431-443
-        ++fi;
-        if (fi < fwd_n) {
-          int max_len = cand_beg + fend[fi];
-          while (max_len < msl && fi < fwd_n) {
-            ++fi;
-            if (fi < fwd_n) stop = fend[fi];
-            max_len = cand_beg + stop;
+        // ---- bwt_smem1a_new(sx, mi), src/bwa_wrapper.cpp:325-450
+        int fwd_n = 0, back_n = 0;
+        Intv ik = set_intv(ix, q[sx]);
+        int ik_end = sx + 1, i;
+        for (i = sx + 1; i < len; ++i) {                       // forward sweep :346-363
+          if (q[i] > 3) { fwd[fwd_n++] = pack_entry(ik, ik_end); break; }
+          const Intv o = extend1(ix, ik, 0, 3 - q[i], &blocks);
+          if (o.x2 != ik.x2) {
+            fwd[fwd_n++] = pack_entry(ik, ik_end);
+            if (o.x2 < (uint64_t)mi) break;
           }
+          ik = o; ik_end = i + 1;
         }
-        if (fi >= fwd_n && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
-        pc = PC_B_HEAD;
-        break;
-      case PC_SMEM_DONE:
+        if (i == len) fwd[fwd_n++] = pack_entry(ik, ik_end);
+        const int ret = entry_pos(fwd[fwd_n - 1]);
+        int start = sx, stop = sx, fi = 0, cand_beg = 0, cand_end = 0;
+        Intv cand = {0, 0, 0};
+        while (fi < fwd_n) {                                   // :367-444
+          int ik_beg = sx, f_end;
+          ik = unpack_entry(fwd[fi], &f_end);
+          if (back_n == 0 || stop - start >= 3) {              // back-enlarge :371-401
+            back[0] = pack_entry(ik, 0); back_n = 1;
+            for (int kb = sx - 1; kb >= 0 && q[kb] < 4; --kb) {
+              const Intv o = extend1(ix, ik, 1, q[kb], &blocks);
+              if (o.x2 < (uint64_t)mi) break;
+              ik = o; ik_beg = kb;
+              back[back_n++] = pack_entry(ik, 0);
+            }
+            start = f_end;
+            stop = fi == fwd_n - 1 ? len : entry_pos(fwd[fi + 1]);
+            if (fi > 0 && ik_beg > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+            cand = ik; cand_beg = ik_beg; cand_end = f_end;
+          } else {                                             // forward-enlarge :403-430
+            stop = f_end;
+            for (int bk = back_n - 1; bk >= 0; --bk) {
+              int dummy, m;
+              ik = unpack_entry(back[bk], &dummy);
+              for (m = start + 1; m <= stop; ++m) {
+                const Intv o = extend1(ix, ik, 0, 3 - q[m - 1], &blocks);
+                if (o.x2 < (uint64_t)mi) break;
+                ik = o;
+              }
+              if (m > stop) {                                  // reached the end of this forward match
+                ik_beg = sx - bk;
+                if (ik_beg > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+                cand = ik; cand_beg = ik_beg; cand_end = f_end;
+                break;
+              }
+            }
+          }
+          ++fi;
+          if (fi < fwd_n) {                                    // :433-441
+            int max_len = cand_beg + entry_pos(fwd[fi]);
+            while (max_len < msl && fi < fwd_n) {
+              ++fi;
+              if (fi < fwd_n) stop = entry_pos(fwd[fi]);
+              max_len = cand_beg + stop;
+            }
+          }
+          if (fi >= fwd_n && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+        }
         if (pass == 1) x = ret;
-        pc = PC_NEXT;
-        break;
-      case PC_P3_HEAD:                                       // bwt_seed_strategy1, bwa/bwt.c:366-378
-        if (i < len) {
-          if (q[i] > 3) { x = i + 1; pc = PC_NEXT; }
-          else { ext_back = 0; ext_c = 3 - q[i]; st = ST_P3; pc = PC_EXTEND; }
-        } else { x = len; pc = PC_NEXT; }
-        break;
-      case PC_FINISH: {                                      // ks_introsort by info (:245); equal keys are equal elements
-        const int n = n_mem < a.cap ? n_mem : a.cap;
-        for (int u = 1; u < n; ++u) {
-          const bwaflow_intv_t v = mem[u];
-          int t = u - 1;
-          while (t >= 0 && mem[t].info > v.info) { mem[t + 1] = mem[t]; --t; }
-          mem[t + 1] = v;
-        }
-        a.counts[r] = n_mem;
-        if (n_mem > a.cap) atomicExch(a.ctl + 1, 1);
-        pc = PC_FETCH;
-        break;
       }
+      // ---- pass 3 (src/bwa_wrapper.cpp:228-243): bwt_seed_strategy1, bwa/bwt.c:358-379
+      if (a.max_mem_intv > 0) {
+        x = 0;
+        while (x < len) {
+          if (q[x] > 3) { ++x; continue; }
+          Intv ik = set_intv(ix, q[x]);
+          int i;
+          for (i = x + 1; i < len; ++i) {
+            if (q[i] > 3) { ++i; break; }
+            const Intv o = extend1(ix, ik, 0, 3 - q[i], &blocks);
+            if (o.x2 < (uint64_t)a.max_mem_intv && i - x >= msl) {
+              if (o.x2 > 0) push_mem(o, x, i + 1);
+              ++i;
+              break;
+            }
+            ik = o;
+          }
+          x = i;
+        }
       }
     }
-    if (__ballot_sync(full, pc == PC_EXTEND) == 0) break;
-    if (pc == PC_EXTEND) {
-      // ---- the one convergent call site of bwt_extend
-      const Intv o = extend1(ix, ik, ext_back, ext_c, &blocks);
-      switch (st) {
-      case ST_F:                                             // :353-357
-        if (o.x2 != ik.x2) {
-          f0[fwd_n] = ik.x0; f1[fwd_n] = ik.x1; f2[fwd_n] = ik.x2; fend[fwd_n] = ik_end; ++fwd_n;
-          if (o.x2 < (uint64_t)mi) { pc = PC_F_DONE; break; }
-        }
-        ik = o; ik_end = i + 1; ++i; pc = PC_F_HEAD;
-        break;
-      case ST_BE:                                            // :377-381
-        if (o.x2 < (uint64_t)mi) { pc = PC_BE_DONE; break; }
-        ik = o; ik_beg = kb;
-        b0[back_n] = ik.x0; b1[back_n] = ik.x1; b2[back_n] = ik.x2; ++back_n;
-        --kb; pc = PC_BE_HEAD;
-        break;
-      case ST_FE:                                            // :409-427
-        if (o.x2 < (uint64_t)mi) { --bk; pc = PC_FE_K; break; }
-        ik = o;
-        if (m == stop) {
-          ik_end = fend[fi]; ik_beg = sx - bk;
-          if (ik_beg > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
-          cand = ik; cand_beg = ik_beg; cand_end = ik_end;
-          pc = PC_B_NEXT;
-        } else { ++m; pc = PC_FE_M; }
-        break;
-      case ST_P3:                                            // bwa/bwt.c:370-375
-        if (o.x2 < (uint64_t)a.max_mem_intv && i - px >= msl) {
-          if (o.x2 > 0) push_mem(o, px, i + 1);
-          x = i + 1; pc = PC_NEXT;
-        } else { ik = o; ++i; pc = PC_P3_HEAD; }
-        break;
+    {                                                          // ks_introsort by info (:245); equal keys are equal elements
+      const int n = n_mem < a.cap ? n_mem : a.cap;
+      for (int u = 1; u < n; ++u) {
+        const bwaflow_intv_t v = mem[u];
+        int t = u - 1;
+        while (t >= 0 && mem[t].info > v.info) { mem[t + 1] = mem[t]; --t; }
+        mem[t + 1] = v;
       }
+      a.counts[r] = n_mem;
+      if (n_mem > a.cap) atomicExch(a.ctl + 1, 1);
     }
   }
   if (blocks) atomicAdd(a.blocks, blocks);
@@ -304,11 +295,9 @@ __device__ __forceinline__ uint64_t sa_lookup(const DevIndex &ix, uint64_t k, un
 #pragma unroll
     for (int t = 0; t < 8; ++t) word = (r >> 4) == t ? sw[t] : word;
     const int c = (word >> ((~r & 15) << 1)) & 3;
-    uint64_t cnt[4];
-    cnt[0] = (uint64_t)c0.y << 32 | c0.x; cnt[1] = (uint64_t)c0.w << 32 | c0.z;
-    cnt[2] = (uint64_t)c1.y << 32 | c1.x; cnt[3] = (uint64_t)c1.w << 32 | c1.z;
-    block_count(s0, s1, r + 1, cnt);
-    k = ix.L2[c] + cnt[c];
+    int e, g;
+    prefix_counts(s0, s1, r + 1, c, &e, &g);
+    k = ix.L2[c] + hdr_count(c0, c1, c) + (uint64_t)e;
     ++*blocks;
   }
   return steps + ix.sa[k >> ix.sa_shift];
@@ -367,23 +356,6 @@ __global__ void seedpos_kernel(DevIndex ix, const bwaflow_intv_t *intv, int64_t 
 
 using namespace bwaflow;
 
-struct bwaflow_smem_batch {
-  bwaflow_ctx_t *ctx;
-  cudaStream_t stream;
-  Timer tm;
-  int64_t max_reads, max_bases, n_reads, max_len;
-  uint8_t *d_bases; int64_t *d_read_off;
-  bwaflow_intv_t *d_slots; int cap; int64_t slots_cap;
-  int *d_counts; int64_t *d_cnt64, *d_off, *h_off;
-  bwaflow_intv_t *d_out, *h_out; int64_t out_cap;
-  int *d_ctl, *h_ctl;               // head | overflow | too-long | pad | blocks(u64)
-  void *d_tmp; size_t tmp_bytes;
-  int64_t n_intv;
-  // seed positions
-  int64_t *d_pcnt, *d_poff, *h_poff, *d_pos, *h_pos; int64_t pos_cap;
-  int blocks_per_launch;
-  bool pending;
-};
 
 static int smem_alloc_slots(bwaflow_smem_batch *b, int cap)
 {
@@ -393,7 +365,7 @@ static int smem_alloc_slots(bwaflow_smem_batch *b, int cap)
   return 0;
 }
 
-static int smem_launch(bwaflow_smem_batch *b)
+int bwaflow::smem_launch(bwaflow_smem_batch *b)
 {
   const int64_t nr = b->n_reads;
   cudaStream_t st = b->stream;
@@ -415,6 +387,84 @@ static int smem_launch(bwaflow_smem_batch *b)
   size_t tmp = b->tmp_bytes;
   BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_cnt64, b->d_off, (int)(nr + 1), st));
   BF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int smem_queue_tail(bwaflow_smem_batch *b)
+{
+  BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_off, b->d_off, (b->n_reads + 1) * 8, cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_ctl, b->d_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  b->pending = true;
+  return 0;
+}
+
+
+// Waits for the seeding kernel, redoes the batch with larger slots if some read overflowed its slot, then compacts
+// the per-read slots into d_out / d_off (device) and h_off (host).  Leaves b->n_intv set.
+int bwaflow::smem_finish_device(bwaflow_smem_batch *b)
+{
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  BF_CUDA(cudaStreamSynchronize(b->stream));
+  while (b->h_ctl[1]) {                      // some read filled its slot: grow the slots and redo the batch on the GPU
+    BF_REQUIRE(b->cap < 4096, -34, "a read produced more than 4096 intervals");
+    int r = smem_alloc_slots(b, b->cap * 4);
+    if (r) return r;
+    if ((r = smem_launch(b))) return r;
+    if ((r = smem_queue_tail(b))) return r;
+    BF_CUDA(cudaStreamSynchronize(b->stream));
+  }
+  b->pending = false;
+  BF_REQUIRE(!b->h_ctl[2], -34, "a read is too long for the seeding kernel instance chosen for this batch");
+  const int64_t total = b->n_reads ? b->h_off[b->n_reads] : 0;
+  if (total > b->out_cap) {
+    cudaFree(b->d_out); cudaFreeHost(b->h_out); cudaFree(b->d_pcnt); cudaFree(b->d_poff); cudaFreeHost(b->h_poff); cudaFree(b->d_tmp);
+    b->out_cap = total + total / 4;
+    BF_CUDA(cudaMalloc(&b->d_out, b->out_cap * sizeof(bwaflow_intv_t)));
+    BF_CUDA(cudaMallocHost(&b->h_out, b->out_cap * sizeof(bwaflow_intv_t)));
+    BF_CUDA(cudaMalloc(&b->d_pcnt, (b->out_cap + 2) * 8));
+    BF_CUDA(cudaMalloc(&b->d_poff, (b->out_cap + 2) * 8));
+    BF_CUDA(cudaMallocHost(&b->h_poff, (b->out_cap + 2) * 8));
+    BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b->tmp_bytes, b->d_cnt64, b->d_off, (int)(b->out_cap + 1), b->stream));
+    b->tmp_bytes += 256;
+    BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
+  }
+  if (total)
+    smem_compact<<<(unsigned)((b->n_reads * 32 + 255) / 256), 256, 0, b->stream>>>(b->d_slots, b->cap, b->d_off, b->n_reads, b->d_out);
+  BF_CUDA(cudaGetLastError());
+  b->n_intv = total;
+  return 0;
+}
+
+// SA positions of the current intervals into d_pos / d_poff (device); *total = number of positions.
+int bwaflow::smem_seedpos_device(bwaflow_smem_batch *b, int64_t *total_out)
+{
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  cudaStream_t st = b->stream;
+  const int64_t ni = b->n_intv;
+  const int max_occ = b->ctx->par.opt.max_occ;
+  BF_CUDA(cudaMemsetAsync(b->d_ctl + 4, 0, 8, st));
+  BF_CUDA(cudaMemsetAsync(b->d_poff, 0, (ni + 1) * 8, st));
+  if (ni) {
+    seedpos_counts<<<(unsigned)((ni + 1 + 255) / 256), 256, 0, st>>>(b->d_out, ni, max_occ, b->d_pcnt);
+    size_t tmp = b->tmp_bytes;
+    BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_pcnt, b->d_poff, (int)(ni + 1), st));
+  }
+  BF_CUDA(cudaMemcpyAsync(b->h_poff, b->d_poff, (ni + 1) * 8, cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaStreamSynchronize(st));
+  const int64_t total = b->h_poff[ni];
+  if (total > b->pos_cap) {
+    cudaFree(b->d_pos);
+    b->pos_cap = total + total / 4 + 1024;
+    BF_CUDA(cudaMalloc(&b->d_pos, b->pos_cap * 8));
+  }
+  BF_CUDA(cudaEventRecord(b->tm.ev[1], st));
+  if (total) {
+    seedpos_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(b->ctx->ix, b->d_out, ni, b->d_poff, total, max_occ, b->d_pos,
+                                                                      (unsigned long long *)(b->d_ctl + 4));
+    BF_CUDA(cudaGetLastError());
+  }
+  *total_out = total;
   return 0;
 }
 
@@ -474,14 +524,6 @@ void bwaflow_smem_batch_destroy(bwaflow_smem_batch_t *b)
   free(b);
 }
 
-static int smem_queue_tail(bwaflow_smem_batch *b)
-{
-  BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
-  BF_CUDA(cudaMemcpyAsync(b->h_off, b->d_off, (b->n_reads + 1) * 8, cudaMemcpyDeviceToHost, b->stream));
-  BF_CUDA(cudaMemcpyAsync(b->h_ctl, b->d_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-  b->pending = true;
-  return 0;
-}
 
 int bwaflow_smem_submit(bwaflow_smem_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off)
 {
@@ -520,36 +562,12 @@ int bwaflow_smem_collect(bwaflow_smem_batch_t *b, const bwaflow_intv_t **intv, c
                          int64_t *n_intv, bwaflow_timing_t *t)
 {
   BF_REQUIRE(b && b->pending, -22, "bwaflow_smem_collect: nothing submitted");
-  BF_CUDA(cudaStreamSynchronize(b->stream));
-  while (b->h_ctl[1]) {                      // some read filled its slot: grow the slots and redo the batch on the GPU
-    BF_REQUIRE(b->cap < 4096, -34, "a read produced more than 4096 intervals");
-    int r = smem_alloc_slots(b, b->cap * 4);
-    if (r) return r;
-    if ((r = smem_launch(b))) return r;
-    if ((r = smem_queue_tail(b))) return r;
-    BF_CUDA(cudaStreamSynchronize(b->stream));
-  }
-  b->pending = false;
-  const int64_t total = b->n_reads ? b->h_off[b->n_reads] : 0;
-  if (total > b->out_cap) {
-    cudaFree(b->d_out); cudaFreeHost(b->h_out); cudaFree(b->d_pcnt); cudaFree(b->d_poff); cudaFreeHost(b->h_poff); cudaFree(b->d_tmp);
-    b->out_cap = total + total / 4;
-    BF_CUDA(cudaMalloc(&b->d_out, b->out_cap * sizeof(bwaflow_intv_t)));
-    BF_CUDA(cudaMallocHost(&b->h_out, b->out_cap * sizeof(bwaflow_intv_t)));
-    BF_CUDA(cudaMalloc(&b->d_pcnt, (b->out_cap + 2) * 8));
-    BF_CUDA(cudaMalloc(&b->d_poff, (b->out_cap + 2) * 8));
-    BF_CUDA(cudaMallocHost(&b->h_poff, (b->out_cap + 2) * 8));
-    BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b->tmp_bytes, b->d_cnt64, b->d_off, (int)(b->out_cap + 1), b->stream));
-    b->tmp_bytes += 256;
-    BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
-  }
-  if (total) {
-    smem_compact<<<(unsigned)((b->n_reads * 32 + 255) / 256), 256, 0, b->stream>>>(b->d_slots, b->cap, b->d_off, b->n_reads, b->d_out);
-    BF_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, total * sizeof(bwaflow_intv_t), cudaMemcpyDeviceToHost, b->stream));
-  }
+  int r = smem_finish_device(b);
+  if (r) return r;
+  const int64_t total = b->n_intv;
+  if (total) BF_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, total * sizeof(bwaflow_intv_t), cudaMemcpyDeviceToHost, b->stream));
   BF_CUDA(cudaEventRecord(b->tm.ev[3], b->stream));
   BF_CUDA(cudaStreamSynchronize(b->stream));
-  b->n_intv = total;
   if (t) {
     memset(t, 0, sizeof(*t));
     cudaEventElapsedTime(&t->h2d_ms, b->tm.ev[0], b->tm.ev[1]);
@@ -559,7 +577,6 @@ int bwaflow_smem_collect(bwaflow_smem_batch_t *b, const bwaflow_intv_t **intv, c
     t->n_launches = b->n_reads ? 5 : 0;
     t->work_units = (double)*(unsigned long long *)(b->h_ctl + 4);   // occ blocks touched (64 B each)
   }
-  BF_REQUIRE(!b->h_ctl[2], -34, "a read is too long for the seeding kernel instance chosen for this batch");
   if (intv) *intv = b->h_out;
   if (intv_off) *intv_off = b->h_off;
   if (n_intv) *n_intv = total;
@@ -570,34 +587,17 @@ int bwaflow_smem_seed_positions(bwaflow_smem_batch_t *b, const int64_t **pos, co
                                 int64_t *n_pos, bwaflow_timing_t *t)
 {
   BF_REQUIRE(b && !b->pending, -22, "bwaflow_smem_seed_positions: collect the batch first");
-  BF_CUDA(cudaSetDevice(b->ctx->device));
   cudaStream_t st = b->stream;
-  const int64_t ni = b->n_intv;
-  const int max_occ = b->ctx->par.opt.max_occ;
+  int64_t total = 0;
   BF_CUDA(cudaEventRecord(b->tm.ev[0], st));
-  BF_CUDA(cudaMemsetAsync(b->d_ctl + 4, 0, 8, st));
-  BF_CUDA(cudaMemsetAsync(b->d_poff, 0, (ni + 1) * 8, st));
-  if (ni) {
-    seedpos_counts<<<(unsigned)((ni + 1 + 255) / 256), 256, 0, st>>>(b->d_out, ni, max_occ, b->d_pcnt);
-    size_t tmp = b->tmp_bytes;
-    BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_pcnt, b->d_poff, (int)(ni + 1), st));
-  }
-  BF_CUDA(cudaMemcpyAsync(b->h_poff, b->d_poff, (ni + 1) * 8, cudaMemcpyDeviceToHost, st));
-  BF_CUDA(cudaStreamSynchronize(st));
-  const int64_t total = b->h_poff[ni];
-  if (total > b->pos_cap) {
-    cudaFree(b->d_pos); cudaFreeHost(b->h_pos);
-    b->pos_cap = total + total / 4 + 1024;
-    BF_CUDA(cudaMalloc(&b->d_pos, b->pos_cap * 8));
-    BF_CUDA(cudaMallocHost(&b->h_pos, b->pos_cap * 8));
-  }
-  BF_CUDA(cudaEventRecord(b->tm.ev[1], st));
-  if (total) {
-    seedpos_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(b->ctx->ix, b->d_out, ni, b->d_poff, total, max_occ, b->d_pos,
-                                                                      (unsigned long long *)(b->d_ctl + 4));
-    BF_CUDA(cudaGetLastError());
-  }
+  int r = smem_seedpos_device(b, &total);
+  if (r) return r;
   BF_CUDA(cudaEventRecord(b->tm.ev[2], st));
+  if (total > b->hpos_cap) {
+    cudaFreeHost(b->h_pos);
+    b->hpos_cap = total + total / 4 + 1024;
+    BF_CUDA(cudaMallocHost(&b->h_pos, b->hpos_cap * 8));
+  }
   if (total) BF_CUDA(cudaMemcpyAsync(b->h_pos, b->d_pos, total * 8, cudaMemcpyDeviceToHost, st));
   BF_CUDA(cudaMemcpyAsync(b->h_ctl, b->d_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
   BF_CUDA(cudaEventRecord(b->tm.ev[3], st));

@@ -99,9 +99,34 @@ class ChainsToRegionsCUDA:
         self.batch.close()
 
 
+class FusedHotPath:
+    """reads -> alignment regions on the device only (bwaflow_hot_*): stage 2 leaves its chains in HBM (tag=1 record whose
+    `chains` is a device handle), ChainsPipe passes through, stage 4 consumes them.  Same results as HotPath."""
+
+    def __init__(self, ctx: capi.Context, max_reads, max_bases, chain_opt=None, ctg_alt=None):
+        self.batch = capi.HotBatch(ctx, max_reads, max_bases, chain_opt, ctg_alt)
+        self.last = None
+
+    def run(self, rec):
+        self.batch.submit(rec["bases"], rec["read_off"])
+        regs, reg_off, t = self.batch.collect()
+        self.last = t
+        return {"name": "RegionsRecord", "start_idx": rec["start_idx"], "batch_num": rec["batch_num"], "bases": rec["bases"],
+                "read_off": rec["read_off"], "chains": None, "alnreg": regs, "alnreg_off": reg_off}
+
+    def rerun(self):
+        self.batch.rerun()
+        regs, reg_off, t = self.batch.collect()
+        self.last = t
+        return regs, reg_off, t
+
+    def close(self):
+        self.batch.close()
+
+
 class HotPath:
     """reads -> alignment regions: stage 2, the host hop and stage 4 chained the way compute_flow wires them
-    (src/main.cpp:302-335)."""
+    (src/main.cpp:302-335), with the chaining hop on the host CPU as in the FPGA flow."""
 
     def __init__(self, ctx: capi.Context, index_like, ctg_off, ctg_len, max_reads, max_bases, chain_opt=None, n_threads=0):
         self.s2 = SeqsToChainsCUDA(ctx, max_reads, max_bases)

@@ -174,6 +174,23 @@ void bwaflow_chain_result_view(const bwaflow_chain_result_t *r, const bwaflow_ch
                                const bwaflow_seed_t **seeds, int64_t *n_seeds, const int64_t **chain_off);
 void bwaflow_chain_result_free(bwaflow_chain_result_t *r);
 
+/* ---- fused hot path: reads -> regions with intervals, SA positions and chains resident in HBM (stage 2, the chaining
+ *      hop of ChainsPipe src/Pipeline.cpp:408-438 and stage 4 back to back on one stream).  Results are identical
+ *      to running the three pieces separately.  ctg_is_alt may be NULL. */
+typedef struct bwaflow_hot_batch bwaflow_hot_batch_t;
+typedef struct {
+  float h2d_ms, smem_ms, seedpos_ms, chain_ms, c2a_ms, d2h_ms, total_ms; int32_t n_launches;
+  double smem_blocks, seedpos_blocks, cells;           /* 64-byte occ-block touches; executed DP cells */
+  int64_t n_intv, n_pos, n_chains, n_seeds;
+} bwaflow_hot_timing_t;
+int bwaflow_hot_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_bases, const bwaflow_chain_opt_t *copt,
+                             const int32_t *ctg_is_alt, bwaflow_hot_batch_t **out);
+void bwaflow_hot_batch_destroy(bwaflow_hot_batch_t *b);
+int bwaflow_hot_submit(bwaflow_hot_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off);
+int bwaflow_hot_rerun(bwaflow_hot_batch_t *b);        /* reads of the last submit, already resident */
+int bwaflow_hot_collect(bwaflow_hot_batch_t *b, const bwaflow_alnreg_t **regs, const int64_t **reg_off, int64_t *n_regs,
+                        bwaflow_hot_timing_t *timing);
+
 /* ---- index construction for synthetic references (workload preparation; the arrays equal what `bwa index`
  *      + bwa_idx_load leave in memory, bwa/bwtindex.c:256-324).  codes: 0..3 = ACGT, >=4 = N, contigs concatenated. */
 typedef struct bwaflow_built_index bwaflow_built_index_t;
