@@ -251,29 +251,15 @@ def main():
     bases[:] = nt4_np
     read_off = capi.pinned((reads.n + 1,), np.int64)
     read_off[:] = reads.offsets
-    threads = max(1, (os.cpu_count() or 1) // world)
-    hp = stages.HotPath(ctx, index, ctg_off, ctg_len, reads.n, len(bases), n_threads=threads)
+    hp = stages.FusedHotPath(ctx, reads.n, len(bases))
     sw = capi.Stopwatch(ctx)
     rec = stages.seqs_record(rank * reads.n, bases, read_off)
 
     def step_e2e():
-        return hp.run(rec)
+        return hp.run(rec)                 # pinned host reads in, regions out (H2D + D2H inside)
 
     def step_resident():
-        # reads already in HBM (both device stages keep the bases of their previous submit)
-        s2, s4 = hp.s2.batch, hp.s4.batch
-        s2.rerun()
-        intv, intv_off, t1 = s2.collect()
-        pos, pos_off, t2 = s2.seed_positions()
-        t = time.perf_counter()
-        chains, seeds, chain_off = capi.chain_build(hp.hop.l_pac, ctg_off, ctg_len, read_off, intv, intv_off, pos, pos_off,
-                                                    n_threads=threads)
-        t_chain = (time.perf_counter() - t) * 1e3
-        regrown = hp.s4._fit(len(chains), len(seeds))
-        hp.s4.batch.submit(bases if regrown else None, read_off, chains, chain_off, seeds)
-        regs, reg_off, t3 = hp.s4.batch.collect()
-        return {"smem": t1, "seedpos": t2, "chain_ms": t_chain, "c2a": t3, "n_regs": len(regs), "n_intv": len(intv), "n_pos": len(pos),
-                "n_chains": len(chains), "n_seeds": len(seeds)}
+        return hp.rerun()[2]               # reads already in HBM from the previous submit
 
     out = step_e2e()                       # first touch: allocations, local-memory setup, capacity growth
     n_regs = len(out["alnreg"])
@@ -307,14 +293,14 @@ def main():
     e2e_val = total_pairs / (ms_e2e / args.steps * 1e-3)
     if rank != 0:
         return
-    # per-kernel means over the timed steps (CUDA events on each batch's stream)
-    k_smem = float(np.mean([p["smem"].kernel_ms for p in parts]))
-    k_pos = float(np.mean([p["seedpos"].kernel_ms for p in parts]))
-    k_c2a = float(np.mean([p["c2a"].kernel_ms for p in parts]))
-    t_chain = float(np.mean([p["chain_ms"] for p in parts]))
-    blocks_smem = parts[-1]["smem"].work_units
-    blocks_pos = parts[-1]["seedpos"].work_units
-    cells = parts[-1]["c2a"].work_units
+    # per-stage means over the timed steps (CUDA events on the batch's stream)
+    k_smem = float(np.mean([p.smem_ms for p in parts]))
+    k_pos = float(np.mean([p.seedpos_ms for p in parts]))
+    k_chain = float(np.mean([p.chain_ms for p in parts]))
+    k_c2a = float(np.mean([p.c2a_ms for p in parts]))
+    blocks_smem = parts[-1].smem_blocks
+    blocks_pos = parts[-1].seedpos_blocks
+    cells = parts[-1].cells
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -333,7 +319,7 @@ def main():
     dpx16, dpx32 = ctx.dpx_peak()
     gcups = cells / (k_c2a * 1e-3) / 1e9
     peak_gcups = dpx16 / 5.0 / 1e9
-    roofline_ext = {"kernel": "c2a_kernel", "bound": "int-alu/dpx", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": gcups / peak_gcups,
+    roofline_ext = {"kernel": "c2a_kernel (+prep/sort/compact)", "bound": "int-alu/dpx", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": gcups / peak_gcups,
                     "cells_per_launch": cells, "kernel_ms": k_c2a, "share_of_step": k_c2a / ms_step,
                     "peak_source": "measured DPX s16x2 issue rate %.3g lane-instr/s / 5 lane-instr per cell (SURVEY 8d); s32 rate %.3g" % (dpx16, dpx32)}
     h2d = int(bases.nbytes + read_off.nbytes)
@@ -342,11 +328,12 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": workload, "clocks": clk,
             "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(args.steps * (parts[-1]["smem"].n_launches + parts[-1]["seedpos"].n_launches + parts[-1]["c2a"].n_launches)),
+            "gpu_launches": int(args.steps * parts[-1].n_launches),
             "roofline": roofline, "roofline_ext": roofline_ext,
-            "breakdown_ms": {"smem_kernel": k_smem, "seedpos_kernel": k_pos, "host_chaining": t_chain, "c2a_kernels": k_c2a,
+            "breakdown_ms": {"smem_stage": k_smem, "seedpos_stage": k_pos, "device_chaining": k_chain, "c2a_stage": k_c2a,
                              "step": ms_step, "e2e_step": ms_e2e / args.steps, "index_build_s": t_index},
-            "counts": {k: parts[-1][k] for k in ("n_intv", "n_pos", "n_chains", "n_seeds", "n_regs")},
+            "counts": {"n_intv": parts[-1].n_intv, "n_pos": parts[-1].n_pos, "n_chains": parts[-1].n_chains,
+                       "n_seeds": parts[-1].n_seeds, "n_regs": n_regs},
             "seedpos_gbs": blocks_pos * 64 / (k_pos * 1e-3) / 1e9 if k_pos > 0 else None}
     if world == 1 and not args.no_cpu_baseline:
         sample = args.cpu_sample_pairs or min(n_pairs, 50_000)
