@@ -130,147 +130,201 @@ __device__ __forceinline__ Intv unpack_entry(const uint4 e, int *pos)
 }
 __device__ __forceinline__ int entry_pos(const uint4 e) { return (int)(e.w >> 21); }
 
-// One read per lane, written the way the reference is (nested loops); lanes of a warp diverge across the loops and the
-// hardware interleaves the divergent groups while they wait on their index loads.
+// One read per lane.  Every trip of the warp loop performs ONE interval extension for every live lane at a single
+// convergent call site (the expensive part: index loads + popcounts), followed by a short consume step for the four
+// kinds of inner loop of the algorithm (forward sweep, back-enlarge, forward-enlarge, pass-3 forward seed) that in
+// the common case just advances a cursor and requests the next extension.  Only loop exits (phase changes) go
+// through the divergent transition machine below.  The read and the end coordinates of the forward list live in
+// shared memory (one row per lane); the 16-byte interval entries of the two lists are per-lane local arrays.
+enum { PH_F = 0, PH_BE = 1, PH_FE = 2, PH_P3 = 3 };
+enum { T_NONE = 0, T_FETCH, T_NEXT, T_F_DONE, T_B_SELECT, T_BE_DONE, T_FE_PICK, T_FE_FAIL, T_FE_REACHED, T_B_NEXT, T_CALL_DONE,
+       T_FINISH, T_EXIT };
+
 template <int MAXL>
 __global__ void __launch_bounds__(128) smem_kernel(const SmemArgs a)
 {
-  uint4 fwd[MAXL], back[MAXL];          // forward matches (interval, end) and the leftward trail of one of them
+  constexpr int QROW = MAXL + 4;                 // bytes per lane for the read (odd word count: conflict-free rows)
+  constexpr bool QS = MAXL <= 256;               // longer reads stay in global memory
+  extern __shared__ uint8_t s_mem[];
+  uint8_t *q_s = s_mem + (size_t)threadIdx.x * QROW;
+  uint8_t *fend = s_mem + (QS ? (size_t)blockDim.x * QROW : 0) + (size_t)threadIdx.x * QROW;   // forward-list end coordinates (u8/u16)
+  uint4 fwd[MAXL], back[MAXL];
   const DevIndex &ix = a.ix;
+  const unsigned full = 0xffffffffu;
   const int msl = a.min_seed_len;
   unsigned long long blocks = 0;
+  // end coordinate of forward-list entry k: a byte in shared memory for reads <= 256, else the entry's own field
+  auto get_end = [&](int k) -> int { return QS ? (int)fend[k] : entry_pos(fwd[k]); };
+
+  int ts = T_FETCH;                              // transition state; T_NONE = an extension is pending
+  int64_t r = -1; int len = 0; const uint8_t *q = nullptr; bwaflow_intv_t *mem = nullptr; int n_mem = 0;
+  int pass = 1, x = 0, k2 = 0, old_n = 0;
+  int sx = 0, mi = 1, fwd_n = 0, back_n = 0, fi = 0, start = 0, stop = 0, ret = 0, px = 0, bk = 0, f_end = 0, ik_beg = 0;
+  int phase = PH_F, cur = 0, c = 0;
+  Intv ik = {0, 0, 0}, cand = {0, 0, 0}; int cand_beg = 0, cand_end = 0;
+
+  auto push_mem = [&](const Intv &v, int beg, int end) {
+    if (n_mem < a.cap) {
+      bwaflow_intv_t o; o.x[0] = v.x0; o.x[1] = v.x1; o.x[2] = v.x2; o.info = (uint64_t)(uint32_t)beg << 32 | (uint32_t)end;
+      mem[n_mem] = o;
+    }
+    ++n_mem;
+  };
+  auto push_fwd = [&](const Intv &v, int end) { fwd[fwd_n] = pack_entry(v, end); if (QS) fend[fwd_n] = (uint8_t)end; ++fwd_n; };
+  auto take_cand = [&](int beg, bool first) {   // src/bwa_wrapper.cpp:392-400 / 418-427
+    if (!first && beg > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+    cand = ik; cand_beg = beg; cand_end = f_end;
+  };
 
   for (;;) {
-    const int64_t r = (int64_t)atomicAdd(a.ctl, 1);
-    if (r >= a.n_reads) break;
-    const int64_t ro = a.read_off[r];
-    const int len = (int)(a.read_off[r + 1] - ro);
-    const uint8_t *q = a.bases + ro;
-    bwaflow_intv_t *mem = a.slots + r * a.cap;
-    int n_mem = 0;
-    auto push_mem = [&](const Intv &v, int beg, int end) {
-      if (n_mem < a.cap) {
-        bwaflow_intv_t o; o.x[0] = v.x0; o.x[1] = v.x1; o.x[2] = v.x2; o.info = (uint64_t)(uint32_t)beg << 32 | (uint32_t)end;
-        mem[n_mem] = o;
+    // ---- transitions: run until this lane has an extension pending (or no reads are left)
+    while (ts != T_NONE && ts != T_EXIT) {
+      switch (ts) {
+      case T_FETCH: {
+        r = (int64_t)atomicAdd(a.ctl, 1);
+        if (r >= a.n_reads) { ts = T_EXIT; break; }
+        const int64_t ro = a.read_off[r];
+        len = (int)(a.read_off[r + 1] - ro);
+        mem = a.slots + r * a.cap; n_mem = 0; pass = 1; x = 0;
+        if (len >= MAXL) { atomicExch(a.ctl + 2, 1); a.counts[r] = 0; break; }
+        if (QS) { for (int t = 0; t < len; ++t) q_s[t] = a.bases[ro + t]; q = q_s; } else q = a.bases + ro;
+        ts = len < msl ? T_FINISH : T_NEXT;                  // src/bwa_wrapper.cpp:150
+        break;
       }
-      ++n_mem;
-    };
-    if (len >= MAXL) { atomicExch(a.ctl + 2, 1); a.counts[r] = 0; continue; }
-    if (len >= msl) {                                          // src/bwa_wrapper.cpp:150
-      // ---- passes 1 and 2 (src/bwa_wrapper.cpp:214-226): a sequence of bwt_smem1a_new(sx, mi) calls
-      int pass = 1, x = 0, k2 = 0, old_n = 0;
-      for (;;) {
-        int sx, mi;
+      case T_NEXT: {                                         // the three loops of mem_collect_intv_new (:214-243)
+        bool call = false;
         if (pass == 1) {
           while (x < len && q[x] > 3) ++x;
-          if (x >= len) { pass = 2; old_n = n_mem < a.cap ? n_mem : a.cap; continue; }
-          sx = x; mi = 1;
-        } else {
-          bool go = false;
+          if (x < len) { sx = x; mi = 1; call = true; }
+          else { pass = 2; old_n = n_mem < a.cap ? n_mem : a.cap; k2 = 0; }
+        }
+        if (pass == 2 && !call) {
           while (k2 < old_n) {
             const bwaflow_intv_t p = mem[k2++];
             const int s = (int)(p.info >> 32), e = (int)(uint32_t)p.info;
             if (e - s < a.split_len || p.x[2] > (uint64_t)a.split_width) continue;
-            sx = (s + e) >> 1; mi = (int)p.x[2] + 1; go = true;
+            if (q[(s + e) >> 1] > 3) continue;               // bwt_smem1a_new :338
+            sx = (s + e) >> 1; mi = (int)p.x[2] + 1; call = true;
             break;
           }
-          if (!go) break;
-          if (q[sx] > 3) continue;                             // bwt_smem1a_new :338
+          if (!call) { pass = 3; x = 0; }
         }
-        // ---- bwt_smem1a_new(sx, mi), src/bwa_wrapper.cpp:325-450
-        int fwd_n = 0, back_n = 0;
-        Intv ik = set_intv(ix, q[sx]);
-        int ik_end = sx + 1, i;
-        for (i = sx + 1; i < len; ++i) {                       // forward sweep :346-363
-          if (q[i] > 3) { fwd[fwd_n++] = pack_entry(ik, ik_end); break; }
-          const Intv o = extend1(ix, ik, 0, 3 - q[i], &blocks);
-          if (o.x2 != ik.x2) {
-            fwd[fwd_n++] = pack_entry(ik, ik_end);
-            if (o.x2 < (uint64_t)mi) break;
-          }
-          ik = o; ik_end = i + 1;
+        if (call) {                                          // bwt_smem1a_new entry (:338-346)
+          fwd_n = 0; back_n = 0; ik = set_intv(ix, q[sx]); cur = sx + 1; phase = PH_F;
+          if (cur < len && q[cur] < 4) { c = 3 - q[cur]; ts = T_NONE; }
+          else { push_fwd(ik, cur); ts = T_F_DONE; }
+          break;
         }
-        if (i == len) fwd[fwd_n++] = pack_entry(ik, ik_end);
-        const int ret = entry_pos(fwd[fwd_n - 1]);
-        int start = sx, stop = sx, fi = 0, cand_beg = 0, cand_end = 0;
-        Intv cand = {0, 0, 0};
-        while (fi < fwd_n) {                                   // :367-444
-          int ik_beg = sx, f_end;
-          ik = unpack_entry(fwd[fi], &f_end);
-          if (back_n == 0 || stop - start >= 3) {              // back-enlarge :371-401
-            back[0] = pack_entry(ik, 0); back_n = 1;
-            for (int kb = sx - 1; kb >= 0 && q[kb] < 4; --kb) {
-              const Intv o = extend1(ix, ik, 1, q[kb], &blocks);
-              if (o.x2 < (uint64_t)mi) break;
-              ik = o; ik_beg = kb;
-              back[back_n++] = pack_entry(ik, 0);
-            }
-            start = f_end;
-            stop = fi == fwd_n - 1 ? len : entry_pos(fwd[fi + 1]);
-            if (fi > 0 && ik_beg > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
-            cand = ik; cand_beg = ik_beg; cand_end = f_end;
-          } else {                                             // forward-enlarge :403-430
-            stop = f_end;
-            for (int bk = back_n - 1; bk >= 0; --bk) {
-              int dummy, m;
-              ik = unpack_entry(back[bk], &dummy);
-              for (m = start + 1; m <= stop; ++m) {
-                const Intv o = extend1(ix, ik, 0, 3 - q[m - 1], &blocks);
-                if (o.x2 < (uint64_t)mi) break;
-                ik = o;
-              }
-              if (m > stop) {                                  // reached the end of this forward match
-                ik_beg = sx - bk;
-                if (ik_beg > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
-                cand = ik; cand_beg = ik_beg; cand_end = f_end;
-                break;
-              }
-            }
-          }
-          ++fi;
-          if (fi < fwd_n) {                                    // :433-441
-            int max_len = cand_beg + entry_pos(fwd[fi]);
-            while (max_len < msl && fi < fwd_n) {
-              ++fi;
-              if (fi < fwd_n) stop = entry_pos(fwd[fi]);
-              max_len = cand_beg + stop;
-            }
-          }
-          if (fi >= fwd_n && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
-        }
-        if (pass == 1) x = ret;
+        // pass 3: bwt_seed_strategy1 entry (bwa/bwt.c:364-366)
+        if (a.max_mem_intv <= 0) { ts = T_FINISH; break; }
+        while (x < len && q[x] > 3) ++x;
+        if (x >= len) { ts = T_FINISH; break; }
+        px = x; ik = set_intv(ix, q[x]); cur = x + 1; phase = PH_P3;
+        if (cur >= len) { x = len; break; }                  // stays in T_NEXT
+        if (q[cur] > 3) { x = cur + 1; break; }
+        c = 3 - q[cur]; ts = T_NONE;
+        break;
       }
-      // ---- pass 3 (src/bwa_wrapper.cpp:228-243): bwt_seed_strategy1, bwa/bwt.c:358-379
-      if (a.max_mem_intv > 0) {
-        x = 0;
-        while (x < len) {
-          if (q[x] > 3) { ++x; continue; }
-          Intv ik = set_intv(ix, q[x]);
-          int i;
-          for (i = x + 1; i < len; ++i) {
-            if (q[i] > 3) { ++i; break; }
-            const Intv o = extend1(ix, ik, 0, 3 - q[i], &blocks);
-            if (o.x2 < (uint64_t)a.max_mem_intv && i - x >= msl) {
-              if (o.x2 > 0) push_mem(o, x, i + 1);
-              ++i;
-              break;
-            }
-            ik = o;
+      case T_F_DONE:                                         // :364-366
+        ret = get_end(fwd_n - 1); start = sx; stop = sx; fi = 0;
+        ts = T_B_SELECT;
+        break;
+      case T_B_SELECT: {                                     // :367-371
+        if (fi >= fwd_n) { ts = T_CALL_DONE; break; }
+        int dummy;
+        ik = unpack_entry(fwd[fi], &dummy); f_end = get_end(fi); ik_beg = sx;
+        if (back_n == 0 || stop - start >= 3) {              // back-enlarge
+          back[0] = pack_entry(ik, 0); back_n = 1; cur = sx - 1; phase = PH_BE;
+          if (cur >= 0 && q[cur] < 4) { c = q[cur]; ts = T_NONE; } else ts = T_BE_DONE;
+        } else { stop = f_end; bk = back_n - 1; ts = T_FE_PICK; }   // forward-enlarge
+        break;
+      }
+      case T_BE_DONE:                                        // :387-400
+        start = f_end; stop = fi == fwd_n - 1 ? len : get_end(fi + 1);
+        take_cand(ik_beg, fi == 0);
+        ts = T_B_NEXT;
+        break;
+      case T_FE_FAIL:
+        --bk;
+        // fall through
+      case T_FE_PICK: {                                      // :405-408
+        if (bk < 0) { ts = T_B_NEXT; break; }
+        int dummy;
+        ik = unpack_entry(back[bk], &dummy); cur = start; phase = PH_FE; c = 3 - q[cur];
+        ts = T_NONE;
+        break;
+      }
+      case T_FE_REACHED:                                     // :413-427
+        take_cand(sx - bk, false);
+        ts = T_B_NEXT;
+        break;
+      case T_B_NEXT:                                         // :431-443
+        ++fi;
+        if (fi < fwd_n) {
+          int max_len = cand_beg + get_end(fi);
+          while (max_len < msl && fi < fwd_n) {
+            ++fi;
+            if (fi < fwd_n) stop = get_end(fi);
+            max_len = cand_beg + stop;
           }
-          x = i;
         }
+        if (fi >= fwd_n && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+        ts = T_B_SELECT;
+        break;
+      case T_CALL_DONE:
+        if (pass == 1) x = ret;
+        ts = T_NEXT;
+        break;
+      case T_FINISH: {                                       // ks_introsort by info (:245); equal keys are equal elements
+        const int n = n_mem < a.cap ? n_mem : a.cap;
+        for (int u = 1; u < n; ++u) {
+          const bwaflow_intv_t v = mem[u];
+          int t = u - 1;
+          while (t >= 0 && mem[t].info > v.info) { mem[t + 1] = mem[t]; --t; }
+          mem[t + 1] = v;
+        }
+        a.counts[r] = n_mem;
+        if (n_mem > a.cap) atomicExch(a.ctl + 1, 1);
+        ts = T_FETCH;
+        break;
+      }
       }
     }
-    {                                                          // ks_introsort by info (:245); equal keys are equal elements
-      const int n = n_mem < a.cap ? n_mem : a.cap;
-      for (int u = 1; u < n; ++u) {
-        const bwaflow_intv_t v = mem[u];
-        int t = u - 1;
-        while (t >= 0 && mem[t].info > v.info) { mem[t + 1] = mem[t]; --t; }
-        mem[t + 1] = v;
+    if (__ballot_sync(full, ts == T_NONE) == 0) break;
+    if (ts == T_NONE) {
+      // ---- the one call site of bwt_extend, then the consume step of the four inner loops
+      const Intv o = extend1(ix, ik, phase == PH_BE, c, &blocks);
+      const bool small = o.x2 < (uint64_t)(phase == PH_P3 ? a.max_mem_intv : mi);
+      if (phase == PH_F) {                                   // :350-357
+        const bool changed = o.x2 != ik.x2;
+        if (changed) push_fwd(ik, cur);
+        if (changed && small) ts = T_F_DONE;
+        else {
+          ik = o; ++cur;
+          if (cur < len && q[cur] < 4) c = 3 - q[cur];
+          else { push_fwd(ik, cur); ts = T_F_DONE; }         // N or end of read (:358-363)
+        }
+      } else if (phase == PH_P3) {                           // bwa/bwt.c:367-376
+        if (small && cur - px >= msl) { if (o.x2 > 0) push_mem(o, px, cur + 1); x = cur + 1; ts = T_NEXT; }
+        else {
+          ik = o; ++cur;
+          if (cur >= len) { x = len; ts = T_NEXT; }
+          else if (q[cur] > 3) { x = cur + 1; ts = T_NEXT; }
+          else c = 3 - q[cur];
+        }
+      } else if (phase == PH_BE) {                           // :374-386
+        if (small) ts = T_BE_DONE;
+        else {
+          ik = o; ik_beg = cur; back[back_n++] = pack_entry(ik, 0); --cur;
+          if (cur >= 0 && q[cur] < 4) c = q[cur]; else ts = T_BE_DONE;
+        }
+      } else {                                               // forward-enlarge :407-417
+        if (small) ts = T_FE_FAIL;
+        else {
+          ik = o; ++cur;
+          if (cur == stop) ts = T_FE_REACHED; else c = 3 - q[cur];
+        }
       }
-      a.counts[r] = n_mem;
-      if (n_mem > a.cap) atomicExch(a.ctl + 1, 1);
     }
   }
   if (blocks) atomicAdd(a.blocks, blocks);
@@ -380,8 +434,9 @@ int bwaflow::smem_launch(bwaflow_smem_batch *b)
   a.split_width = o.split_width; a.max_mem_intv = o.max_mem_intv;
   int64_t want = (nr + 127) / 128;
   const int grid = (int)(want < b->blocks_per_launch ? want : b->blocks_per_launch);
-  if (b->max_len < 160) smem_kernel<160><<<grid, 128, 0, st>>>(a);
-  else if (b->max_len < 256) smem_kernel<256><<<grid, 128, 0, st>>>(a);
+  // dynamic shared memory: per lane one row for the read (<= 256 bases) and one for the forward-list end coordinates
+  if (b->max_len < 160) smem_kernel<160><<<grid, 128, 2 * 128 * 164, st>>>(a);
+  else if (b->max_len < 256) smem_kernel<256><<<grid, 128, 2 * 128 * 260, st>>>(a);
   else smem_kernel<1024><<<grid, 128, 0, st>>>(a);
   smem_compact_counts<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(b->d_counts, nr, b->cap, b->d_cnt64);
   size_t tmp = b->tmp_bytes;
@@ -501,7 +556,9 @@ int bwaflow_smem_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max
   BF_CUDA(cudaMallocHost(&b->h_poff, (b->out_cap + 2) * 8));
   b->pos_cap = 0; b->d_pos = 0; b->h_pos = 0;
   int per_sm = 0;
-  BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smem_kernel<256>, 128, 0));
+  BF_CUDA(cudaFuncSetAttribute(smem_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 164));
+  BF_CUDA(cudaFuncSetAttribute(smem_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 260));
+  BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smem_kernel<160>, 128, 2 * 128 * 164));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;
   if (const char *s = getenv("BWAFLOW_SMEM_BLOCKS_PER_SM")) per_sm = atoi(s) > 0 ? atoi(s) : per_sm;
