@@ -21,28 +21,34 @@ namespace bwaflow {
 
 struct Intv { uint64_t x0, x1, x2; };
 
-// Among the first n symbols of a 64-byte occ block (symbol words as u64, 32 symbols each, MSB first): how many equal
-// base c (*eq) and how many are greater than c (*gt).  POPC runs on the narrow XU pipe, so the masks of two words
-// (which only use even bit positions) are interleaved into one word before counting: 4 popcounts per call.
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, int sh)
+{ // PTX shl clamps shift amounts above 31 (result 0); C++ << would be undefined there
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(sh));
+  return r;
+}
+
+// Among the first n symbols (1..128) of a 64-byte occ block, whose 128 two-bit symbols are the eight 32-bit words
+// w[0..7] (16 symbols each, MSB first): how many equal base c (*eq) and how many are greater than c (*gt).
+// All 32-bit single-instruction logic; the per-word prefix mask is one clamped shift.  POPC runs on the narrow XU
+// pipe, so the masks of two words (which only use even bit positions) are interleaved before counting: 4+4 popcounts.
 __device__ __forceinline__ void prefix_counts(const uint4 s0, const uint4 s1, int n, int c, int *eq, int *gt)
 {
-  const uint64_t W[4] = {(uint64_t)s0.x << 32 | s0.y, (uint64_t)s0.z << 32 | s0.w,
-                         (uint64_t)s1.x << 32 | s1.y, (uint64_t)s1.z << 32 | s1.w};
-  const uint64_t ODD = 0x5555555555555555ull;
-  const uint64_t cpat = (uint64_t)c * ODD;                       // c in every 2-bit field
-  const uint64_t g_or = c == 0 ? ~0ull : 0ull, g_hi = c == 1 ? ~0ull : 0ull, g_and = c == 2 ? ~0ull : 0ull;
-  uint64_t e[4], g[4];
+  const uint32_t w[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const uint32_t ODD = 0x55555555u;
+  const uint32_t cpat = (uint32_t)c * ODD;                       // c in every 2-bit field
+  const uint32_t g_or = c == 0 ? ~0u : 0u, g_hi = c == 1 ? ~0u : 0u, g_and = c == 2 ? ~0u : 0u;
+  const int base = 32 - 2 * n;                                   // word j keeps its top 2*clamp(n-16j,0,16) bits
+  uint32_t e[8], g[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int m = n - 32 * i;                                          // symbols of this word that count
-    m = m < 0 ? 0 : (m > 32 ? 32 : m);
-    const uint64_t keep = m ? (~0ull << (64 - 2 * m)) & ODD : 0ull;
-    const uint64_t x = W[i] ^ cpat, lo = W[i], hi = W[i] >> 1;
-    e[i] = ~(x | x >> 1) & keep;
-    g[i] = (((hi | lo) & g_or) | (hi & g_hi) | (hi & lo & g_and)) & keep;
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t keep = shl_clamp(ODD, max(base + 32 * j, 0));   // even bit of every kept symbol
+    const uint32_t x = w[j] ^ cpat, lo = w[j], hi = w[j] >> 1;
+    e[j] = ~(x | x >> 1) & keep;
+    g[j] = (((hi | lo) & g_or) | (hi & g_hi) | (hi & lo & g_and)) & keep;
   }
-  *eq = __popcll(e[0] | e[1] << 1) + __popcll(e[2] | e[3] << 1);
-  *gt = __popcll(g[0] | g[1] << 1) + __popcll(g[2] | g[3] << 1);
+  *eq = __popc(e[0] | e[1] << 1) + __popc(e[2] | e[3] << 1) + __popc(e[4] | e[5] << 1) + __popc(e[6] | e[7] << 1);
+  *gt = __popc(g[0] | g[1] << 1) + __popc(g[2] | g[3] << 1) + __popc(g[4] | g[5] << 1) + __popc(g[6] | g[7] << 1);
 }
 
 __device__ __forceinline__ uint64_t hdr_count(const uint4 c0, const uint4 c1, int b)
@@ -57,41 +63,28 @@ __device__ __forceinline__ uint64_t hdr_count_gt(const uint4 c0, const uint4 c1,
   return (c < 1 ? n1 : 0) + (c < 2 ? n2 : 0) + (c < 3 ? n3 : 0);
 }
 
-// Occ of base c and of all bases > c among BWT rows [0,k]: the part of bwt_occ4 (bwa/bwt.c:169-186) that one
-// interval extension needs.  k == -1 cannot occur here (interval starts are >= 1).
-__device__ __forceinline__ void occ_eq_gt(const DevIndex &ix, uint64_t k, int c, uint64_t *eq, uint64_t *gt, unsigned long long *blocks)
-{
-  k -= (k >= ix.primary);
-  const uint4 *b = ix.bwt + ((k >> 7) << 2);
-  const uint4 c0 = __ldg(b), c1 = __ldg(b + 1), s0 = __ldg(b + 2), s1 = __ldg(b + 3);
-  int e, g;
-  prefix_counts(s0, s1, (int)(k & 127) + 1, c, &e, &g);
-  *eq = hdr_count(c0, c1, c) + (uint64_t)e;
-  *gt = hdr_count_gt(c0, c1, c) + (uint64_t)g;
-  ++*blocks;
-}
-
-// ok[c] of bwt_extend (bwa/bwt.c:262-275) for the one base c the caller wants.  The two Occ lookups share the
-// block load when both ends fall in the same 128-symbol interval (bwt_2occ4, bwa/bwt.c:189-220).
+// ok[c] of bwt_extend (bwa/bwt.c:262-275) for the one base c the caller wants: Occ of c and of all bases > c at both
+// ends of the interval (the part of bwt_2occ4, bwa/bwt.c:189-220, that is consumed).  Straight-line code so that all
+// lanes of the warp run the counting once: the second block is only re-loaded when the two ends fall in different
+// 128-symbol blocks, otherwise the registers of the first are reused.
 __device__ __forceinline__ Intv extend1(const DevIndex &ix, const Intv ik, int is_back, int c, unsigned long long *blocks)
 {
   const uint64_t xf = is_back ? ik.x0 : ik.x1, xg = is_back ? ik.x1 : ik.x0;
   const uint64_t k = xf - 1, l = xf - 1 + ik.x2;
   const uint64_t _k = k - (k >= ix.primary), _l = l - (l >= ix.primary);
-  uint64_t ek, gk, el, gl;
-  if ((_k >> 7) == (_l >> 7)) {
-    const uint4 *b = ix.bwt + ((_k >> 7) << 2);
-    const uint4 c0 = __ldg(b), c1 = __ldg(b + 1), s0 = __ldg(b + 2), s1 = __ldg(b + 3);
-    int e0, g0, e1, g1;
-    prefix_counts(s0, s1, (int)(_k & 127) + 1, c, &e0, &g0);
-    prefix_counts(s0, s1, (int)(_l & 127) + 1, c, &e1, &g1);
-    const uint64_t he = hdr_count(c0, c1, c), hg = hdr_count_gt(c0, c1, c);
-    ek = he + (uint64_t)e0; el = he + (uint64_t)e1; gk = hg + (uint64_t)g0; gl = hg + (uint64_t)g1;
-    ++*blocks;
-  } else {
-    occ_eq_gt(ix, k, c, &ek, &gk, blocks);
-    occ_eq_gt(ix, l, c, &el, &gl, blocks);
+  const uint4 *bk = ix.bwt + ((_k >> 7) << 2);
+  uint4 c0 = __ldg(bk), c1 = __ldg(bk + 1), s0 = __ldg(bk + 2), s1 = __ldg(bk + 3);
+  int e0, g0, e1, g1;
+  prefix_counts(s0, s1, (int)(_k & 127) + 1, c, &e0, &g0);
+  const uint64_t ek = hdr_count(c0, c1, c) + (uint64_t)e0, gk = hdr_count_gt(c0, c1, c) + (uint64_t)g0;
+  const bool other = (_k >> 7) != (_l >> 7);
+  if (other) {
+    const uint4 *bl = ix.bwt + ((_l >> 7) << 2);
+    c0 = __ldg(bl); c1 = __ldg(bl + 1); s0 = __ldg(bl + 2); s1 = __ldg(bl + 3);
   }
+  prefix_counts(s0, s1, (int)(_l & 127) + 1, c, &e1, &g1);
+  const uint64_t el = hdr_count(c0, c1, c) + (uint64_t)e1, gl = hdr_count_gt(c0, c1, c) + (uint64_t)g1;
+  *blocks += other ? 2 : 1;
   Intv o;
   const uint64_t acc = xg + (xf <= ix.primary && xf + ik.x2 - 1 >= ix.primary) + (gl - gk);
   const uint64_t nf = ix.L2[c] + 1 + ek;
