@@ -35,6 +35,34 @@ void fill_score(const bwaflow_opt_t &o, DevScore &s)
 
 using namespace bwaflow;
 
+// bwa layout (4 x u64 counts + 8 x u32 symbols per 128 symbols, bwa/bwt.h:72-73) -> occ32 blocks (internal.cuh).
+// Pass 1, one thread per 64-symbol block: absolute suffix counts S1,S2,S3 (symbols >0, >1, >2 before the block).
+__global__ void occ32_count_kernel(const uint32_t *bwt, uint64_t n64, uint4 *occ, uint64_t *absS)
+{
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n64) return;
+  const uint32_t *blk = bwt + (b >> 1) * 16;
+  uint64_t c1 = (uint64_t)blk[3] << 32 | blk[2], c2 = (uint64_t)blk[5] << 32 | blk[4], c3 = (uint64_t)blk[7] << 32 | blk[6];
+  const uint32_t *sym = blk + 8;
+  if (b & 1) {                                         // second half of the bwa block: add its first 64 symbols
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w = sym[j], lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+      c1 += __popc(~hi & lo & 0x55555555u); c2 += __popc(hi & ~lo); c3 += __popc(hi & lo);
+    }
+    sym += 4;
+  }
+  absS[b] = c1 + c2 + c3; absS[n64 + b] = c2 + c3; absS[2 * n64 + b] = c3;
+  occ[2 * b + 1] = make_uint4(sym[0], sym[1], sym[2], sym[3]);
+}
+// Pass 2: counts relative to the block's 2^31-symbol superblock, as u32.
+__global__ void occ32_pack_kernel(uint64_t n64, uint4 *occ, const uint64_t *absS, DevIndex ix)
+{
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n64) return;
+  const uint64_t *sb = ix.sbt + (b >> 25) * 5;
+  occ[2 * b] = make_uint4((uint32_t)(absS[b] - sb[1]), (uint32_t)(absS[n64 + b] - sb[2]), (uint32_t)(absS[2 * n64 + b] - sb[3]), 0u);
+}
+
 // dependency-free DPX issue-rate probe: 8 independent accumulator chains per thread
 template <int PACKED>
 __global__ void dpx_peak_kernel(unsigned *out, int iters, unsigned seed)
@@ -162,7 +190,7 @@ int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt
     d.sa_shift = 0; while ((1LL << d.sa_shift) < idx->sa_intv) ++d.sa_shift;
     d.l_pac = idx->l_pac; d.n_seqs = idx->n_seqs;
     // bwt_size words; pad to whole 64-byte blocks so 128-bit block loads never run off the end
-    size_t bwt_bytes = (size_t)idx->bwt_size * 4, bwt_pad = (bwt_bytes + 63) / 64 * 64 + 64;
+    size_t bwt_bytes = (size_t)idx->bwt_size * 4, bwt_pad = (bwt_bytes + 63) / 64 * 64 + 256;
     BF_CUDA(cudaMalloc(&c->d_bwt, bwt_pad));
     BF_CUDA(cudaMemset(c->d_bwt, 0, bwt_pad));
     BF_CUDA(cudaMemcpy(c->d_bwt, idx->bwt, bwt_bytes, cudaMemcpyHostToDevice));
@@ -170,7 +198,30 @@ int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt
     if ((r = upload(&c->d_pac, idx->pac, (size_t)(idx->l_pac / 4 + 1)))) return r;
     if ((r = upload(&c->d_ctg_off, idx->ctg_offset, (size_t)idx->n_seqs * 8))) return r;
     if ((r = upload(&c->d_ctg_len, idx->ctg_len, (size_t)idx->n_seqs * 4))) return r;
-    d.bwt = (const uint4 *)c->d_bwt; d.sa = (const uint64_t *)c->d_sa; d.pac = (const uint8_t *)c->d_pac;
+    {
+      // re-lay the occurrence array out for the device (occ32), then drop the upload of bwa's layout
+      const uint64_t n64 = (idx->seq_len + 63) / 64 + 1;
+      BF_REQUIRE(n64 <= (8ull << 25), -22, "reference too long for the superblock table (max 2^34 BWT symbols)");
+      uint4 *d_occ = 0; uint64_t *d_abs = 0;
+      BF_CUDA(cudaMalloc(&d_occ, (n64 + 2) * 32));
+      BF_CUDA(cudaMemset(d_occ, 0, (n64 + 2) * 32));
+      BF_CUDA(cudaMalloc(&d_abs, 3 * n64 * 8));
+      occ32_count_kernel<<<(unsigned)((n64 + 255) / 256), 256>>>((const uint32_t *)c->d_bwt, n64, d_occ, d_abs);
+      BF_CUDA(cudaGetLastError());
+      memset(d.sbt, 0, sizeof(d.sbt));
+      for (uint64_t j = 0; (j << 25) < n64; ++j) {
+        d.sbt[j * 5 + 0] = j << 31;
+        for (int t = 0; t < 3; ++t)
+          BF_CUDA(cudaMemcpy(&d.sbt[j * 5 + 1 + t], d_abs + t * n64 + (j << 25), 8, cudaMemcpyDeviceToHost));
+      }
+      occ32_pack_kernel<<<(unsigned)((n64 + 255) / 256), 256>>>(n64, d_occ, d_abs, d);
+      BF_CUDA(cudaGetLastError());
+      BF_CUDA(cudaDeviceSynchronize());
+      cudaFree(d_abs); cudaFree(c->d_bwt);
+      c->d_bwt = d_occ;
+      d.occ = d_occ;
+    }
+    d.sa = (const uint64_t *)c->d_sa; d.pac = (const uint8_t *)c->d_pac;
     d.ctg_offset = (const int64_t *)c->d_ctg_off; d.ctg_len = (const int32_t *)c->d_ctg_len;
     c->has_index = true;
   }

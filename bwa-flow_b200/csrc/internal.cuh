@@ -31,7 +31,12 @@ void set_error(const char *fmt, ...);
 struct DevIndex {
   uint64_t primary, seq_len;
   uint64_t L2[5];
-  const uint4 *bwt;        // occ-interleaved BWT viewed as 16-byte quarters of the 64-byte blocks
+  // Device-side occurrence array ("occ32"): one 32-byte block per 64 BWT symbols =
+  //   u32 S1,S2,S3 (symbols >0, >1, >2 before the block, relative to its 2^31-symbol superblock), u32 pad, 64 two-bit symbols.
+  // Same information as bwa's 64-byte/128-symbol blocks (bwa/bwt.h:72-73), re-laid out at upload: one 32-byte sector per
+  // lookup and half the symbols to count.  sbt[j*5+t] = absolute count of symbols >= t before superblock j (t=0: its start).
+  const uint4 *occ;
+  uint64_t sbt[8 * 5];
   const uint64_t *sa;
   int sa_shift;            // log2(sa_intv)
   int64_t l_pac;

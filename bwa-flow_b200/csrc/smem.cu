@@ -6,7 +6,8 @@
 // slot is detected on the device and the batch is re-run with larger slots.
 //
 // The FM-index (occ-interleaved BWT, 64-byte blocks = 4 x u64 counts + 128 two-bit symbols,
-// bwa/bwt.h:72-73) is resident in HBM; an occurrence lookup is four 128-bit loads of one block.
+// bwa/bwt.h:72-73) is re-laid out at upload into 32-byte blocks of 64 symbols (internal.cuh); an occurrence lookup is
+// two 128-bit loads of one aligned 32-byte sector.
 // Seeding is a chain of dependent random block reads, so the kernel keeps one read per lane and many
 // lanes in flight, and the irregular control flow of bwt_smem1a_new is written as a per-lane flow
 // machine whose ONLY expensive operation -- bwt_extend (bwa/bwt.c:262-275) -- sits at one convergent
@@ -28,63 +29,60 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, int sh)
   return r;
 }
 
-// Among the first n symbols (1..128) of a 64-byte occ block, whose 128 two-bit symbols are the eight 32-bit words
-// w[0..7] (16 symbols each, MSB first): how many equal base c (*eq) and how many are greater than c (*gt).
-// All 32-bit single-instruction logic; the per-word prefix mask is one clamped shift.  POPC runs on the narrow XU
-// pipe, so the masks of two words (which only use even bit positions) are interleaved before counting: 4+4 popcounts.
-__device__ __forceinline__ void prefix_counts(const uint4 s0, const uint4 s1, int n, int c, int *eq, int *gt)
+// Among the first n symbols (1..64) of an occ32 block, whose 64 two-bit symbols are the four 32-bit words of `sy`
+// (16 symbols each, MSB first): how many equal base c (*eq) and how many are greater than c (*gt).  32-bit
+// single-instruction logic; the per-word prefix mask is one clamped shift.  POPC runs on the narrow XU pipe, so the
+// masks of two words (which only use even bit positions) are interleaved before counting: 2+2 popcounts.
+__device__ __forceinline__ void prefix_counts(const uint4 sy, int n, int c, int *eq, int *gt)
 {
-  const uint32_t w[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const uint32_t w[4] = {sy.x, sy.y, sy.z, sy.w};
   const uint32_t ODD = 0x55555555u;
   const uint32_t cpat = (uint32_t)c * ODD;                       // c in every 2-bit field
   const uint32_t g_or = c == 0 ? ~0u : 0u, g_hi = c == 1 ? ~0u : 0u, g_and = c == 2 ? ~0u : 0u;
   const int base = 32 - 2 * n;                                   // word j keeps its top 2*clamp(n-16j,0,16) bits
-  uint32_t e[8], g[8];
+  uint32_t e[4], g[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
     const uint32_t keep = shl_clamp(ODD, max(base + 32 * j, 0));   // even bit of every kept symbol
     const uint32_t x = w[j] ^ cpat, lo = w[j], hi = w[j] >> 1;
     e[j] = ~(x | x >> 1) & keep;
     g[j] = (((hi | lo) & g_or) | (hi & g_hi) | (hi & lo & g_and)) & keep;
   }
-  *eq = __popc(e[0] | e[1] << 1) + __popc(e[2] | e[3] << 1) + __popc(e[4] | e[5] << 1) + __popc(e[6] | e[7] << 1);
-  *gt = __popc(g[0] | g[1] << 1) + __popc(g[2] | g[3] << 1) + __popc(g[4] | g[5] << 1) + __popc(g[6] | g[7] << 1);
+  *eq = __popc(e[0] | e[1] << 1) + __popc(e[2] | e[3] << 1);
+  *gt = __popc(g[0] | g[1] << 1) + __popc(g[2] | g[3] << 1);
 }
 
-__device__ __forceinline__ uint64_t hdr_count(const uint4 c0, const uint4 c1, int b)
-{ // running count of base b stored at the head of the block (4 x u64)
-  const uint32_t lo = b == 0 ? c0.x : b == 1 ? c0.z : b == 2 ? c1.x : c1.z;
-  const uint32_t hi = b == 0 ? c0.y : b == 1 ? c0.w : b == 2 ? c1.y : c1.w;
-  return (uint64_t)hi << 32 | lo;
-}
-__device__ __forceinline__ uint64_t hdr_count_gt(const uint4 c0, const uint4 c1, int c)
-{ // sum of the running counts of all bases greater than c
-  const uint64_t n1 = (uint64_t)c0.w << 32 | c0.z, n2 = (uint64_t)c1.y << 32 | c1.x, n3 = (uint64_t)c1.w << 32 | c1.z;
-  return (c < 1 ? n1 : 0) + (c < 2 ? n2 : 0) + (c < 3 ? n3 : 0);
+// Occ(c, k) and Occ(>c, k) over BWT rows [0, k] (k already adjusted for the '$' row): one 32-byte occ32 block.
+// Header S1,S2,S3 = symbols >0,>1,>2 before the block (relative to its superblock); S0 = the block start, S4 = 0:
+//   Occ(>c) = S[c+1] + gt,   Occ(c) = S[c] - S[c+1] + eq.
+__device__ __forceinline__ void occ_eq_gt(const DevIndex &ix, uint64_t k, int c, uint64_t *eq, uint64_t *gt)
+{
+  const uint4 *b = ix.occ + ((k >> 6) << 1);
+  const uint4 hd = __ldg(b), sy = __ldg(b + 1);
+  int e, g;
+  prefix_counts(sy, (int)(k & 63) + 1, c, &e, &g);
+  const uint64_t *sb = ix.sbt + (k >> 31) * 5;
+  const uint32_t r0 = (uint32_t)(k & 0x7fffffffull) & ~63u;    // block start relative to the superblock
+  const uint32_t lo_rel = c == 0 ? r0 : c == 1 ? hd.x : c == 2 ? hd.y : hd.z;        // S[c]
+  const uint32_t hi_rel = c == 0 ? hd.x : c == 1 ? hd.y : c == 2 ? hd.z : 0u;        // S[c+1]
+  const uint64_t Sc = sb[c] + lo_rel, Sc1 = sb[c + 1] + hi_rel;
+  *gt = Sc1 + (uint64_t)g;
+  *eq = Sc - Sc1 + (uint64_t)e;
 }
 
 // ok[c] of bwt_extend (bwa/bwt.c:262-275) for the one base c the caller wants: Occ of c and of all bases > c at both
-// ends of the interval (the part of bwt_2occ4, bwa/bwt.c:189-220, that is consumed).  Straight-line code so that all
-// lanes of the warp run the counting once: the second block is only re-loaded when the two ends fall in different
-// 128-symbol blocks, otherwise the registers of the first are reused.
+// ends of the interval (the part of bwt_2occ4, bwa/bwt.c:189-220, that is consumed).  Straight-line code: all lanes of
+// the warp run the two lookups together.  `blocks` counts touches of the REFERENCE's 64-byte blocks (the algorithmic
+// unit of SURVEY 8d: one if both ends share a 128-symbol block, else two), not of our 32-byte device blocks.
 __device__ __forceinline__ Intv extend1(const DevIndex &ix, const Intv ik, int is_back, int c, unsigned long long *blocks)
 {
   const uint64_t xf = is_back ? ik.x0 : ik.x1, xg = is_back ? ik.x1 : ik.x0;
   const uint64_t k = xf - 1, l = xf - 1 + ik.x2;
   const uint64_t _k = k - (k >= ix.primary), _l = l - (l >= ix.primary);
-  const uint4 *bk = ix.bwt + ((_k >> 7) << 2);
-  uint4 c0 = __ldg(bk), c1 = __ldg(bk + 1), s0 = __ldg(bk + 2), s1 = __ldg(bk + 3);
-  int e0, g0, e1, g1;
-  prefix_counts(s0, s1, (int)(_k & 127) + 1, c, &e0, &g0);
-  const uint64_t ek = hdr_count(c0, c1, c) + (uint64_t)e0, gk = hdr_count_gt(c0, c1, c) + (uint64_t)g0;
-  const bool other = (_k >> 7) != (_l >> 7);
-  if (other) {
-    const uint4 *bl = ix.bwt + ((_l >> 7) << 2);
-    c0 = __ldg(bl); c1 = __ldg(bl + 1); s0 = __ldg(bl + 2); s1 = __ldg(bl + 3);
-  }
-  prefix_counts(s0, s1, (int)(_l & 127) + 1, c, &e1, &g1);
-  const uint64_t el = hdr_count(c0, c1, c) + (uint64_t)e1, gl = hdr_count_gt(c0, c1, c) + (uint64_t)g1;
-  *blocks += other ? 2 : 1;
+  uint64_t ek, gk, el, gl;
+  occ_eq_gt(ix, _k, c, &ek, &gk);
+  occ_eq_gt(ix, _l, c, &el, &gl);
+  *blocks += (_k >> 7) != (_l >> 7) ? 2 : 1;
   Intv o;
   const uint64_t acc = xg + (xf <= ix.primary && xf + ik.x2 - 1 >= ix.primary) + (gl - gk);
   const uint64_t nf = ix.L2[c] + 1 + ek;
@@ -325,7 +323,7 @@ __global__ void __launch_bounds__(128) smem_kernel(const SmemArgs a)
 
 // ---- SA -----------------------------------------------------------------------------------------
 
-// bwt_sa, bwa/bwt.c:86-96 with bwt_invPsi :53-59 (symbol and its Occ come from the same block)
+// bwt_sa, bwa/bwt.c:86-96 with bwt_invPsi :53-59 (symbol and its Occ come from the same occ32 block)
 __device__ __forceinline__ uint64_t sa_lookup(const DevIndex &ix, uint64_t k, unsigned long long *blocks)
 {
   uint64_t steps = 0;
@@ -334,17 +332,18 @@ __device__ __forceinline__ uint64_t sa_lookup(const DevIndex &ix, uint64_t k, un
     ++steps;
     if (k == ix.primary) { k = 0; continue; }
     const uint64_t x = k - (k > ix.primary);
-    const uint4 *b = ix.bwt + ((x >> 7) << 2);
-    const uint4 c0 = __ldg(b), c1 = __ldg(b + 1), s0 = __ldg(b + 2), s1 = __ldg(b + 3);
-    const int r = (int)(x & 127);
-    const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    uint32_t word = 0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) word = (r >> 4) == t ? sw[t] : word;
+    const uint4 *b = ix.occ + ((x >> 6) << 1);
+    const uint4 hd = __ldg(b), sy = __ldg(b + 1);
+    const int r = (int)(x & 63);
+    const uint32_t word = (r >> 4) == 0 ? sy.x : (r >> 4) == 1 ? sy.y : (r >> 4) == 2 ? sy.z : sy.w;
     const int c = (word >> ((~r & 15) << 1)) & 3;
     int e, g;
-    prefix_counts(s0, s1, r + 1, c, &e, &g);
-    k = ix.L2[c] + hdr_count(c0, c1, c) + (uint64_t)e;
+    prefix_counts(sy, r + 1, c, &e, &g);
+    const uint64_t *sb = ix.sbt + (x >> 31) * 5;
+    const uint32_t r0 = (uint32_t)(x & 0x7fffffffull) & ~63u;
+    const uint32_t lo_rel = c == 0 ? r0 : c == 1 ? hd.x : c == 2 ? hd.y : hd.z;
+    const uint32_t hi_rel = c == 0 ? hd.x : c == 1 ? hd.y : c == 2 ? hd.z : 0u;
+    k = ix.L2[c] + (sb[c] + lo_rel) - (sb[c + 1] + hi_rel) + (uint64_t)e;
     ++*blocks;
   }
   return steps + ix.sa[k >> ix.sa_shift];
