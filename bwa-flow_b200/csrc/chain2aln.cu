@@ -122,8 +122,8 @@ __global__ void c2a_gather_seeds(const bwaflow_seed_t *seeds, const uint32_t *va
   if (i < n) out[i] = seeds[vals[i]];
 }
 
-__global__ void c2a_read_prep(const int64_t *read_off, const int64_t *chain_off, const int64_t *sbase, int64_t n_reads,
-                              uint32_t *keys, uint32_t *vals, int *hist, int *err)
+__global__ void c2a_read_prep(const int64_t *read_off, const int64_t *chain_off, const int64_t *sbase, const bwaflow_seed_t *sseeds,
+                              int64_t n_reads, uint32_t *keys, uint32_t *vals, int *hist, int *err)
 {
   __shared__ int sh[C2A_NCLASS];
   if (threadIdx.x < C2A_NCLASS) sh[threadIdx.x] = 0;
@@ -134,9 +134,13 @@ __global__ void c2a_read_prep(const int64_t *read_off, const int64_t *chain_off,
     int c = 0;
     while (c < C2A_NCLASS - 1 && lq > c_c2a_qmax[c]) ++c;
     if (lq > c_c2a_qmax[C2A_NCLASS - 1]) atomicExch(err, 1);
-    int64_t est = sbase[chain_off[r + 1]] - sbase[chain_off[r]];
-    est = est > 0xFFFFFF ? 0xFFFFFF : est;
-    keys[r] = (uint32_t)c << 24 | (uint32_t)est;
+    // queue order inside a class: reads with many seeds first (longest-processing-time first), and among equals the
+    // ones whose first extension has a similar left-flank length next to each other, so that the lanes of a warp
+    // walk rows of similar width
+    int64_t ns = sbase[chain_off[r + 1]] - sbase[chain_off[r]];
+    const int flank = ns > 0 ? sseeds[sbase[chain_off[r]]].qbeg : 0;
+    ns = ns > 0xFFF ? 0xFFF : ns;
+    keys[r] = (uint32_t)c << 24 | (uint32_t)ns << 12 | (uint32_t)(flank & 0xFFF);
     vals[r] = (uint32_t)r;
     atomicAdd(&sh[c], 1);
   }
@@ -379,7 +383,7 @@ int bwaflow::c2a_launch(bwaflow_c2a_batch *b)
     }
   }
   // read queue
-  c2a_read_prep<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(b->d_read_off, b->d_chain_off, b->d_sbase, nr, b->d_rkeys[0], b->d_rvals[0], hist, err);
+  c2a_read_prep<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(b->d_read_off, b->d_chain_off, b->d_sbase, b->d_sseeds, nr, b->d_rkeys[0], b->d_rvals[0], hist, err);
   cub::DoubleBuffer<uint32_t> rk(b->d_rkeys[0], b->d_rkeys[1]), rv(b->d_rvals[0], b->d_rvals[1]);
   tmp = b->tmp_bytes;
   BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(b->d_tmp, tmp, rk, rv, (int)nr, 0, 27, st));
