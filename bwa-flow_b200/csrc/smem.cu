@@ -131,21 +131,26 @@ enum { PH_F = 0, PH_BE = 1, PH_FE = 2, PH_P3 = 3 };
 enum { T_NONE = 0, T_FETCH, T_NEXT, T_F_DONE, T_B_SELECT, T_BE_DONE, T_FE_PICK, T_FE_FAIL, T_FE_REACHED, T_B_NEXT, T_CALL_DONE,
        T_FINISH, T_EXIT };
 
+#ifndef SMEM_MIN_BLOCKS
+#define SMEM_MIN_BLOCKS 6
+#endif
+constexpr int SMEM_FEND = 64;   // forward-list end coordinates kept in shared memory; later entries read their local-memory copy
+
 template <int MAXL>
-__global__ void __launch_bounds__(128) smem_kernel(const SmemArgs a)
+__global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_kernel(const SmemArgs a)
 {
   constexpr int QROW = MAXL + 4;                 // bytes per lane for the read (odd word count: conflict-free rows)
   constexpr bool QS = MAXL <= 256;               // longer reads stay in global memory
   extern __shared__ uint8_t s_mem[];
   uint8_t *q_s = s_mem + (size_t)threadIdx.x * QROW;
-  uint8_t *fend = s_mem + (QS ? (size_t)blockDim.x * QROW : 0) + (size_t)threadIdx.x * QROW;   // forward-list end coordinates (u8/u16)
+  uint8_t *fend = s_mem + (QS ? (size_t)blockDim.x * QROW : 0) + (size_t)threadIdx.x * SMEM_FEND;   // forward-list end coordinates
   uint4 fwd[MAXL], back[MAXL];
   const DevIndex &ix = a.ix;
   const unsigned full = 0xffffffffu;
   const int msl = a.min_seed_len;
   unsigned long long blocks = 0;
   // end coordinate of forward-list entry k: a byte in shared memory for reads <= 256, else the entry's own field
-  auto get_end = [&](int k) -> int { return QS ? (int)fend[k] : entry_pos(fwd[k]); };
+  auto get_end = [&](int k) -> int { return QS && k < SMEM_FEND ? (int)fend[k] : entry_pos(fwd[k]); };
 
   int ts = T_FETCH;                              // transition state; T_NONE = an extension is pending
   int64_t r = -1; int len = 0; const uint8_t *q = nullptr; bwaflow_intv_t *mem = nullptr; int n_mem = 0;
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(128) smem_kernel(const SmemArgs a)
     }
     ++n_mem;
   };
-  auto push_fwd = [&](const Intv &v, int end) { fwd[fwd_n] = pack_entry(v, end); if (QS) fend[fwd_n] = (uint8_t)end; ++fwd_n; };
+  auto push_fwd = [&](const Intv &v, int end) { fwd[fwd_n] = pack_entry(v, end); if (QS && fwd_n < SMEM_FEND) fend[fwd_n] = (uint8_t)end; ++fwd_n; };
   auto take_cand = [&](int beg, bool first) {   // src/bwa_wrapper.cpp:392-400 / 418-427
     if (!first && beg > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
     cand = ik; cand_beg = beg; cand_end = f_end;
@@ -427,8 +432,8 @@ int bwaflow::smem_launch(bwaflow_smem_batch *b)
   int64_t want = (nr + 127) / 128;
   const int grid = (int)(want < b->blocks_per_launch ? want : b->blocks_per_launch);
   // dynamic shared memory: per lane one row for the read (<= 256 bases) and one for the forward-list end coordinates
-  if (b->max_len < 160) smem_kernel<160><<<grid, 128, 2 * 128 * 164, st>>>(a);
-  else if (b->max_len < 256) smem_kernel<256><<<grid, 128, 2 * 128 * 260, st>>>(a);
+  if (b->max_len < 160) smem_kernel<160><<<grid, 128, 128 * (164 + SMEM_FEND), st>>>(a);
+  else if (b->max_len < 256) smem_kernel<256><<<grid, 128, 128 * (260 + SMEM_FEND), st>>>(a);
   else smem_kernel<1024><<<grid, 128, 0, st>>>(a);
   smem_compact_counts<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(b->d_counts, nr, b->cap, b->d_cnt64);
   size_t tmp = b->tmp_bytes;
@@ -548,9 +553,9 @@ int bwaflow_smem_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max
   BF_CUDA(cudaMallocHost(&b->h_poff, (b->out_cap + 2) * 8));
   b->pos_cap = 0; b->d_pos = 0; b->h_pos = 0;
   int per_sm = 0;
-  BF_CUDA(cudaFuncSetAttribute(smem_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 164));
-  BF_CUDA(cudaFuncSetAttribute(smem_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 260));
-  BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smem_kernel<160>, 128, 2 * 128 * 164));
+  BF_CUDA(cudaFuncSetAttribute(smem_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (164 + SMEM_FEND)));
+  BF_CUDA(cudaFuncSetAttribute(smem_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (260 + SMEM_FEND)));
+  BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smem_kernel<160>, 128, 128 * (164 + SMEM_FEND)));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;
   if (const char *s = getenv("BWAFLOW_SMEM_BLOCKS_PER_SM")) per_sm = atoi(s) > 0 ? atoi(s) : per_sm;
