@@ -46,10 +46,9 @@ __global__ void ext_key_kernel(const bwaflow_ext_job_t *jobs, int64_t n, uint32_
     int c = 0;
     while (c < EXT_NCLASS - 1 && qlen > c_ext_qmax[c]) ++c;
     if (qlen > c_ext_qmax[EXT_NCLASS - 1] || qlen < 0 || tlen < 0) { atomicExch(err, 1); }
-    // rows are at most tlen, columns per row at most min(qlen, 2w+1): a cheap upper bound of the cell count
-    int64_t est = (int64_t)qlen * tlen;
-    if (est > 0xFFFFFF) est = 0xFFFFFF;
-    keys[i] = (uint32_t)c << 24 | (uint32_t)est;
+    // queue order inside a class: widest rows first (qlen), then most rows (tlen): the lanes of a warp then walk rows of
+    // the same width and finish at about the same time
+    keys[i] = (uint32_t)c << 24 | (uint32_t)(qlen & 0x3FF) << 14 | (uint32_t)(tlen > 0x3FFF ? 0x3FFF : tlen);
     vals[i] = (uint32_t)i;
     atomicAdd(&sh[c], 1);
   }

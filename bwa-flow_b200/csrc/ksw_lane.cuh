@@ -5,24 +5,29 @@
 // Row state lives in shared memory, one 32-bit word per (column, thread), laid out [column][thread] so
 // that a warp's accesses hit 32 distinct banks whatever column each lane is at:
 //     bits  0..13  H(i-1, j-1)      (eh[j].h of the reference)
-//     bits 14..27  E(i, j)          (eh[j].e)
-//     bits 28..30  query base j     (0..3, 4 = N)   -- folded in so a cell needs a single LDS
+//     bits 14..16  query base j     (0..3, 4 = N)   -- folded in so a cell needs a single LDS
+//     bits 17..30  E(i, j)          (eh[j].e)
 // Scores therefore must stay below 2^14; begin() reports jobs that could exceed it (h0 + qlen*max_mat).
 //
 // Arithmetic is int32 on the DPX paths: VIMNMX3 for h = max(M,e,f) and VIADDMNMX.RELU for
 // e' = max(e-e_del, M-oe_del, 0), f' likewise.  The row maximum and "last column attaining it"
-// (ksw.c:437-438) are tracked as one key (h<<16 | j) under a plain max.
+// (ksw.c:437-438) are tracked as one key (h<<16 | j) under a plain max.  The substitution score comes from a
+// byte permute of the target row of the matrix held in two registers as BIASED bytes (score + 128), so that the
+// selector is just the query base (no sign-replication nibbles): decode + score + pack cost 7 instructions.
 #pragma once
 #include "internal.cuh"
 
 namespace bwaflow {
 
 constexpr uint32_t KSW_HMASK = (1u << 14) - 1;
-constexpr uint32_t KSW_HEMASK = (1u << 28) - 1;
-constexpr uint32_t KSW_QMASK = 0xF0000000u;
+constexpr uint32_t KSW_QMASK = 7u << 14;
+constexpr uint32_t KSW_HEMASK = ~KSW_QMASK & 0x7FFFFFFFu;      // H and E fields
+constexpr int KSW_ESHIFT = 17;
 constexpr int KSW_MAX_SCORE = (1 << 14) - 1;
+constexpr int KSW_BIAS = 128;                                   // matrix bytes are stored as score + 128
 
-__device__ __forceinline__ int prmt_sx(uint32_t lo, uint32_t hi, uint32_t sel)
+// byte `sel & 7` of {hi:lo} into the low byte, the other three bytes taken from hi's bytes 1..3 (which are zero)
+__device__ __forceinline__ int prmt_byte(uint32_t lo, uint32_t hi, uint32_t sel)
 {
   int r;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel));
@@ -56,7 +61,7 @@ struct KswLane {
     uint32_t *p = col;
     int hv = h0;                                         // H(-1,-1)
     for (int j = 0; j < qlen; ++j, p += stride) {
-      *p = (uint32_t)qf(j) << 28 | (uint32_t)hv;
+      *p = (uint32_t)qf(j) << 14 | (uint32_t)hv;
       hv = h0 - gi - j * sc.e_ins;                       // H(-1, j)
       hv = hv > 0 ? hv : 0;
     }
@@ -78,15 +83,15 @@ struct KswLane {
     uint32_t *p = col + lo * stride;
     for (int j = lo; j < hi; ++j, p += stride) {
       const uint32_t wv = *p;
-      const int s = prmt_sx(rlo, rhi, (wv >> 28) * 0x1111u + 0x8880u);
+      const int sb = prmt_byte(rlo, rhi, ((wv >> 14) & 7u) | 0x7650u);       // biased score of (target row, query base)
       const int hd = (int)(wv & KSW_HMASK);
-      const int e = (int)((wv >> 14) & KSW_HMASK);
-      const int M = hd ? hd + s : 0;
+      const int e = (int)(wv >> KSW_ESHIFT);
+      const int M = hd ? hd + sb - KSW_BIAS : 0;
       const int h = __vimax3_s32(M, e, f);
       const int e2 = __viaddmax_s32_relu(M, -gd, e - sc.e_del);
       f = __viaddmax_s32_relu(M, -gi, f - sc.e_ins);
       mkey = max(mkey, (h << 16) | j);
-      *p = (wv & KSW_QMASK) | (uint32_t)(e2 << 14) | (uint32_t)left;
+      *p = ((wv & KSW_QMASK) | (uint32_t)left) + ((uint32_t)e2 << KSW_ESHIFT);
       left = h;
     }
     const int jend = lo < hi ? hi : lo;
