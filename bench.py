@@ -193,7 +193,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = args.cpu_sample_pairs or min(n_pairs, 50_000)
+        sample = args.cpu_sample_pairs or n_pairs
         R, one_pass, cores = run_reference_cpu(args, ref, reads, sample)
         for _ in range(min(args.warmup, 1)):
             one_pass()
@@ -336,7 +336,7 @@ def main():
                        "n_seeds": parts[-1].n_seeds, "n_regs": n_regs},
             "seedpos_gbs": blocks_pos * 64 / (k_pos * 1e-3) / 1e9 if k_pos > 0 else None}
     if world == 1 and not args.no_cpu_baseline:
-        sample = args.cpu_sample_pairs or min(n_pairs, 50_000)
+        sample = args.cpu_sample_pairs or n_pairs
         R, one_pass, cores = run_reference_cpu(args, ref, reads, sample, built=built)
         sec = one_pass()
         line["cpu_baseline"] = {"value": sample / sec, "unit": "pairs/s", "cores": cores, "kind": "reference",

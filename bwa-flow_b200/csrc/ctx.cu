@@ -23,11 +23,11 @@ void fill_score(const bwaflow_opt_t &o, DevScore &s)
   s.o_del = o.o_del; s.e_del = o.e_del; s.o_ins = o.o_ins; s.e_ins = o.e_ins; s.zdrop = o.zdrop;
   s.smax = 0;
   for (int i = 0; i < 25; ++i) if (o.mat[i] > s.smax) s.smax = o.mat[i];
-  for (int t = 0; t < 5; ++t) {                          // biased bytes (score + 128), see ksw_lane.cuh
+  for (int t = 0; t < 5; ++t) {
     uint32_t lo = 0;
-    for (int q = 0; q < 4; ++q) lo |= (uint32_t)(uint8_t)(o.mat[t * 5 + q] + 128) << (8 * q);
+    for (int q = 0; q < 4; ++q) lo |= (uint32_t)(uint8_t)o.mat[t * 5 + q] << (8 * q);
     s.row_lo[t] = lo;
-    s.row_hi[t] = (uint32_t)(uint8_t)(o.mat[t * 5 + 4] + 128);
+    s.row_hi[t] = (uint32_t)(uint8_t)o.mat[t * 5 + 4];
   }
 }
 

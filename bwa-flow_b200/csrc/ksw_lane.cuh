@@ -12,8 +12,7 @@
 // Arithmetic is int32 on the DPX paths: VIMNMX3 for h = max(M,e,f) and VIADDMNMX.RELU for
 // e' = max(e-e_del, M-oe_del, 0), f' likewise.  The row maximum and "last column attaining it"
 // (ksw.c:437-438) are tracked as one key (h<<16 | j) under a plain max.  The substitution score comes from a
-// byte permute of the target row of the matrix held in two registers as BIASED bytes (score + 128), so that the
-// selector is just the query base (no sign-replication nibbles): decode + score + pack cost 7 instructions.
+// sign-extending byte permute of the target row of the matrix held in two registers.
 #pragma once
 #include "internal.cuh"
 
@@ -24,13 +23,21 @@ constexpr uint32_t KSW_QMASK = 7u << 14;
 constexpr uint32_t KSW_HEMASK = ~KSW_QMASK & 0x7FFFFFFFu;      // H and E fields
 constexpr int KSW_ESHIFT = 17;
 constexpr int KSW_MAX_SCORE = (1 << 14) - 1;
-constexpr int KSW_BIAS = 128;                                   // matrix bytes are stored as score + 128
 
-// byte `sel & 7` of {hi:lo} into the low byte, the other three bytes taken from hi's bytes 1..3 (which are zero)
-__device__ __forceinline__ int prmt_byte(uint32_t lo, uint32_t hi, uint32_t sel)
+// byte q of {hi:lo} sign-extended to 32 bits: selector nibbles q, q|8, q|8, q|8 (msb of a nibble = replicate the sign)
+__device__ __forceinline__ int prmt_sx(uint32_t lo, uint32_t hi, uint32_t sel)
 {
   int r;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel));
+  return r;
+}
+// The integer ALU pipe (LOP3/SHF/PRMT and the DPX min/max forms) is what saturates in the cell loop, so shifts and adds
+// are expressed as multiply-adds, which issue on the FMA pipe.
+__device__ __forceinline__ uint32_t shr_fma(uint32_t v, int sh) { return __umulhi(v, 1u << (32 - sh)); }   // v >> sh
+__device__ __forceinline__ int add_fma(int a, int b)
+{
+  int r;
+  asm("mad.lo.s32 %0, %1, 1, %2;" : "=r"(r) : "r"(a), "r"(b));
   return r;
 }
 
@@ -83,15 +90,17 @@ struct KswLane {
     uint32_t *p = col + lo * stride;
     for (int j = lo; j < hi; ++j, p += stride) {
       const uint32_t wv = *p;
-      const int sb = prmt_byte(rlo, rhi, ((wv >> 14) & 7u) | 0x7650u);       // biased score of (target row, query base)
+      const int s = prmt_sx(rlo, rhi, (shr_fma(wv, 14) & 7u) * 0x1111u + 0x8880u);   // score of (target row, query base)
       const int hd = (int)(wv & KSW_HMASK);
-      const int e = (int)(wv >> KSW_ESHIFT);
-      const int M = hd ? hd + sb - KSW_BIAS : 0;
+      const int e = (int)shr_fma(wv, KSW_ESHIFT);
+      // M = hd ? hd + s : 0 (ksw.c:433).  Any M <= 0 is equivalent to 0 below (e, f >= 0 and the relu), and
+      // min(hd + s, 128*hd) is <= 0 when hd == 0 and equals hd + s otherwise (|s| <= 127): one DPX op, no compare/select
+      const int M = __viaddmin_s32(hd, s, hd * 128);
       const int h = __vimax3_s32(M, e, f);
-      const int e2 = __viaddmax_s32_relu(M, -gd, e - sc.e_del);
-      f = __viaddmax_s32_relu(M, -gi, f - sc.e_ins);
-      mkey = max(mkey, (h << 16) | j);
-      *p = ((wv & KSW_QMASK) | (uint32_t)left) + ((uint32_t)e2 << KSW_ESHIFT);
+      const int e2 = __viaddmax_s32_relu(M, -gd, add_fma(e, -sc.e_del));
+      f = __viaddmax_s32_relu(M, -gi, add_fma(f, -sc.e_ins));
+      mkey = max(mkey, h * 65536 + j);
+      *p = ((wv & KSW_QMASK) | (uint32_t)left) + (uint32_t)e2 * (1u << KSW_ESHIFT);
       left = h;
     }
     const int jend = lo < hi ? hi : lo;
