@@ -100,7 +100,7 @@ struct SmemArgs {
   const uint8_t *bases; const int64_t *read_off; int64_t n_reads;
   bwaflow_intv_t *slots; int cap;            // per-read output slot of `cap` intervals
   int *counts;                               // per-read interval count (or cap+1 on overflow)
-  int *ctl;                                  // [0] queue head, [1] overflow flag, [2] too-long flag
+  int *ctl;                                  // [0] queue head, [1] overflow flag, [2] too-long flag, [3] pass-3 queue head
   unsigned long long *blocks;                // occ-block touches (64 B each)
   DevIndex ix;
   int min_seed_len, split_len, split_width, max_mem_intv;
@@ -211,14 +211,7 @@ __global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_k
           else { push_fwd(ik, cur); ts = T_F_DONE; }
           break;
         }
-        // pass 3: bwt_seed_strategy1 entry (bwa/bwt.c:364-366)
-        if (a.max_mem_intv <= 0) { ts = T_FINISH; break; }
-        while (x < len && q[x] > 3) ++x;
-        if (x >= len) { ts = T_FINISH; break; }
-        px = x; ik = set_intv(ix, q[x]); cur = x + 1; phase = PH_P3;
-        if (cur >= len) { x = len; break; }                  // stays in T_NEXT
-        if (q[cur] > 3) { x = cur + 1; break; }
-        c = 3 - q[cur]; ts = T_NONE;
+        ts = T_FINISH;                                       // pass 3 runs in smem_p3_kernel
         break;
       }
       case T_F_DONE:                                         // :364-366
@@ -271,26 +264,18 @@ __global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_k
         if (pass == 1) x = ret;
         ts = T_NEXT;
         break;
-      case T_FINISH: {                                       // ks_introsort by info (:245); equal keys are equal elements
-        const int n = n_mem < a.cap ? n_mem : a.cap;
-        for (int u = 1; u < n; ++u) {
-          const bwaflow_intv_t v = mem[u];
-          int t = u - 1;
-          while (t >= 0 && mem[t].info > v.info) { mem[t + 1] = mem[t]; --t; }
-          mem[t + 1] = v;
-        }
+      case T_FINISH:                                         // passes 1 and 2 done: pass 3, the sort and the final count follow
         a.counts[r] = n_mem;
         if (n_mem > a.cap) atomicExch(a.ctl + 1, 1);
         ts = T_FETCH;
         break;
-      }
       }
     }
     if (__ballot_sync(full, ts == T_NONE) == 0) break;
     if (ts == T_NONE) {
       // ---- the one call site of bwt_extend, then the consume step of the four inner loops
       const Intv o = extend1(ix, ik, phase == PH_BE, c, &blocks);
-      const bool small = o.x2 < (uint64_t)(phase == PH_P3 ? a.max_mem_intv : mi);
+      const bool small = o.x2 < (uint64_t)mi;
       if (phase == PH_F) {                                   // :350-357
         const bool changed = o.x2 != ik.x2;
         if (changed) push_fwd(ik, cur);
@@ -299,14 +284,6 @@ __global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_k
           ik = o; ++cur;
           if (cur < len && q[cur] < 4) c = 3 - q[cur];
           else { push_fwd(ik, cur); ts = T_F_DONE; }         // N or end of read (:358-363)
-        }
-      } else if (phase == PH_P3) {                           // bwa/bwt.c:367-376
-        if (small && cur - px >= msl) { if (o.x2 > 0) push_mem(o, px, cur + 1); x = cur + 1; ts = T_NEXT; }
-        else {
-          ik = o; ++cur;
-          if (cur >= len) { x = len; ts = T_NEXT; }
-          else if (q[cur] > 3) { x = cur + 1; ts = T_NEXT; }
-          else c = 3 - q[cur];
         }
       } else if (phase == PH_BE) {                           // :374-386
         if (small) ts = T_BE_DONE;
@@ -327,6 +304,77 @@ __global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_k
 }
 
 // ---- SA -----------------------------------------------------------------------------------------
+
+// Pass 3 of mem_collect_intv_new (src/bwa_wrapper.cpp:228-243): bwt_seed_strategy1 (bwa/bwt.c:358-379) from every
+// position the previous seed ended at -- a plain forward loop, so it gets its own kernel: one read per lane, one
+// interval extension per trip for every live lane, nothing but a cursor between two extensions, no local memory.
+// It appends to the read's slot after the SMEMs of passes 1-2, sorts the slot by info (:245) and writes the count.
+template <int MAXL>
+__global__ void __launch_bounds__(128) smem_p3_kernel(const SmemArgs a)
+{
+  constexpr int QROW = MAXL + 4;
+  constexpr bool QS = MAXL <= 256;
+  extern __shared__ uint8_t s_mem[];
+  uint8_t *q_s = s_mem + (size_t)threadIdx.x * QROW;
+  const DevIndex &ix = a.ix;
+  const unsigned full = 0xffffffffu;
+  const int msl = a.min_seed_len;
+  unsigned long long blocks = 0;
+  int64_t r = -1; int len = 0, x = 0, px = 0, cur = 0, c = 0, n_mem = 0; const uint8_t *q = nullptr; bwaflow_intv_t *mem = nullptr;
+  Intv ik = {0, 0, 0};
+  bool pending = false, live = true;
+  for (;;) {
+    while (live && !pending) {                               // find the next extension of this lane
+      if (r < 0) {
+        r = (int64_t)atomicAdd(a.ctl + 3, 1);
+        if (r >= a.n_reads) { live = false; break; }
+        const int64_t ro = a.read_off[r];
+        len = (int)(a.read_off[r + 1] - ro);
+        mem = a.slots + r * a.cap; n_mem = a.counts[r]; x = 0;
+        if (len >= MAXL || len < msl || a.max_mem_intv <= 0) x = len;   // nothing to add (too-long reads are flagged by pass 1)
+        else if (QS) { for (int t = 0; t < len; ++t) q_s[t] = a.bases[ro + t]; q = q_s; } else q = a.bases + ro;
+      }
+      while (x < len && q[x] > 3) ++x;
+      if (x >= len) {                                        // read finished: sort by info, final count
+        const int n = n_mem < a.cap ? n_mem : a.cap;
+        for (int u = 1; u < n; ++u) {
+          const bwaflow_intv_t v = mem[u];
+          int t = u - 1;
+          while (t >= 0 && mem[t].info > v.info) { mem[t + 1] = mem[t]; --t; }
+          mem[t + 1] = v;
+        }
+        a.counts[r] = n_mem;
+        if (n_mem > a.cap) atomicExch(a.ctl + 1, 1);
+        r = -1;
+        continue;
+      }
+      px = x; ik = set_intv(ix, q[x]); cur = x + 1;          // bwa/bwt.c:364-366
+      if (cur >= len) { x = len; continue; }
+      if (q[cur] > 3) { x = cur + 1; continue; }
+      c = 3 - q[cur]; pending = true;
+    }
+    if (__ballot_sync(full, pending) == 0) break;
+    if (pending) {
+      const Intv o = extend1(ix, ik, 0, c, &blocks);         // bwa/bwt.c:367-376
+      if (o.x2 < (uint64_t)a.max_mem_intv && cur - px >= msl) {
+        if (o.x2 > 0) {
+          if (n_mem < a.cap) {
+            bwaflow_intv_t w; w.x[0] = o.x0; w.x[1] = o.x1; w.x[2] = o.x2; w.info = (uint64_t)(uint32_t)px << 32 | (uint32_t)(cur + 1);
+            mem[n_mem] = w;
+          }
+          ++n_mem;
+        }
+        x = cur + 1; pending = false;
+      } else {
+        ik = o; ++cur;
+        if (cur >= len) { x = len; pending = false; }
+        else if (q[cur] > 3) { x = cur + 1; pending = false; }
+        else c = 3 - q[cur];
+      }
+    }
+  }
+  if (blocks) atomicAdd(a.blocks, blocks);
+}
 
 // bwt_sa, bwa/bwt.c:86-96 with bwt_invPsi :53-59 (symbol and its Occ come from the same occ32 block)
 __device__ __forceinline__ uint64_t sa_lookup(const DevIndex &ix, uint64_t k, unsigned long long *blocks)
@@ -432,9 +480,18 @@ int bwaflow::smem_launch(bwaflow_smem_batch *b)
   int64_t want = (nr + 127) / 128;
   const int grid = (int)(want < b->blocks_per_launch ? want : b->blocks_per_launch);
   // dynamic shared memory: per lane one row for the read (<= 256 bases) and one for the forward-list end coordinates
-  if (b->max_len < 160) smem_kernel<160><<<grid, 128, 128 * (164 + SMEM_FEND), st>>>(a);
-  else if (b->max_len < 256) smem_kernel<256><<<grid, 128, 128 * (260 + SMEM_FEND), st>>>(a);
-  else smem_kernel<1024><<<grid, 128, 0, st>>>(a);
+  // dynamic shared memory: per lane one row for the read (<= 256 bases) and one for the forward-list end coordinates
+  const int grid3 = (int)(want < (int64_t)b->ctx->n_sm * 8 ? want : (int64_t)b->ctx->n_sm * 8);
+  if (b->max_len < 160) {
+    smem_kernel<160><<<grid, 128, 128 * (164 + SMEM_FEND), st>>>(a);
+    smem_p3_kernel<160><<<grid3, 128, 128 * 164, st>>>(a);
+  } else if (b->max_len < 256) {
+    smem_kernel<256><<<grid, 128, 128 * (260 + SMEM_FEND), st>>>(a);
+    smem_p3_kernel<256><<<grid3, 128, 128 * 260, st>>>(a);
+  } else {
+    smem_kernel<1024><<<grid, 128, 0, st>>>(a);
+    smem_p3_kernel<1024><<<grid3, 128, 0, st>>>(a);
+  }
   smem_compact_counts<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(b->d_counts, nr, b->cap, b->d_cnt64);
   size_t tmp = b->tmp_bytes;
   BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_cnt64, b->d_off, (int)(nr + 1), st));
