@@ -219,3 +219,111 @@ def batch_bounds(offsets, chunk_bp=10_000_000):
     if cuts[-1] != n:
         cuts.append(n)
     return cuts
+
+
+def extension_jobs(ref: Reference, reads: ReadBatch, a=1, w=100, end_bonus=5, zdrop=100, min_seed=19, seed=7):
+    """Extension jobs of the shape mem_chain2aln issues (bwa/bwamem.c:724-771), generated without running the aligner:
+    for every read a seed = a stretch of at least `min_seed` bases around a random anchor, then the LEFT job (reversed
+    query prefix vs reversed reference window, h0 = seed length) and the RIGHT job (query suffix vs reference window,
+    h0 = seed length + left flank length, i.e. roughly the left score), each window as long as the flank plus the largest
+    gap cal_max_gap allows (bwa/bwamem.c:630-637, 651-666).  Reads are taken as placed by simulate_pairs (their true
+    reference position is re-derived by exact search of the seed, so only reads whose seed is unique and error-free are
+    used).  Returns (jobs[EXT_JOB-like dict of arrays], qpool, tpool) with byte-per-base pools (codes 0..4 / 0..3)."""
+    rng = np.random.default_rng(seed)
+    whole = ref.concat()
+    nt4 = reads.nt4()
+    L = int(reads.offsets[1] - reads.offsets[0])
+    n = reads.n
+    R = nt4.reshape(n, L)
+    # anchor k-mer (32 bases) looked up in a hash of the reference's forward and reverse strands would be the general
+    # way; the simulator's layout makes it simpler: reads are substrings of `whole` or of its reverse complement
+    # with substitutions, so locate each read by its first exact 24-mer via a sorted k-mer table of the reference
+    K = 24
+    def kmers(arr):
+        v = np.zeros(len(arr) - K + 1, dtype=np.uint64)
+        for i in range(K):
+            v = (v << np.uint64(2)) | arr[i:len(arr) - K + 1 + i].astype(np.uint64)
+        return v
+    fw = kmers(np.where(whole < 4, whole, 0))
+    order = np.argsort(fw, kind="stable")
+    fws = fw[order]
+    jobs_q, jobs_t, meta = [], [], []
+    sel = rng.permutation(n)
+    comp = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
+    for strand in (0, 1):
+        RR = R if strand == 0 else comp[R[:, ::-1]]
+        for off in (0, L // 2, L - K):
+            km = np.zeros(n, dtype=np.uint64)
+            ok = np.ones(n, dtype=bool)
+            for i in range(K):
+                col = RR[:, off + i]
+                ok &= col < 4
+                km = (km << np.uint64(2)) | (col & 3).astype(np.uint64)
+            pos = np.searchsorted(fws, km)
+            pos = np.minimum(pos, len(fws) - 1)
+            hit = ok & (fws[pos] == km)
+            nxt = np.minimum(pos + 1, len(fws) - 1)
+            uniq = hit & ((fws[nxt] != km) | (nxt == pos))
+            meta.append((strand, off, uniq, order[pos] - off))
+    placed = np.zeros(n, dtype=bool)
+    rpos = np.zeros(n, dtype=np.int64)
+    rstrand = np.zeros(n, dtype=np.int8)
+    for strand, off, uniq, p in meta:
+        take = uniq & ~placed & (p >= 0) & (p + L <= len(whole))
+        rpos[take] = p[take]
+        rstrand[take] = strand
+        placed |= take
+    idx = np.nonzero(placed)[0]
+    # oriented read and its reference window start
+    Q = np.where(rstrand[idx, None] == 0, R[idx], comp[R[idx][:, ::-1]])
+    P = rpos[idx]
+    T = whole[P[:, None] + np.arange(L)[None, :]]
+    match = (Q == T) & (Q < 4)
+    # seed: the longest exact run containing a random anchor column (>= min_seed), found by run-length labelling
+    m = len(idx)
+    anchor = rng.integers(0, L, size=m)
+    run_id = np.cumsum(~match, axis=1)
+    rid_a = run_id[np.arange(m), anchor]
+    in_run = (run_id == rid_a[:, None]) & match
+    qb = np.argmax(in_run, axis=1)
+    ln = in_run.sum(axis=1)
+    good = (ln >= min_seed) & match[np.arange(m), anchor]
+    Q, P, qb, ln = Q[good], P[good], qb[good], ln[good]
+    qe = qb + ln
+
+    def max_gap(q):
+        l = np.maximum((q * a - 6) // 1 + 1, 1)
+        return np.minimum(l, w << 1)
+    out = {k: [] for k in ("qlen", "tlen", "w", "h0", "end_bonus", "zdrop", "q_off", "t_off")}
+    qparts, tparts = [], []
+    qo = to = 0
+    N = len(whole)
+    for side in (0, 1):
+        if side == 0:
+            ql = qb
+            keep = ql > 0
+        else:
+            ql = L - qe
+            keep = ql > 0
+        for i in np.nonzero(keep)[0]:
+            qn = int(ql[i])
+            g = int(max_gap(np.int64(qn)))
+            if side == 0:
+                t0 = max(0, int(P[i] + qb[i]) - (qn + g))
+                t = whole[t0:int(P[i] + qb[i])][::-1]
+                q = Q[i, :qn][::-1]
+                h0 = int(ln[i]) * a
+            else:
+                t1 = min(N, int(P[i] + qe[i]) + qn + g)
+                t = whole[int(P[i] + qe[i]):t1]
+                q = Q[i, int(qe[i]):]
+                h0 = (int(ln[i]) + int(qb[i])) * a
+            t = np.where(t < 4, t, 0).astype(np.uint8)
+            out["qlen"].append(qn); out["tlen"].append(len(t)); out["w"].append(w); out["h0"].append(max(h0, 1))
+            out["end_bonus"].append(end_bonus); out["zdrop"].append(zdrop); out["q_off"].append(qo); out["t_off"].append(to)
+            qparts.append(q.astype(np.uint8)); tparts.append(t)
+            qo += qn; to += len(t)
+    jobs = {k: np.array(v, dtype=np.int64 if k.endswith("_off") else np.int32) for k, v in out.items()}
+    qpool = np.concatenate(qparts) if qparts else np.zeros(0, np.uint8)
+    tpool = np.concatenate(tparts) if tparts else np.zeros(0, np.uint8)
+    return jobs, qpool, tpool
