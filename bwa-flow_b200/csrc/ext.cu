@@ -13,10 +13,14 @@
 #include <stdlib.h>
 #include "internal.cuh"
 #include "ksw_lane.cuh"
+#include "ksw_pair.cuh"
 
 namespace bwaflow {
 
 constexpr int EXT_NCLASS = 8;
+constexpr int EXT_NQ = EXT_NCLASS + 1;
+constexpr int CTL_HIST = 0, CTL_QUEUE = EXT_NCLASS, CTL_ERR = CTL_QUEUE + 2 * EXT_NQ, CTL_CELLS = CTL_ERR + 2, CTL_INTS = CTL_CELLS + 2;
+constexpr int EXT_PAIR_CLASSES = 7;      // classes 0..6 run on the packed two-jobs-per-lane engine (row state of class 7 would not fit)
 // qlen <= qmax runs in class c with `threads` lanes per block; row state = threads*(qmax+1)*4 bytes
 __constant__ int c_ext_qmax[EXT_NCLASS] = {31, 63, 95, 127, 159, 255, 511, 1023};
 static const int h_ext_qmax[EXT_NCLASS] = {31, 63, 95, 127, 159, 255, 511, 1023};
@@ -26,13 +30,15 @@ struct ExtArgs {
   const bwaflow_ext_job_t *jobs;
   const uint8_t *qpool, *tpool;
   const uint32_t *order;
-  int *queue;                 // [EXT_NCLASS] heads, [EXT_NCLASS] ends
+  int *queue;                 // [EXT_NQ] heads, [EXT_NQ] ends; queue EXT_NCLASS = jobs deferred to the int32 engine
+  uint32_t *slow;             // job ids of that queue (appended by the packed kernel)
   bwaflow_ext_result_t *out;
   int *err;
   unsigned long long *cells;
   int cls, qmax;
   int refill;                 // refill idle lanes once at least this many are idle
   DevScore sc;
+  PairConsts pc;
 };
 
 __global__ void ext_key_kernel(const bwaflow_ext_job_t *jobs, int64_t n, uint32_t *keys, uint32_t *vals, int *hist, int *err)
@@ -62,8 +68,9 @@ __global__ void ext_ranges_kernel(const int *hist, int *queue)
   for (int c = EXT_NCLASS - 1; c >= 0; --c) {
     queue[c] = pos;
     pos += hist[c];
-    queue[EXT_NCLASS + c] = pos;
+    queue[EXT_NQ + c] = pos;
   }
+  queue[EXT_NCLASS] = 0; queue[EXT_NQ + EXT_NCLASS] = 0;
 }
 
 template <int THREADS>
@@ -75,7 +82,7 @@ __global__ void __launch_bounds__(THREADS) ext_kernel(const ExtArgs a)
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   int *head = a.queue + a.cls;
-  const int q_end = a.queue[EXT_NCLASS + a.cls];
+  const int q_end = a.queue[EXT_NQ + a.cls];
 
   KswLane k;
   bool active = false, drained = false;
@@ -122,6 +129,94 @@ __global__ void __launch_bounds__(THREADS) ext_kernel(const ExtArgs a)
   }
 }
 
+// Packed engine: every lane owns two slots (ksw_pair.cuh); one warp per block, row state of both slots interleaved in
+// shared memory.  Jobs the packed form cannot represent are appended to the deferred queue for ext_kernel.
+__global__ void __launch_bounds__(32) ext_pair_kernel(const ExtArgs a)
+{
+  extern __shared__ uint2 s_pair[];
+  const int stride = 32;
+  const int lane = threadIdx.x;
+  const int ncol = a.qmax + 1, ngrp = (a.qmax >> 3) + 1;
+  uint2 *st = s_pair + lane;
+  uint32_t *qa = (uint32_t *)(s_pair + (size_t)ncol * stride) + lane;
+  for (int j = 0; j < ncol; ++j) st[(size_t)j * stride] = make_uint2(a.pc.B2, a.pc.B2);
+  for (int g = 0; g < ngrp; ++g) qa[(size_t)g * stride] = 0;
+  const unsigned full = 0xffffffffu;
+  int *head = a.queue + a.cls;
+  const int q_end = a.queue[EXT_NQ + a.cls];
+
+  KswSlot k[2];
+  bool act[2] = {false, false};
+  int job[2] = {-1, -1};
+  const uint8_t *tp[2] = {nullptr, nullptr};
+  int tcur[2] = {0, 0};
+  bool drained = false;
+
+  for (;;) {
+    const unsigned idle0 = __ballot_sync(full, !act[0]), idle1 = __ballot_sync(full, !act[1]);
+    const int n_idle = __popc(idle0) + __popc(idle1);
+    if (n_idle == 64 || (!drained && n_idle >= a.refill)) {
+      int base = q_end;
+      if (!drained) {
+        if (lane == 0) base = atomicAdd(head, n_idle);
+        base = __shfl_sync(full, base, 0);
+        if (base + n_idle >= q_end) drained = true;
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (act[s]) continue;
+        const int slot = base + (s ? __popc(idle0) + __popc(idle1 & ((1u << lane) - 1)) : __popc(idle0 & ((1u << lane) - 1)));
+        if (slot >= q_end) continue;
+        job[s] = (int)a.order[slot];
+        const bwaflow_ext_job_t jb = a.jobs[job[s]];
+        const uint8_t *qp = a.qpool + jb.q_off;
+        tp[s] = a.tpool + jb.t_off;
+        int r = PAIR_BAD;
+        if (jb.qlen >= 0 && jb.qlen <= a.qmax)
+          r = pair_begin(k[s], s, st, qa, stride, a.sc, a.pc, jb.qlen, jb.tlen, jb.w, jb.h0, jb.end_bonus,
+                         [&](int j) { return (uint32_t)qp[j]; });
+        if (r == PAIR_BAD) {
+          atomicExch(a.err, 2);
+          a.out[job[s]] = bwaflow_ext_result_t{0, 0, 0, 0, 0, 0};
+        } else if (jb.tlen <= 0) {
+          a.out[job[s]] = bwaflow_ext_result_t{k[s].best, 0, 0, 0, -1, 0};
+        } else if (r == PAIR_SLOW) {
+          a.slow[atomicAdd(a.queue + EXT_NQ + EXT_NCLASS, 1)] = (uint32_t)job[s];
+        } else {
+          act[s] = true;
+          tcur[s] = tp[s][0];
+        }
+        if (!act[s]) pair_reset(s, st, stride, a.pc, jb.qlen <= a.qmax ? jb.qlen : a.qmax);
+      }
+      if (__ballot_sync(full, act[0] || act[1]) == 0) break;
+    }
+    // an ambiguous target base sends the job to the int32 engine
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (act[s] && tcur[s] > 3) {
+        a.slow[atomicAdd(a.queue + EXT_NQ + EXT_NCLASS, 1)] = (uint32_t)job[s];
+        act[s] = false;
+        pair_reset(s, st, stride, a.pc, k[s].qlen);
+      }
+    if (act[0] || act[1]) {
+      bool d0, d1;
+      const int t0 = tcur[0], t1 = tcur[1];
+      // next rows' target bases are fetched before the row so that the load overlaps it
+      if (act[0] && k[0].i + 1 < k[0].tlen) tcur[0] = tp[0][k[0].i + 1];
+      if (act[1] && k[1].i + 1 < k[1].tlen) tcur[1] = tp[1][k[1].i + 1];
+      pair_step(st, qa, stride, a.sc, a.pc, k[0], k[1], act[0], act[1], t0 & 3, t1 & 3, d0, d1);
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        if (s ? d1 : d0) {
+          a.out[job[s]] = bwaflow_ext_result_t{k[s].best, k[s].best_j + 1, k[s].best_i + 1, k[s].end_i + 1, k[s].gscore, k[s].max_off};
+          atomicAdd(a.cells, (unsigned long long)k[s].cells);
+          act[s] = false;
+          pair_reset(s, st, stride, a.pc, k[s].qlen);
+        }
+    }
+  }
+}
+
 } // namespace bwaflow
 
 using namespace bwaflow;
@@ -138,17 +233,22 @@ struct bwaflow_ext_batch {
   int *d_ctl;                       // hist[8] | queue[16] | err | pad | cells (u64)
   bwaflow_ext_result_t *d_out, *h_out;
   int *h_err;                       // err | pad | cells (u64)
-  int blocks[EXT_NCLASS];
-  int refill;
+  int blocks[EXT_NCLASS], blocks_pair[EXT_NCLASS];
+  int refill, refill_pair;
+  bool use_pair;
+  PairConsts pc;
+  uint32_t *d_slow;
   bool pending;
   double cells_hint;
 };
 
+static size_t pair_smem(int qmax) { return (size_t)32 * ((qmax + 1) * sizeof(uint2) + ((qmax >> 3) + 1) * sizeof(uint32_t)); }
+
 static int ext_launch(bwaflow_ext_batch *b)
 {
   const int64_t n = b->n_jobs;
-  int *hist = b->d_ctl, *queue = b->d_ctl + EXT_NCLASS, *err = b->d_ctl + 3 * EXT_NCLASS;
-  BF_CUDA(cudaMemsetAsync(b->d_ctl, 0, (3 * EXT_NCLASS + 4) * sizeof(int), b->stream));
+  int *hist = b->d_ctl + CTL_HIST, *queue = b->d_ctl + CTL_QUEUE, *err = b->d_ctl + CTL_ERR;
+  BF_CUDA(cudaMemsetAsync(b->d_ctl, 0, CTL_INTS * sizeof(int), b->stream));
   if (n == 0) return 0;
   ext_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_jobs, n, b->d_keys[0], b->d_vals[0], hist, err);
   cub::DoubleBuffer<uint32_t> keys(b->d_keys[0], b->d_keys[1]), vals(b->d_vals[0], b->d_vals[1]);
@@ -156,13 +256,25 @@ static int ext_launch(bwaflow_ext_batch *b)
   BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(b->d_tmp, tmp, keys, vals, (int)n, 0, 27, b->stream));
   ext_ranges_kernel<<<1, 1, 0, b->stream>>>(hist, queue);
   ExtArgs a;
-  a.jobs = b->d_jobs; a.qpool = b->d_q; a.tpool = b->d_t; a.order = vals.Current(); a.queue = queue;
-  a.out = b->d_out; a.err = err; a.cells = (unsigned long long *)(b->d_ctl + 3 * EXT_NCLASS + 2); a.refill = b->refill; a.sc = b->ctx->par.sc;
+  a.jobs = b->d_jobs; a.qpool = b->d_q; a.tpool = b->d_t; a.order = vals.Current(); a.queue = queue; a.slow = b->d_slow;
+  a.out = b->d_out; a.err = err; a.cells = (unsigned long long *)(b->d_ctl + CTL_CELLS); a.refill = b->refill; a.sc = b->ctx->par.sc;
+  a.pc = b->pc;
   for (int c = EXT_NCLASS - 1; c >= 0; --c) {
     a.cls = c; a.qmax = h_ext_qmax[c];
+    if (b->use_pair && c < EXT_PAIR_CLASSES) {
+      a.refill = b->refill_pair;
+      ext_pair_kernel<<<b->blocks_pair[c], 32, pair_smem(h_ext_qmax[c]), b->stream>>>(a);
+      continue;
+    }
+    a.refill = b->refill;
     const size_t smem = (size_t)h_ext_threads[c] * (h_ext_qmax[c] + 1) * sizeof(uint32_t);
     if (h_ext_threads[c] == 64) ext_kernel<64><<<b->blocks[c], 64, smem, b->stream>>>(a);
     else ext_kernel<32><<<b->blocks[c], 32, smem, b->stream>>>(a);
+  }
+  if (b->use_pair) {                                   // jobs the packed engine deferred (ambiguous bases, 16-bit range)
+    const int c = EXT_NCLASS - 1;
+    a.cls = EXT_NCLASS; a.qmax = h_ext_qmax[c]; a.order = b->d_slow; a.refill = b->refill;
+    ext_kernel<32><<<b->blocks[c], 32, (size_t)32 * (h_ext_qmax[c] + 1) * sizeof(uint32_t), b->stream>>>(a);
   }
   BF_CUDA(cudaGetLastError());
   return 0;
@@ -180,6 +292,11 @@ int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_q
   b->ctx = ctx; b->max_jobs = max_jobs; b->max_q = max_qbytes; b->max_t = max_tbytes;
   b->refill = 8;
   if (const char *s = getenv("BWAFLOW_EXT_REFILL")) b->refill = atoi(s) > 0 ? atoi(s) : 8;
+  b->refill_pair = 16;
+  if (const char *s = getenv("BWAFLOW_EXT_REFILL_PAIR")) b->refill_pair = atoi(s) > 0 ? atoi(s) : 16;
+  fill_pair_consts(ctx->par.opt, ctx->par.sc, b->pc);
+  b->use_pair = b->pc.ok != 0;
+  if (const char *s = getenv("BWAFLOW_EXT_ENGINE")) if (!strcmp(s, "int32")) b->use_pair = false;
   BF_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   if (b->tm.init()) return -5;
   BF_CUDA(cudaMalloc(&b->d_jobs, max_jobs * sizeof(bwaflow_ext_job_t)));
@@ -192,7 +309,8 @@ int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_q
   cub::DoubleBuffer<uint32_t> keys(b->d_keys[0], b->d_keys[1]), vals(b->d_vals[0], b->d_vals[1]);
   BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, b->tmp_bytes, keys, vals, (int)max_jobs, 0, 27, b->stream));
   BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
-  BF_CUDA(cudaMalloc(&b->d_ctl, (3 * EXT_NCLASS + 4) * sizeof(int)));
+  BF_CUDA(cudaMalloc(&b->d_ctl, CTL_INTS * sizeof(int)));
+  BF_CUDA(cudaMalloc(&b->d_slow, max_jobs * 4));
   BF_CUDA(cudaMalloc(&b->d_out, max_jobs * sizeof(bwaflow_ext_result_t)));
   BF_CUDA(cudaMallocHost(&b->h_out, max_jobs * sizeof(bwaflow_ext_result_t)));
   BF_CUDA(cudaMallocHost(&b->h_err, 4 * sizeof(int)));
@@ -208,6 +326,13 @@ int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_q
     }
     BF_REQUIRE(per_sm > 0, -12, "extension kernel class %d does not fit on an SM", c);
     b->blocks[c] = per_sm * ctx->n_sm;
+    b->blocks_pair[c] = 0;
+    if (c < EXT_PAIR_CLASSES) {
+      BF_CUDA(cudaFuncSetAttribute(ext_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_pair_kernel, 32, pair_smem(h_ext_qmax[c])));
+      BF_REQUIRE(per_sm > 0, -12, "packed extension kernel class %d does not fit on an SM", c);
+      b->blocks_pair[c] = per_sm * ctx->n_sm;
+    }
   }
   *out = b;
   return 0;
@@ -220,7 +345,7 @@ void bwaflow_ext_batch_destroy(bwaflow_ext_batch_t *b)
   cudaStreamSynchronize(b->stream);
   cudaFree(b->d_jobs); cudaFree(b->d_q); cudaFree(b->d_t);
   for (int i = 0; i < 2; ++i) { cudaFree(b->d_keys[i]); cudaFree(b->d_vals[i]); }
-  cudaFree(b->d_tmp); cudaFree(b->d_ctl); cudaFree(b->d_out);
+  cudaFree(b->d_tmp); cudaFree(b->d_ctl); cudaFree(b->d_out); cudaFree(b->d_slow);
   cudaFreeHost(b->h_out); cudaFreeHost(b->h_err);
   b->tm.destroy();
   cudaStreamDestroy(b->stream);
@@ -231,7 +356,7 @@ static int ext_queue_d2h(bwaflow_ext_batch *b)
 {
   BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
   if (b->n_jobs) BF_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, b->n_jobs * sizeof(bwaflow_ext_result_t), cudaMemcpyDeviceToHost, b->stream));
-  BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_ctl + 3 * EXT_NCLASS, 4 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_ctl + CTL_ERR, 4 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
   BF_CUDA(cudaEventRecord(b->tm.ev[3], b->stream));
   b->pending = true;
   return 0;
@@ -266,7 +391,7 @@ int bwaflow_ext_rerun(bwaflow_ext_batch_t *b)
   int r = ext_launch(b);
   if (r) return r;
   BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
-  BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_ctl + 3 * EXT_NCLASS, 4 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_ctl + CTL_ERR, 4 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
   BF_CUDA(cudaEventRecord(b->tm.ev[3], b->stream));
   b->pending = true;
   return 0;
@@ -283,7 +408,7 @@ int bwaflow_ext_collect(bwaflow_ext_batch_t *b, const bwaflow_ext_result_t **out
     cudaEventElapsedTime(&t->kernel_ms, b->tm.ev[1], b->tm.ev[2]);
     cudaEventElapsedTime(&t->d2h_ms, b->tm.ev[2], b->tm.ev[3]);
     cudaEventElapsedTime(&t->total_ms, b->tm.ev[0], b->tm.ev[3]);
-    t->n_launches = b->n_jobs ? 3 + EXT_NCLASS + 7 : 0;   // key + ranges + 8 class kernels + cub passes
+    t->n_launches = b->n_jobs ? 3 + EXT_NCLASS + 1 + 7 : 0;   // key + ranges + 8 class kernels + deferred queue + cub passes
     t->work_units = (double)*(unsigned long long *)(b->h_err + 2);   // DP cells executed
   }
   BF_REQUIRE(*b->h_err != 1, -34, "extension job with qlen > %d (or negative length)", h_ext_qmax[EXT_NCLASS - 1]);

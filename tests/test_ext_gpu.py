@@ -25,8 +25,15 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(params=["packed", "int32"])
+def engine(request, monkeypatch):
+    """Both extension engines: the packed two-jobs-per-lane s16x2 one (default) and the one-job-per-lane int32 one."""
+    monkeypatch.setenv("BWAFLOW_EXT_ENGINE", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("case", ["golden_c1", "golden_c5"])
-def test_ext_matches_golden(case, request, ctx):
+def test_ext_matches_golden(case, request, ctx, engine):
     from bwaflow_b200 import capi
     g = request.getfixturevalue(case)
     jobs, qp, tp, exp = _jobs_from_golden(g)
@@ -83,7 +90,7 @@ def _random_jobs(rng, n, qmax, mat, opt, zdrops=(0, 10, 100), ws=(1, 5, 100, 200
 
 
 @pytest.mark.parametrize("qmax,zdrop", [(40, 100), (200, 100), (600, 30), (1000, 0)])
-def test_ext_matches_oracle_random(qmax, zdrop, ctx):
+def test_ext_matches_oracle_random(qmax, zdrop, ctx, engine):
     """All qlen classes (shared-memory row-state sizes), ragged/empty targets, N bases, tiny bands, z-drop on/off."""
     from bwaflow_b200 import capi
     rng = np.random.default_rng(qmax)
@@ -94,6 +101,44 @@ def test_ext_matches_oracle_random(qmax, zdrop, ctx):
     n = 1500 if qmax <= 200 else 300
     jobs, qp, tp, exp = _random_jobs(rng, n, qmax, mat, opt)
     b = capi.ExtBatch(ctx, n, len(qp), len(tp))
+    b.submit(jobs, qp, tp)
+    got, _ = b.collect()
+    bad = np.nonzero(got != exp)[0]
+    assert len(bad) == 0, (bad[:5], got[bad[:5]], exp[bad[:5]], jobs[bad[:5]])
+    b.close()
+    ctx.set_opt(capi.default_opt())
+
+
+@pytest.mark.parametrize("refill", [1, 64])
+def test_ext_packed_refill_policies(refill, ctx, monkeypatch):
+    """Slots refilled one at a time (maximal desynchronisation of the two jobs of a lane) and only when a whole warp is idle."""
+    from bwaflow_b200 import capi
+    monkeypatch.setenv("BWAFLOW_EXT_REFILL_PAIR", str(refill))
+    rng = np.random.default_rng(refill)
+    opt = capi.default_opt()
+    mat = np.array(list(opt.mat), dtype=np.int8)
+    jobs, qp, tp, exp = _random_jobs(rng, 2500, 150, mat, opt, ws=(3, 100))
+    b = capi.ExtBatch(ctx, len(jobs), len(qp), len(tp))
+    b.submit(jobs, qp, tp)
+    got, _ = b.collect()
+    bad = np.nonzero(got != exp)[0]
+    assert len(bad) == 0, (bad[:5], got[bad[:5]], exp[bad[:5]], jobs[bad[:5]])
+    b.close()
+
+
+def test_ext_general_matrix_uses_int32_engine(ctx):
+    """A scoring matrix outside the bwa_fill_scmat form (here: transitions cheaper than transversions) cannot be packed."""
+    from bwaflow_b200 import capi
+    rng = np.random.default_rng(11)
+    opt = capi.default_opt()
+    m = list(opt.mat)
+    m[0 * 5 + 2] = m[2 * 5 + 0] = m[1 * 5 + 3] = m[3 * 5 + 1] = -2
+    for i, v in enumerate(m):
+        opt.mat[i] = v
+    ctx.set_opt(opt)
+    mat = np.array(list(opt.mat), dtype=np.int8)
+    jobs, qp, tp, exp = _random_jobs(rng, 600, 120, mat, opt)
+    b = capi.ExtBatch(ctx, len(jobs), len(qp), len(tp))
     b.submit(jobs, qp, tp)
     got, _ = b.collect()
     bad = np.nonzero(got != exp)[0]
