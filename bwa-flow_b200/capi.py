@@ -87,6 +87,7 @@ def lib():
         L.bwaflow_ext_submit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
         L.bwaflow_ext_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(Timing)]
         L.bwaflow_ext_rerun.argtypes = [C.c_void_p]
+        L.bwaflow_ext_rerun_counted.argtypes = [C.c_void_p]
         if hasattr(L, "bwaflow_c2a_batch_create"):
             L.bwaflow_c2a_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
             L.bwaflow_c2a_batch_destroy.argtypes = [C.c_void_p]
@@ -240,8 +241,9 @@ class ExtBatch:
         self.n = len(jobs)
         check(self.L.bwaflow_ext_submit(self.h, len(jobs), _p(jobs), _p(qpool), len(qpool), _p(tpool), len(tpool)))
 
-    def rerun(self):
-        check(self.L.bwaflow_ext_rerun(self.h))
+    def rerun(self, counted=False):
+        """Device-resident re-run; counted=True uses the kernel variant that also counts the executed DP cells."""
+        check(self.L.bwaflow_ext_rerun_counted(self.h) if counted else self.L.bwaflow_ext_rerun(self.h))
 
     def collect(self):
         out = C.c_void_p()

@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(THREADS) ext_kernel(const ExtArgs a)
 
 // Packed engine: every lane owns two slots (ksw_pair.cuh); one warp per block, row state of both slots interleaved in
 // shared memory.  Jobs the packed form cannot represent are appended to the deferred queue for ext_kernel.
+// EXACT = also count the DP cells the reference executes (the GCUPS work unit); results are identical either way.
+template <bool EXACT>
 __global__ void __launch_bounds__(32) ext_pair_kernel(const ExtArgs a)
 {
   extern __shared__ uint2 s_pair[];
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(32) ext_pair_kernel(const ExtArgs a)
   uint2 *st = s_pair + lane;
   uint32_t *qa = (uint32_t *)(s_pair + (size_t)ncol * stride) + lane;
   for (int j = 0; j < ncol; ++j) st[(size_t)j * stride] = make_uint2(a.pc.B2, a.pc.B2);
-  for (int g = 0; g < ngrp; ++g) qa[(size_t)g * stride] = 0;
+  for (int g = 0; g < ngrp; ++g) qa[(size_t)g * stride] = 0xFFFFFFFFu;
   const unsigned full = 0xffffffffu;
   int *head = a.queue + a.cls;
   const int q_end = a.queue[EXT_NQ + a.cls];
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(32) ext_pair_kernel(const ExtArgs a)
           act[s] = true;
           tcur[s] = tp[s][0];
         }
-        if (!act[s]) pair_reset(s, st, stride, a.pc, jb.qlen <= a.qmax ? jb.qlen : a.qmax);
+        if (!act[s]) pair_retire(s, qa, stride, jb.qlen <= a.qmax ? jb.qlen : a.qmax);
       }
       if (__ballot_sync(full, act[0] || act[1]) == 0) break;
     }
@@ -196,22 +198,22 @@ __global__ void __launch_bounds__(32) ext_pair_kernel(const ExtArgs a)
       if (act[s] && tcur[s] > 3) {
         a.slow[atomicAdd(a.queue + EXT_NQ + EXT_NCLASS, 1)] = (uint32_t)job[s];
         act[s] = false;
-        pair_reset(s, st, stride, a.pc, k[s].qlen);
+        pair_retire(s, qa, stride, k[s].qlen);
       }
     if (act[0] || act[1]) {
       bool d0, d1;
-      const int t0 = tcur[0], t1 = tcur[1];
+      const int t0 = act[0] ? tcur[0] : 0, t1 = act[1] ? tcur[1] : 0;
       // next rows' target bases are fetched before the row so that the load overlaps it
       if (act[0] && k[0].i + 1 < k[0].tlen) tcur[0] = tp[0][k[0].i + 1];
       if (act[1] && k[1].i + 1 < k[1].tlen) tcur[1] = tp[1][k[1].i + 1];
-      pair_step(st, qa, stride, a.sc, a.pc, k[0], k[1], act[0], act[1], t0 & 3, t1 & 3, d0, d1);
+      pair_step<EXACT>(st, qa, stride, a.sc, a.pc, k[0], k[1], act[0], act[1], t0, t1, d0, d1);
 #pragma unroll
       for (int s = 0; s < 2; ++s)
         if (s ? d1 : d0) {
           a.out[job[s]] = bwaflow_ext_result_t{k[s].best, k[s].best_j + 1, k[s].best_i + 1, k[s].end_i + 1, k[s].gscore, k[s].max_off};
-          atomicAdd(a.cells, (unsigned long long)k[s].cells);
+          if (EXACT) atomicAdd(a.cells, (unsigned long long)k[s].cells);
           act[s] = false;
-          pair_reset(s, st, stride, a.pc, k[s].qlen);
+          pair_retire(s, qa, stride, k[s].qlen);
         }
     }
   }
@@ -235,9 +237,13 @@ struct bwaflow_ext_batch {
   int *h_err;                       // err | pad | cells (u64)
   int blocks[EXT_NCLASS], blocks_pair[EXT_NCLASS];
   int refill, refill_pair;
-  bool use_pair;
+  bool use_pair, multi_stream;
+  double cells_known;
+  bool count_cells;            // this launch runs the cell-counting (EXACT) variant of the packed kernel
   PairConsts pc;
   uint32_t *d_slow;
+  cudaStream_t cstream[EXT_NCLASS];
+  cudaEvent_t ev_fork, ev_join[EXT_NCLASS];
   bool pending;
   double cells_hint;
 };
@@ -259,17 +265,27 @@ static int ext_launch(bwaflow_ext_batch *b)
   a.jobs = b->d_jobs; a.qpool = b->d_q; a.tpool = b->d_t; a.order = vals.Current(); a.queue = queue; a.slow = b->d_slow;
   a.out = b->d_out; a.err = err; a.cells = (unsigned long long *)(b->d_ctl + CTL_CELLS); a.refill = b->refill; a.sc = b->ctx->par.sc;
   a.pc = b->pc;
+  // one persistent launch per class, each on its own stream: a class's blocks take the SMs as the previous class drains,
+  // so the tails (few long jobs left) overlap with the next class instead of idling the GPU
+  BF_CUDA(cudaEventRecord(b->ev_fork, b->stream));
   for (int c = EXT_NCLASS - 1; c >= 0; --c) {
     a.cls = c; a.qmax = h_ext_qmax[c];
+    cudaStream_t cs = b->multi_stream ? b->cstream[c] : b->stream;
+    if (b->multi_stream) BF_CUDA(cudaStreamWaitEvent(cs, b->ev_fork, 0));
     if (b->use_pair && c < EXT_PAIR_CLASSES) {
       a.refill = b->refill_pair;
-      ext_pair_kernel<<<b->blocks_pair[c], 32, pair_smem(h_ext_qmax[c]), b->stream>>>(a);
-      continue;
+      if (b->count_cells) ext_pair_kernel<true><<<b->blocks_pair[c], 32, pair_smem(h_ext_qmax[c]), cs>>>(a);
+      else ext_pair_kernel<false><<<b->blocks_pair[c], 32, pair_smem(h_ext_qmax[c]), cs>>>(a);
+    } else {
+      a.refill = b->refill;
+      const size_t smem = (size_t)h_ext_threads[c] * (h_ext_qmax[c] + 1) * sizeof(uint32_t);
+      if (h_ext_threads[c] == 64) ext_kernel<64><<<b->blocks[c], 64, smem, cs>>>(a);
+      else ext_kernel<32><<<b->blocks[c], 32, smem, cs>>>(a);
     }
-    a.refill = b->refill;
-    const size_t smem = (size_t)h_ext_threads[c] * (h_ext_qmax[c] + 1) * sizeof(uint32_t);
-    if (h_ext_threads[c] == 64) ext_kernel<64><<<b->blocks[c], 64, smem, b->stream>>>(a);
-    else ext_kernel<32><<<b->blocks[c], 32, smem, b->stream>>>(a);
+    if (b->multi_stream) {
+      BF_CUDA(cudaEventRecord(b->ev_join[c], cs));
+      BF_CUDA(cudaStreamWaitEvent(b->stream, b->ev_join[c], 0));
+    }
   }
   if (b->use_pair) {                                   // jobs the packed engine deferred (ambiguous bases, 16-bit range)
     const int c = EXT_NCLASS - 1;
@@ -294,11 +310,18 @@ int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_q
   if (const char *s = getenv("BWAFLOW_EXT_REFILL")) b->refill = atoi(s) > 0 ? atoi(s) : 8;
   b->refill_pair = 16;
   if (const char *s = getenv("BWAFLOW_EXT_REFILL_PAIR")) b->refill_pair = atoi(s) > 0 ? atoi(s) : 16;
+  b->multi_stream = true;
+  if (const char *s = getenv("BWAFLOW_EXT_STREAMS")) b->multi_stream = atoi(s) != 1;
   fill_pair_consts(ctx->par.opt, ctx->par.sc, b->pc);
   b->use_pair = b->pc.ok != 0;
   if (const char *s = getenv("BWAFLOW_EXT_ENGINE")) if (!strcmp(s, "int32")) b->use_pair = false;
   BF_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   if (b->tm.init()) return -5;
+  BF_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+  for (int c = 0; c < EXT_NCLASS; ++c) {
+    BF_CUDA(cudaStreamCreateWithFlags(&b->cstream[c], cudaStreamNonBlocking));
+    BF_CUDA(cudaEventCreateWithFlags(&b->ev_join[c], cudaEventDisableTiming));
+  }
   BF_CUDA(cudaMalloc(&b->d_jobs, max_jobs * sizeof(bwaflow_ext_job_t)));
   BF_CUDA(cudaMalloc(&b->d_q, max_qbytes + 16));
   BF_CUDA(cudaMalloc(&b->d_t, max_tbytes + 16));
@@ -328,8 +351,12 @@ int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_q
     b->blocks[c] = per_sm * ctx->n_sm;
     b->blocks_pair[c] = 0;
     if (c < EXT_PAIR_CLASSES) {
-      BF_CUDA(cudaFuncSetAttribute(ext_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_pair_kernel, 32, pair_smem(h_ext_qmax[c])));
+      BF_CUDA(cudaFuncSetAttribute(ext_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      BF_CUDA(cudaFuncSetAttribute(ext_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      int per_sm2 = 0;
+      BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, ext_pair_kernel<true>, 32, pair_smem(h_ext_qmax[c])));
+      BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_pair_kernel<false>, 32, pair_smem(h_ext_qmax[c])));
+      if (per_sm2 < per_sm) per_sm = per_sm2;
       BF_REQUIRE(per_sm > 0, -12, "packed extension kernel class %d does not fit on an SM", c);
       b->blocks_pair[c] = per_sm * ctx->n_sm;
     }
@@ -348,6 +375,8 @@ void bwaflow_ext_batch_destroy(bwaflow_ext_batch_t *b)
   cudaFree(b->d_tmp); cudaFree(b->d_ctl); cudaFree(b->d_out); cudaFree(b->d_slow);
   cudaFreeHost(b->h_out); cudaFreeHost(b->h_err);
   b->tm.destroy();
+  cudaEventDestroy(b->ev_fork);
+  for (int c = 0; c < EXT_NCLASS; ++c) { cudaStreamDestroy(b->cstream[c]); cudaEventDestroy(b->ev_join[c]); }
   cudaStreamDestroy(b->stream);
   free(b);
 }
@@ -377,25 +406,26 @@ int bwaflow_ext_submit(bwaflow_ext_batch_t *b, int64_t n_jobs, const bwaflow_ext
     BF_CUDA(cudaMemcpyAsync(b->d_t, tpool, tbytes, cudaMemcpyHostToDevice, b->stream));
   }
   BF_CUDA(cudaEventRecord(b->tm.ev[1], b->stream));
+  b->count_cells = false; b->cells_known = 0.0;
   int r = ext_launch(b);
   if (r) return r;
   return ext_queue_d2h(b);
 }
 
-int bwaflow_ext_rerun(bwaflow_ext_batch_t *b)
+static int ext_rerun(bwaflow_ext_batch *b, bool counted)
 {
   BF_REQUIRE(b, -22, "bwaflow_ext_rerun: null batch");
   BF_CUDA(cudaSetDevice(b->ctx->device));
   BF_CUDA(cudaEventRecord(b->tm.ev[0], b->stream));
   BF_CUDA(cudaEventRecord(b->tm.ev[1], b->stream));
+  b->count_cells = counted;
   int r = ext_launch(b);
   if (r) return r;
-  BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
-  BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_ctl + CTL_ERR, 4 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-  BF_CUDA(cudaEventRecord(b->tm.ev[3], b->stream));
-  b->pending = true;
-  return 0;
+  return ext_queue_d2h(b);
 }
+
+int bwaflow_ext_rerun(bwaflow_ext_batch_t *b) { return ext_rerun(b, false); }
+int bwaflow_ext_rerun_counted(bwaflow_ext_batch_t *b) { return ext_rerun(b, true); }
 
 int bwaflow_ext_collect(bwaflow_ext_batch_t *b, const bwaflow_ext_result_t **out, bwaflow_timing_t *t)
 {
@@ -409,7 +439,8 @@ int bwaflow_ext_collect(bwaflow_ext_batch_t *b, const bwaflow_ext_result_t **out
     cudaEventElapsedTime(&t->d2h_ms, b->tm.ev[2], b->tm.ev[3]);
     cudaEventElapsedTime(&t->total_ms, b->tm.ev[0], b->tm.ev[3]);
     t->n_launches = b->n_jobs ? 3 + EXT_NCLASS + 1 + 7 : 0;   // key + ranges + 8 class kernels + deferred queue + cub passes
-    t->work_units = (double)*(unsigned long long *)(b->h_err + 2);   // DP cells executed
+    if (b->count_cells || !b->use_pair) b->cells_known = (double)*(unsigned long long *)(b->h_err + 2);
+    t->work_units = b->cells_known;                      // DP cells the reference executes for these jobs (0 = not counted yet)
   }
   BF_REQUIRE(*b->h_err != 1, -34, "extension job with qlen > %d (or negative length)", h_ext_qmax[EXT_NCLASS - 1]);
   BF_REQUIRE(*b->h_err != 2, -34, "extension job whose scores may exceed %d (h0 + qlen*max_mat) or with h0 <= 0", KSW_MAX_SCORE);

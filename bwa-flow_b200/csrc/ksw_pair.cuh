@@ -112,16 +112,13 @@ __device__ __forceinline__ int pair_begin(KswSlot &k, int S, uint2 *st, uint32_t
   return bad > 3 ? PAIR_SLOW : PAIR_OK;
 }
 
-// Puts the halves of slot S back to the all-zero (= BIAS) state for columns 0..qlen.  That state is absorbing under the cell
-// recurrence (H = 0 gives M <= 0, so h, E', F' stay 0), which is what makes it safe for an idle slot to shadow its
-// partner's window: the values it computes there can never grow and spill into the partner's half.
-__device__ __forceinline__ void pair_reset(int S, uint2 *st, int stride, const PairConsts &c, int qlen)
+// Retires the job of slot S: its query becomes all-T (code 3) while an idle slot's target base is A (code 0), so the values the idle
+// half goes on computing while it shadows its partner's window see a mismatch in every cell and can only decay.  That bounds
+// them by the finished job's own (valid) values: they can never overflow 16 bits and spill into the partner's half.
+__device__ __forceinline__ void pair_retire(int S, uint32_t *qa, int stride, int qlen)
 {
-  uint16_t *h16 = (uint16_t *)st + S, *e16 = (uint16_t *)st + 2 + S;
-  for (int j = 0; j <= qlen; ++j) {
-    h16[(size_t)j * stride * 4] = (uint16_t)c.bias;
-    e16[(size_t)j * stride * 4] = (uint16_t)c.bias;
-  }
+  uint16_t *q16 = (uint16_t *)qa + S;
+  for (int g = 0; g <= (qlen >> 3); ++g) q16[(size_t)g * stride * 2] = 0xFFFFu;
 }
 
 struct PairRow {                 // packed loop-carried state of one row of both slots
@@ -130,8 +127,7 @@ struct PairRow {                 // packed loop-carried state of one row of both
 };
 
 // One cell of both slots.  qsh = query codes of the two slots already shifted to bits 14-15 / 30-31 (other bits arbitrary).
-template <bool MASKED>
-__device__ __forceinline__ void pair_cell(uint2 *p, uint32_t qsh, int j, PairRow &r, const PairConsts &c, int sel)
+__device__ __forceinline__ void pair_cell(uint2 *p, uint32_t qsh, int j, PairRow &r, const PairConsts &c)
 {
   const uint2 v = *p;
   const uint32_t d = (qsh ^ r.tt) & 0xC000C000u;
@@ -146,47 +142,84 @@ __device__ __forceinline__ void pair_cell(uint2 *p, uint32_t qsh, int j, PairRow
   r.m = __vibmax_s16x2(h, r.m, &ph, &pl);                            // predicates: h >= running max (last column wins ties)
   r.mj0 = pl ? j : r.mj0;
   r.mj1 = ph ? j : r.mj1;
-  if (!MASKED) *p = make_uint2(r.left, e2);
-  else {                                                             // only slot `sel` is inside its window here
-    uint16_t *p16 = (uint16_t *)p + sel;
-    const int sh = sel * 16;
-    p16[0] = (uint16_t)(r.left >> sh);
-    p16[2] = (uint16_t)(e2 >> sh);
-  }
+  *p = make_uint2(r.left, e2);
   r.left = h;
 }
 
-template <bool MASKED>
-__device__ __forceinline__ void pair_cols(uint2 *st, const uint32_t *qa, int stride, int j0, int j1, PairRow &r,
-                                          const PairConsts &c, int sel)
+// A cell of a column group that is only partly inside the two windows: computed unconditionally (the columns exist and hold
+// valid halves), every effect gated per half by gm (0xFFFF per half whose slot has this column inside its window).
+// A gated-out half contributes h = 0 < BIAS to the running maximum, so neither the maximum nor its column can change.
+__device__ __forceinline__ void pair_cell_gated(uint2 *p, uint32_t qsh, int j, PairRow &r, const PairConsts &c, uint32_t gm)
 {
-  int j = j0;
-  uint2 *p = st + (size_t)j * stride;
-  for (; j < j1 && (j & 7); ++j, p += stride) pair_cell<MASKED>(p, qa[(j >> 3) * stride] << (14 - 2 * (j & 7)), j, r, c, sel);
-  for (; j + 8 <= j1; j += 8, p += 8 * stride) {
-    const uint32_t qw = qa[(j >> 3) * stride];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) pair_cell<MASKED>(p + u * stride, mad_fma(qw, 1u << (14 - 2 * u), 0u), j + u, r, c, sel);
-  }
-  for (; j < j1; ++j, p += stride) pair_cell<MASKED>(p, qa[(j >> 3) * stride] << (14 - 2 * (j & 7)), j, r, c, sel);
+  const uint2 v = *p;
+  const uint32_t d = (qsh ^ r.tt) & 0xC000C000u;
+  const uint32_t nm = __vminu2(d, 0x00010001u);
+  const uint32_t x = mad_fma(nm, c.NAB, mad_fma(v.x, 1u, c.A2));
+  const uint32_t hk = mad_fma(v.x, c.K, c.HKC);
+  const uint32_t M = __vmins2(x, hk);
+  const uint32_t hg = __vimax3_s16x2(M, v.y, r.f) & gm;
+  const uint32_t e2 = __vimax3_s16x2(sub_fma(M, c.OED2), sub_fma(v.y, c.ED2), c.B2);
+  const uint32_t f2 = __vimax3_s16x2(sub_fma(M, c.OEI2), sub_fma(r.f, c.EI2), c.B2);
+  r.f = (f2 & gm) | (r.f & ~gm);
+  bool ph, pl;
+  r.m = __vibmax_s16x2(hg, r.m, &ph, &pl);
+  r.mj0 = pl ? j : r.mj0;
+  r.mj1 = ph ? j : r.mj1;
+  *p = make_uint2((r.left & gm) | (v.x & ~gm), (e2 & gm) | (v.y & ~gm));
+  r.left = hg | (r.left & ~gm);
 }
 
-__device__ __forceinline__ void slot_row_begin(KswSlot &k, const DevScore &sc, int &left)
+// Columns of one row for both slots: slot 0 in [a0,a1), slot 1 in [b0,b1) (empty = [0,0)), walked in aligned groups of
+// 8 columns (one query word).  Groups entirely inside both windows run the plain cell with constant query shifts; the
+// boundary groups run the gated cell.
+__device__ __forceinline__ void pair_cols(uint2 *st, const uint32_t *qa, int stride, int a0, int a1, int b0, int b1, PairRow &r,
+                                          const PairConsts &c)
+{
+  const int in0 = max(a0, b0), in1 = min(a1, b1);                  // columns inside both windows
+  int jb = (a0 < a1 ? (b0 < b1 ? min(a0, b0) : a0) : b0) & ~7;
+  const int jend = max(a1, b1);
+  uint2 *p = st + (size_t)jb * stride;
+  const uint32_t *qp = qa + (jb >> 3) * stride;
+#pragma unroll 1
+  for (; jb < jend; jb += 8, p += 8 * stride, qp += stride) {
+    const uint32_t qw = *qp;
+    if (jb >= in0 && jb + 8 <= in1) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) pair_cell(p + u * stride, mad_fma(qw, 1u << (14 - 2 * u), 0u), jb + u, r, c);
+    } else {
+      // bit u (slot 0) / bit 16+u (slot 1) = column jb+u inside the slot's window
+      const int sa = min(max(a0 - jb, 0), 8), ea = min(max(a1 - jb, 0), 8), sb = min(max(b0 - jb, 0), 8), eb = min(max(b1 - jb, 0), 8);
+      const uint32_t mm = (((1u << ea) - 1u) & ~((1u << sa) - 1u)) | (((1u << eb) - 1u) & ~((1u << sb) - 1u)) << 16;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        pair_cell_gated(p + u * stride, mad_fma(qw, 1u << (14 - 2 * u), 0u), jb + u, r, c, ((mm >> u) & 0x00010001u) * 0xFFFFu);
+    }
+  }
+}
+
+// Band of the row (ksw.c:416-423).  k.lo is a lower bound of the reference's `beg` (exact when EXACT): columns below `beg`
+// hold the all-zero state, which the recurrence reproduces (H = E = F = 0 gives h = E' = F' = 0 and passes h1 = 0 on), so starting a
+// row anywhere in [max(0, i-w), beg] gives the same row.  c0 = the column this row starts at.
+template <bool EXACT>
+__device__ __forceinline__ void slot_row_begin(KswSlot &k, const DevScore &sc, int &left, int &c0)
 {
   if (k.lo < k.i - k.w) k.lo = k.i - k.w;
   if (k.hi > k.i + k.w + 1) k.hi = k.i + k.w + 1;
   if (k.hi > k.qlen) k.hi = k.qlen;
+  c0 = k.lo;
+  if (!EXACT) { c0 &= ~7; if (c0 < k.i - k.w) c0 = k.i - k.w; }     // start on a group boundary when the band allows
   left = 0;
-  if (k.lo == 0) { left = k.h0 - (sc.o_del + sc.e_del * (k.i + 1)); left = left > 0 ? left : 0; }
+  if (c0 == 0) { left = k.h0 - (sc.o_del + sc.e_del * (k.i + 1)); left = left > 0 ? left : 0; }
 }
 
-// Everything of ksw.c:449-469 for one slot after its row's cells.  left/m are unbiased.  Returns true when the job is finished.
-__device__ __forceinline__ bool slot_row_end(KswSlot &k, int S, uint2 *st, int stride, const DevScore &sc, int bias, int left, int m, int mj)
+// ksw.c:449-464 for one slot after its row's cells (left/m unbiased).  Returns true when the job is finished.
+template <bool EXACT>
+__device__ __forceinline__ bool slot_row_score(KswSlot &k, int S, uint2 *st, int stride, const DevScore &sc, int bias, int left, int m, int mj)
 {
   uint16_t *h16 = (uint16_t *)st + S, *e16 = (uint16_t *)st + 2 + S;
   const size_t cs = (size_t)stride * 4;                // u16 elements per column
   const int jend = k.lo < k.hi ? k.hi : k.lo;
-  k.cells += (unsigned)(jend - k.lo);
+  if (EXACT) k.cells += (unsigned)(jend - k.lo);
   h16[k.hi * cs] = (uint16_t)(left + bias);            // eh[end] = {h1, 0}   ksw.c:449
   e16[k.hi * cs] = (uint16_t)bias;
   if (jend == k.qlen) {                                // ksw.c:450-453
@@ -203,28 +236,65 @@ __device__ __forceinline__ bool slot_row_end(KswSlot &k, int S, uint2 *st, int s
     if (di > dj) { if (k.best - m - (di - dj) * sc.e_del > sc.zdrop) return true; }
     else if (k.best - m - (dj - di) * sc.e_ins > sc.zdrop) return true;
   }
-  const uint16_t z = (uint16_t)bias;                   // ksw.c:466-469
-  int j = k.lo;
-  while (j < k.hi && h16[j * cs] == z && e16[j * cs] == z) ++j;
+  return false;
+}
+
+struct TrimProbe { uint32_t a, b, d; };                // (H,E) of columns lo, lo+1 and hi-1, each as H | E << 16
+
+__device__ __forceinline__ void slot_trim_probe(const KswSlot &k, int S, const uint2 *st, int stride, TrimProbe &t)
+{
+  const uint16_t *h16 = (const uint16_t *)st + S, *e16 = (const uint16_t *)st + 2 + S;
+  const size_t cs = (size_t)stride * 4;
+  t.a = h16[k.lo * cs] | (uint32_t)e16[k.lo * cs] << 16;
+  t.b = h16[(k.lo + 1) * cs] | (uint32_t)e16[(k.lo + 1) * cs] << 16;
+  t.d = h16[(k.hi - 1) * cs] | (uint32_t)e16[(k.hi - 1) * cs] << 16;
+}
+
+// ksw.c:466-469: next row's window.  `left` = the value just stored at eh[hi].h (its e is 0).  Returns true when all rows are done.
+// The right end is always exact (columns beyond it keep stale values that later rows may read, so none may be touched).  The left
+// end is exact when EXACT; otherwise it advances by at most two columns per row, which keeps it a lower bound (a row with
+// m > 0 has a non-zero column, so neither scan of the reference can run past the other end).
+template <bool EXACT>
+__device__ __forceinline__ bool slot_trim(KswSlot &k, int S, const uint2 *st, int stride, uint32_t z2, const TrimProbe &t, int left)
+{
+  const uint16_t *h16 = (const uint16_t *)st + S, *e16 = (const uint16_t *)st + 2 + S;
+  const size_t cs = (size_t)stride * 4;
+  const uint16_t z = (uint16_t)z2;
+  int j = k.lo;                                        // here lo < hi
+  if (t.a == z2) {
+    ++j;
+    if (j < k.hi && t.b == z2) {
+      ++j;
+      if (EXACT) while (j < k.hi && h16[j * cs] == z && e16[j * cs] == z) ++j;
+    }
+  }
   k.lo = j;
   j = k.hi;
-  while (j >= k.lo && h16[j * cs] == z && e16[j * cs] == z) --j;
+  if (left == 0) {                                     // eh[hi] is all zero
+    --j;
+    if (j >= k.lo && t.d == z2) {
+      --j;
+      while (j >= k.lo && h16[j * cs] == z && e16[j * cs] == z) --j;
+    }
+  }
   k.hi = j + 2 < k.qlen ? j + 2 : k.qlen;
   return ++k.i >= k.tlen;
 }
 
 // One row of each active slot of this lane.  t0/t1 = target bases of the slots' current rows (0..3).
-// done0/done1 are set when the slot's job finished with this row.
+// done0/done1 are set when the slot's job finished with this row.  EXACT: keep the reference's exact left band end and count
+// the DP cells the reference executes (work-unit counter); the default trades that for register-only row bookkeeping.
+template <bool EXACT>
 __device__ __forceinline__ void pair_step(uint2 *st, const uint32_t *qa, int stride, const DevScore &sc, const PairConsts &c,
                                           KswSlot &k0, KswSlot &k1, bool act0, bool act1, int t0, int t1, bool &done0, bool &done1)
 {
-  int l0 = 0, l1 = 0;
-  if (act0) slot_row_begin(k0, sc, l0);
-  if (act1) slot_row_begin(k1, sc, l1);
-  // windows; an idle slot shadows the other one (it computes on valid-format stale halves that nobody reads)
-  int a0 = k0.lo, a1 = k0.hi, b0 = k1.lo, b1 = k1.hi;
-  if (!act0 || a0 >= a1) { a0 = 0; a1 = 0; }
-  if (!act1 || b0 >= b1) { b0 = 0; b1 = 0; }
+  int l0 = 0, l1 = 0, a0 = 0, b0 = 0;
+  if (act0) slot_row_begin<EXACT>(k0, sc, l0, a0);
+  if (act1) slot_row_begin<EXACT>(k1, sc, l1, b0);
+  // windows; an idle slot shadows the other one (it computes on all-zero halves that nobody reads, see pair_reset)
+  int a1 = k0.hi, b1 = k1.hi;
+  if (!act0 || k0.lo >= a1) { a0 = 0; a1 = 0; }
+  if (!act1 || k1.lo >= b1) { b0 = 0; b1 = 0; }
   if (!act0) { a0 = b0; a1 = b1; }
   if (!act1) { b0 = a0; b1 = a1; }
   PairRow r;
@@ -232,48 +302,16 @@ __device__ __forceinline__ void pair_step(uint2 *st, const uint32_t *qa, int str
   r.left = (uint32_t)(l0 + c.bias) | (uint32_t)(l1 + c.bias) << 16;
   r.tt = (uint32_t)t0 << 14 | (uint32_t)t1 << 30;
   r.mj0 = -1; r.mj1 = -1;
-  // the four window ends in order: [v0,v1) at most one slot, [v1,v2) both (when they overlap), [v2,v3) at most one slot
-  const int v0 = min(a0, b0), v3 = max(a1, b1);
-  const int x1 = max(a0, b0), x2 = min(a1, b1);
-  const int v1 = min(x1, x2), v2 = max(x1, x2);
-  {                                                    // phase 1
-    const int in0 = (v0 >= a0 && v1 <= a1), in1 = (v0 >= b0 && v1 <= b1);
-    if (v0 < v1 && (in0 || in1)) {
-      const int sel = in0 ? 0 : 1;
-      const uint32_t keep = sel ? 0x0000FFFFu : 0xFFFF0000u;
-      const PairRow s = r;
-      pair_cols<true>(st, qa, stride, v0, v1, r, c, sel);
-      r.f = (r.f & ~keep) | (s.f & keep); r.left = (r.left & ~keep) | (s.left & keep); r.m = (r.m & ~keep) | (s.m & keep);
-      if (sel) r.mj0 = s.mj0; else r.mj1 = s.mj1;
-    }
-  }
-  if (v1 < v2 && v1 >= a0 && v2 <= a1 && v1 >= b0 && v2 <= b1)   // phase 2: both slots inside their windows
-    pair_cols<false>(st, qa, stride, v1, v2, r, c, 0);
-  else if (v1 < v2) {                                  // disjoint windows: the gap belongs to nobody, unless one window is empty
-    const int in0 = (v1 >= a0 && v2 <= a1), in1 = (v1 >= b0 && v2 <= b1);
-    if (in0 || in1) {
-      const int sel = in0 ? 0 : 1;
-      const uint32_t keep = sel ? 0x0000FFFFu : 0xFFFF0000u;
-      const PairRow s = r;
-      pair_cols<true>(st, qa, stride, v1, v2, r, c, sel);
-      r.f = (r.f & ~keep) | (s.f & keep); r.left = (r.left & ~keep) | (s.left & keep); r.m = (r.m & ~keep) | (s.m & keep);
-      if (sel) r.mj0 = s.mj0; else r.mj1 = s.mj1;
-    }
-  }
-  {                                                    // phase 3
-    const int in0 = (v2 >= a0 && v3 <= a1), in1 = (v2 >= b0 && v3 <= b1);
-    if (v2 < v3 && (in0 || in1)) {
-      const int sel = in0 ? 0 : 1;
-      const uint32_t keep = sel ? 0x0000FFFFu : 0xFFFF0000u;
-      const PairRow s = r;
-      pair_cols<true>(st, qa, stride, v2, v3, r, c, sel);
-      r.f = (r.f & ~keep) | (s.f & keep); r.left = (r.left & ~keep) | (s.left & keep); r.m = (r.m & ~keep) | (s.m & keep);
-      if (sel) r.mj0 = s.mj0; else r.mj1 = s.mj1;
-    }
-  }
-  done0 = done1 = false;
-  if (act0) done0 = slot_row_end(k0, 0, st, stride, sc, c.bias, (int)(r.left & 0xFFFFu) - c.bias, (int)(r.m & 0xFFFFu) - c.bias, r.mj0);
-  if (act1) done1 = slot_row_end(k1, 1, st, stride, sc, c.bias, (int)(r.left >> 16) - c.bias, (int)(r.m >> 16) - c.bias, r.mj1);
+  pair_cols(st, qa, stride, a0, a1, b0, b1, r, c);
+  const int e0 = (int)(r.left & 0xFFFFu) - c.bias, e1 = (int)(r.left >> 16) - c.bias;
+  done0 = act0 && slot_row_score<EXACT>(k0, 0, st, stride, sc, c.bias, e0, (int)(r.m & 0xFFFFu) - c.bias, r.mj0);
+  done1 = act1 && slot_row_score<EXACT>(k1, 1, st, stride, sc, c.bias, e1, (int)(r.m >> 16) - c.bias, r.mj1);
+  const bool tr0 = act0 && !done0, tr1 = act1 && !done1;
+  TrimProbe p0, p1;
+  if (tr0) slot_trim_probe(k0, 0, st, stride, p0);
+  if (tr1) slot_trim_probe(k1, 1, st, stride, p1);
+  if (tr0) done0 = slot_trim<EXACT>(k0, 0, st, stride, c.B2, p0, e0);
+  if (tr1) done1 = slot_trim<EXACT>(k1, 1, st, stride, c.B2, p1, e1);
 }
 
 } // namespace bwaflow

@@ -114,6 +114,10 @@ int bwaflow_ext_collect(bwaflow_ext_batch_t *b, const bwaflow_ext_result_t **out
 /* device-resident re-run of the last submitted inputs (bench: inputs already in HBM); results stay on device
  * until bwaflow_ext_collect.  */
 int bwaflow_ext_rerun(bwaflow_ext_batch_t *b);
+/* same, with the kernel variant that also counts the DP cells ksw_extend2 executes for these jobs (the GCUPS work unit,
+ * bwa/ksw.c:424-448 iterations); the count is reported as timing.work_units by this and later collects of the same inputs.
+ * Results are identical to the uncounted variant. */
+int bwaflow_ext_rerun_counted(bwaflow_ext_batch_t *b);
 
 /* ---- stage 4: chains -> alignment regions (replaces ChainsToRegionsFPGA::compute, src/fpga/FPGAPipeline.cpp:367;
  *      arithmetic = mem_chain2aln bwa/bwamem.c:641-795 incl. the containment skip the FPGA path drops) */

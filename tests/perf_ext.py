@@ -41,6 +41,10 @@ def main():
     eb = capi.ExtBatch(ctx, len(ej), len(qpp) + 1, len(tpp) + 1)
     eb.submit(ej, qpp, tpp)
     res, t = eb.collect()
+    eb.rerun(counted=True)
+    res2, tc = eb.collect()
+    assert all((res2[k] == res[k]).all() for k in capi.EXT_RES.names), "counted and plain kernel variants disagree"
+    t.work_units = tc.work_units
     ok = all((res[k][:n0] == jobs[k]).all() for k in capi.EXT_RES.names) and all((res[k][-n0:] == jobs[k]).all() for k in capi.EXT_RES.names)
     cells = t.work_units
     print("parity %s; e2e %.2f ms (h2d %.2f kernel %.2f d2h %.2f); cells %.4g (%.0f per job)" % (ok, t.total_ms, t.h2d_ms, t.kernel_ms, t.d2h_ms, cells, cells / len(ej)))

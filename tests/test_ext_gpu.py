@@ -42,9 +42,14 @@ def test_ext_matches_golden(case, request, ctx, engine):
     got, t = b.collect()
     bad = np.nonzero(got != exp)[0]
     assert len(bad) == 0, (bad[:5], got[bad[:5]], exp[bad[:5]], jobs[bad[:5]])
-    # resubmitting and re-running are idempotent
+    # re-running (plain and cell-counting kernel variants) and resubmitting are idempotent
     b.rerun()
-    b.collect()
+    got1, _ = b.collect()
+    assert (got1 == exp).all()
+    b.rerun(counted=True)
+    got1, t1 = b.collect()
+    assert (got1 == exp).all()
+    assert t1.work_units == float(g["jobs"]["cells"].sum()) if "cells" in g["jobs"].dtype.names else t1.work_units > 0
     b.submit(jobs, qp, tp)
     got2, _ = b.collect()
     assert (got2 == exp).all()
@@ -99,12 +104,20 @@ def test_ext_matches_oracle_random(qmax, zdrop, ctx, engine):
     ctx.set_opt(opt)
     mat = np.array(list(opt.mat), dtype=np.int8)
     n = 1500 if qmax <= 200 else 300
+    from oracle import api
+    api.orc_lib().orc_counters_reset()
     jobs, qp, tp, exp = _random_jobs(rng, n, qmax, mat, opt)
+    cells = int(api.orc_lib().orc_cells())
     b = capi.ExtBatch(ctx, n, len(qp), len(tp))
     b.submit(jobs, qp, tp)
     got, _ = b.collect()
     bad = np.nonzero(got != exp)[0]
     assert len(bad) == 0, (bad[:5], got[bad[:5]], exp[bad[:5]], jobs[bad[:5]])
+    b.rerun(counted=True)
+    got, tc = b.collect()
+    bad = np.nonzero(got != exp)[0]
+    assert len(bad) == 0, (bad[:5], got[bad[:5]], exp[bad[:5]], jobs[bad[:5]])
+    assert tc.work_units == float(cells), (tc.work_units, cells)
     b.close()
     ctx.set_opt(capi.default_opt())
 
