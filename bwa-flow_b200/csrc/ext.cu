@@ -37,6 +37,7 @@ struct ExtArgs {
   unsigned long long *cells;
   int cls, qmax;
   int refill;                 // refill idle lanes once at least this many are idle
+  int pair_sync;              // packed kernel: refill the two slots of a lane together
   DevScore sc;
   PairConsts pc;
 };
@@ -155,9 +156,13 @@ __global__ void __launch_bounds__(32) ext_pair_kernel(const ExtArgs a)
   bool drained = false;
 
   for (;;) {
-    const unsigned idle0 = __ballot_sync(full, !act[0]), idle1 = __ballot_sync(full, !act[1]);
+    // Refill.  pair_sync: a lane takes two queue-adjacent jobs (same qlen class, nearly the same qlen and tlen after the
+    // sort) when BOTH its slots are idle, so the two jobs of a lane walk the same band windows row for row; otherwise
+    // every idle slot is refilled on its own.
+    unsigned idle0 = __ballot_sync(full, !act[0]), idle1 = __ballot_sync(full, !act[1]);
+    if (a.pair_sync) idle0 = idle1 = idle0 & idle1;
     const int n_idle = __popc(idle0) + __popc(idle1);
-    if (n_idle == 64 || (!drained && n_idle >= a.refill)) {
+    if (__popc(__ballot_sync(full, !act[0] && !act[1])) == 32 || (!drained && n_idle >= a.refill)) {
       int base = q_end;
       if (!drained) {
         if (lane == 0) base = atomicAdd(head, n_idle);
@@ -166,8 +171,9 @@ __global__ void __launch_bounds__(32) ext_pair_kernel(const ExtArgs a)
       }
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        if (act[s]) continue;
-        const int slot = base + (s ? __popc(idle0) + __popc(idle1 & ((1u << lane) - 1)) : __popc(idle0 & ((1u << lane) - 1)));
+        if (act[s] || !((s ? idle1 : idle0) >> lane & 1)) continue;
+        const int below = __popc(idle0 & ((1u << lane) - 1));
+        const int slot = base + (a.pair_sync ? 2 * below + s : s ? __popc(idle0) + __popc(idle1 & ((1u << lane) - 1)) : below);
         if (slot >= q_end) continue;
         job[s] = (int)a.order[slot];
         const bwaflow_ext_job_t jb = a.jobs[job[s]];
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(32) ext_pair_kernel(const ExtArgs a)
         act[s] = false;
         pair_retire(s, qa, stride, k[s].qlen);
       }
-    if (act[0] || act[1]) {
+    {
       bool d0, d1;
       const int t0 = act[0] ? tcur[0] : 0, t1 = act[1] ? tcur[1] : 0;
       // next rows' target bases are fetched before the row so that the load overlaps it
@@ -236,7 +242,7 @@ struct bwaflow_ext_batch {
   bwaflow_ext_result_t *d_out, *h_out;
   int *h_err;                       // err | pad | cells (u64)
   int blocks[EXT_NCLASS], blocks_pair[EXT_NCLASS];
-  int refill, refill_pair;
+  int refill, refill_pair, pair_sync;
   bool use_pair, multi_stream;
   double cells_known;
   bool count_cells;            // this launch runs the cell-counting (EXACT) variant of the packed kernel
@@ -273,7 +279,7 @@ static int ext_launch(bwaflow_ext_batch *b)
     cudaStream_t cs = b->multi_stream ? b->cstream[c] : b->stream;
     if (b->multi_stream) BF_CUDA(cudaStreamWaitEvent(cs, b->ev_fork, 0));
     if (b->use_pair && c < EXT_PAIR_CLASSES) {
-      a.refill = b->refill_pair;
+      a.refill = b->refill_pair; a.pair_sync = b->pair_sync;
       if (b->count_cells) ext_pair_kernel<true><<<b->blocks_pair[c], 32, pair_smem(h_ext_qmax[c]), cs>>>(a);
       else ext_pair_kernel<false><<<b->blocks_pair[c], 32, pair_smem(h_ext_qmax[c]), cs>>>(a);
     } else {
@@ -310,6 +316,8 @@ int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_q
   if (const char *s = getenv("BWAFLOW_EXT_REFILL")) b->refill = atoi(s) > 0 ? atoi(s) : 8;
   b->refill_pair = 16;
   if (const char *s = getenv("BWAFLOW_EXT_REFILL_PAIR")) b->refill_pair = atoi(s) > 0 ? atoi(s) : 16;
+  b->pair_sync = 0;
+  if (const char *s = getenv("BWAFLOW_EXT_PAIR_SYNC")) b->pair_sync = atoi(s) != 0;
   b->multi_stream = true;
   if (const char *s = getenv("BWAFLOW_EXT_STREAMS")) b->multi_stream = atoi(s) != 1;
   fill_pair_consts(ctx->par.opt, ctx->par.sc, b->pc);

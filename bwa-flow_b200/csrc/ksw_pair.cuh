@@ -169,29 +169,37 @@ __device__ __forceinline__ void pair_cell_gated(uint2 *p, uint32_t qsh, int j, P
   r.left = hg | (r.left & ~gm);
 }
 
-// Columns of one row for both slots: slot 0 in [a0,a1), slot 1 in [b0,b1) (empty = [0,0)), walked in aligned groups of
-// 8 columns (one query word).  Groups entirely inside both windows run the plain cell with constant query shifts; the
-// boundary groups run the gated cell.
+// Columns of one row for both slots of every lane of the warp: slot 0 in [a0,a1), slot 1 in [b0,b1) (empty = [0,0)).
+// The warp walks aligned 4-column subgroups from the leftmost window start to the rightmost window end of ANY lane, and
+// decides per subgroup, by vote, between the plain cell (every lane has the subgroup inside both of its windows) and the
+// gated cell (per-lane, per-half masks; a lane with nothing there rewrites what it read).  Control flow is therefore
+// warp-uniform: no divergence, no reconvergence stacks, and the cells of a subgroup overlap in the pipeline.
+// Must be called by all 32 lanes.
 __device__ __forceinline__ void pair_cols(uint2 *st, const uint32_t *qa, int stride, int a0, int a1, int b0, int b1, PairRow &r,
                                           const PairConsts &c)
 {
-  const int in0 = max(a0, b0), in1 = min(a1, b1);                  // columns inside both windows
-  int jb = (a0 < a1 ? (b0 < b1 ? min(a0, b0) : a0) : b0) & ~7;
-  const int jend = max(a1, b1);
+  const unsigned full = 0xffffffffu;
+  const int in0 = max(a0, b0), in1 = min(a1, b1);                  // columns inside both windows of this lane
+  const int lo = a0 < a1 ? (b0 < b1 ? min(a0, b0) : a0) : (b0 < b1 ? b0 : 0x7fffffff);
+  const int hi = max(a1, b1);
+  const bool nowin = hi == 0;                                      // a lane without any window goes along with the plain cell: what it
+                                                                   // computes on its retired halves can only decay (pair_retire)
+  int jb = __reduce_min_sync(full, lo) & ~3;
+  const int jend = __reduce_max_sync(full, hi);
   uint2 *p = st + (size_t)jb * stride;
-  const uint32_t *qp = qa + (jb >> 3) * stride;
 #pragma unroll 1
-  for (; jb < jend; jb += 8, p += 8 * stride, qp += stride) {
-    const uint32_t qw = *qp;
-    if (jb >= in0 && jb + 8 <= in1) {
+  for (; jb < jend; jb += 4, p += 4 * stride) {
+    uint32_t qw = qa[(jb >> 3) * stride];
+    if (jb & 4) qw >>= 8;
+    if (__all_sync(full, nowin || (jb >= in0 && jb + 4 <= in1))) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) pair_cell(p + u * stride, mad_fma(qw, 1u << (14 - 2 * u), 0u), jb + u, r, c);
+      for (int u = 0; u < 4; ++u) pair_cell(p + u * stride, mad_fma(qw, 1u << (14 - 2 * u), 0u), jb + u, r, c);
     } else {
       // bit u (slot 0) / bit 16+u (slot 1) = column jb+u inside the slot's window
-      const int sa = min(max(a0 - jb, 0), 8), ea = min(max(a1 - jb, 0), 8), sb = min(max(b0 - jb, 0), 8), eb = min(max(b1 - jb, 0), 8);
+      const int sa = min(max(a0 - jb, 0), 4), ea = min(max(a1 - jb, 0), 4), sb = min(max(b0 - jb, 0), 4), eb = min(max(b1 - jb, 0), 4);
       const uint32_t mm = (((1u << ea) - 1u) & ~((1u << sa) - 1u)) | (((1u << eb) - 1u) & ~((1u << sb) - 1u)) << 16;
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < 4; ++u)
         pair_cell_gated(p + u * stride, mad_fma(qw, 1u << (14 - 2 * u), 0u), jb + u, r, c, ((mm >> u) & 0x00010001u) * 0xFFFFu);
     }
   }
@@ -207,7 +215,7 @@ __device__ __forceinline__ void slot_row_begin(KswSlot &k, const DevScore &sc, i
   if (k.hi > k.i + k.w + 1) k.hi = k.i + k.w + 1;
   if (k.hi > k.qlen) k.hi = k.qlen;
   c0 = k.lo;
-  if (!EXACT) { c0 &= ~7; if (c0 < k.i - k.w) c0 = k.i - k.w; }     // start on a group boundary when the band allows
+  if (!EXACT) { c0 &= ~3; if (c0 < k.i - k.w) c0 = k.i - k.w; }     // start on a subgroup boundary when the band allows
   left = 0;
   if (c0 == 0) { left = k.h0 - (sc.o_del + sc.e_del * (k.i + 1)); left = left > 0 ? left : 0; }
 }
@@ -302,7 +310,9 @@ __device__ __forceinline__ void pair_step(uint2 *st, const uint32_t *qa, int str
   r.left = (uint32_t)(l0 + c.bias) | (uint32_t)(l1 + c.bias) << 16;
   r.tt = (uint32_t)t0 << 14 | (uint32_t)t1 << 30;
   r.mj0 = -1; r.mj1 = -1;
+  const PairRow r0 = r;
   pair_cols(st, qa, stride, a0, a1, b0, b1, r, c);
+  if (a1 == 0 && b1 == 0) r = r0;                       // no window: whatever the lane computed along with the warp is discarded
   const int e0 = (int)(r.left & 0xFFFFu) - c.bias, e1 = (int)(r.left >> 16) - c.bias;
   done0 = act0 && slot_row_score<EXACT>(k0, 0, st, stride, sc, c.bias, e0, (int)(r.m & 0xFFFFu) - c.bias, r.mj0);
   done1 = act1 && slot_row_score<EXACT>(k1, 1, st, stride, sc, c.bias, e1, (int)(r.m >> 16) - c.bias, r.mj1);
