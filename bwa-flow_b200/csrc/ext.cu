@@ -242,7 +242,7 @@ struct bwaflow_ext_batch {
   bwaflow_ext_result_t *d_out, *h_out;
   int *h_err;                       // err | pad | cells (u64)
   int blocks[EXT_NCLASS], blocks_pair[EXT_NCLASS];
-  int refill, refill_pair, pair_sync;
+  int refill, refill_pair, pair_sync, pair_classes;
   bool use_pair, multi_stream;
   double cells_known;
   bool count_cells;            // this launch runs the cell-counting (EXACT) variant of the packed kernel
@@ -278,7 +278,7 @@ static int ext_launch(bwaflow_ext_batch *b)
     a.cls = c; a.qmax = h_ext_qmax[c];
     cudaStream_t cs = b->multi_stream ? b->cstream[c] : b->stream;
     if (b->multi_stream) BF_CUDA(cudaStreamWaitEvent(cs, b->ev_fork, 0));
-    if (b->use_pair && c < EXT_PAIR_CLASSES) {
+    if (b->use_pair && c < b->pair_classes) {
       a.refill = b->refill_pair; a.pair_sync = b->pair_sync;
       if (b->count_cells) ext_pair_kernel<true><<<b->blocks_pair[c], 32, pair_smem(h_ext_qmax[c]), cs>>>(a);
       else ext_pair_kernel<false><<<b->blocks_pair[c], 32, pair_smem(h_ext_qmax[c]), cs>>>(a);
@@ -317,6 +317,8 @@ int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_q
   b->refill_pair = 16;
   if (const char *s = getenv("BWAFLOW_EXT_REFILL_PAIR")) b->refill_pair = atoi(s) > 0 ? atoi(s) : 16;
   b->pair_sync = 0;
+  b->pair_classes = EXT_PAIR_CLASSES;
+  if (const char *s = getenv("BWAFLOW_EXT_PAIR_CLASSES")) b->pair_classes = atoi(s) < EXT_PAIR_CLASSES ? atoi(s) : EXT_PAIR_CLASSES;
   if (const char *s = getenv("BWAFLOW_EXT_PAIR_SYNC")) b->pair_sync = atoi(s) != 0;
   b->multi_stream = true;
   if (const char *s = getenv("BWAFLOW_EXT_STREAMS")) b->multi_stream = atoi(s) != 1;

@@ -33,7 +33,7 @@ namespace bwaflow {
 struct PairConsts {
   int ok;                      // scoring matrix has the packed form
   int a, b, bias;
-  uint32_t B2, A2, NAB, K, HKC, OED2, ED2, OEI2, EI2;
+  uint32_t B2, A2, NAB, K, HKC, OED2, ED2, OEI2, EI2, NEI2;
 };
 
 inline void fill_pair_consts(const bwaflow_opt_t &o, const DevScore &sc, PairConsts &c)
@@ -57,6 +57,7 @@ inline void fill_pair_consts(const bwaflow_opt_t &o, const DevScore &sc, PairCon
   c.HKC = (uint32_t)0 - (uint32_t)(c.bias * a) * one;
   c.OED2 = (uint32_t)(sc.o_del + sc.e_del) * one; c.ED2 = (uint32_t)sc.e_del * one;
   c.OEI2 = (uint32_t)(sc.o_ins + sc.e_ins) * one; c.EI2 = (uint32_t)sc.e_ins * one;
+  c.NEI2 = (uint32_t)(uint16_t)(-sc.e_ins) * one;      // per-half -e_ins, added inside the DPX instruction
 }
 
 __device__ __forceinline__ uint32_t mad_fma(uint32_t a, uint32_t b, uint32_t c)
@@ -137,7 +138,7 @@ __device__ __forceinline__ void pair_cell(uint2 *p, uint32_t qsh, int j, PairRow
   const uint32_t M = __vmins2(x, hk);
   const uint32_t h = __vimax3_s16x2(M, v.y, r.f);
   const uint32_t e2 = __vimax3_s16x2(sub_fma(M, c.OED2), sub_fma(v.y, c.ED2), c.B2);
-  r.f = __vimax3_s16x2(sub_fma(M, c.OEI2), sub_fma(r.f, c.EI2), c.B2);
+  r.f = __viaddmax_s16x2(r.f, c.NEI2, __vmaxs2(sub_fma(M, c.OEI2), c.B2));   // one dependent op per cell on the F chain
   bool ph, pl;
   r.m = __vibmax_s16x2(h, r.m, &ph, &pl);                            // predicates: h >= running max (last column wins ties)
   r.mj0 = pl ? j : r.mj0;
@@ -159,7 +160,7 @@ __device__ __forceinline__ void pair_cell_gated(uint2 *p, uint32_t qsh, int j, P
   const uint32_t M = __vmins2(x, hk);
   const uint32_t hg = __vimax3_s16x2(M, v.y, r.f) & gm;
   const uint32_t e2 = __vimax3_s16x2(sub_fma(M, c.OED2), sub_fma(v.y, c.ED2), c.B2);
-  const uint32_t f2 = __vimax3_s16x2(sub_fma(M, c.OEI2), sub_fma(r.f, c.EI2), c.B2);
+  const uint32_t f2 = __viaddmax_s16x2(r.f, c.NEI2, __vmaxs2(sub_fma(M, c.OEI2), c.B2));
   r.f = (f2 & gm) | (r.f & ~gm);
   bool ph, pl;
   r.m = __vibmax_s16x2(hg, r.m, &ph, &pl);
