@@ -20,7 +20,7 @@ namespace bwaflow {
 constexpr int EXT_NCLASS = 8;
 constexpr int EXT_NQ = EXT_NCLASS + 1;
 constexpr int CTL_HIST = 0, CTL_QUEUE = EXT_NCLASS, CTL_ERR = CTL_QUEUE + 2 * EXT_NQ, CTL_CELLS = CTL_ERR + 2, CTL_INTS = CTL_CELLS + 2;
-constexpr int EXT_PAIR_CLASSES = 7;      // classes 0..6 run on the packed two-jobs-per-lane engine (row state of class 7 would not fit)
+constexpr int EXT_PAIR_CLASSES = 5;      // classes 0..4 (qlen <= 159) run on the packed two-jobs-per-lane engine; wider row states leave too few warps per SM for it to pay (measured)
 // qlen <= qmax runs in class c with `threads` lanes per block; row state = threads*(qmax+1)*4 bytes
 __constant__ int c_ext_qmax[EXT_NCLASS] = {31, 63, 95, 127, 159, 255, 511, 1023};
 static const int h_ext_qmax[EXT_NCLASS] = {31, 63, 95, 127, 159, 255, 511, 1023};
