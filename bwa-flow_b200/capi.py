@@ -114,6 +114,7 @@ def lib():
         L.bwaflow_ctx_sync.argtypes = [C.c_void_p]
         L.bwaflow_dpx_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.bwaflow_index_build.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.bwaflow_index_build_gpu.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
         L.bwaflow_built_index_view.restype = C.POINTER(Index)
         L.bwaflow_built_index_view.argtypes = [C.c_void_p]
         L.bwaflow_built_index_free.argtypes = [C.c_void_p]
@@ -367,12 +368,16 @@ def chain_build(l_pac, ctg_off, ctg_len, read_off, intv, intv_off, pos, pos_off,
 class BuiltIndex:
     """FM-index of a synthetic reference built by the library (same arrays as `bwa index` + bwa_idx_load)."""
 
-    def __init__(self, codes, contig_len, n_threads=0):
+    def __init__(self, codes, contig_len, n_threads=0, device=None):
+        """device=None: host builder (threads); device=i: the CUDA builder on GPU i."""
         self.L = lib()
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         cl = np.ascontiguousarray(contig_len, dtype=np.int64)
         self.h = C.c_void_p()
-        check(self.L.bwaflow_index_build(_p(codes), len(codes), len(cl), _p(cl), int(n_threads), C.byref(self.h)))
+        if device is None:
+            check(self.L.bwaflow_index_build(_p(codes), len(codes), len(cl), _p(cl), int(n_threads), C.byref(self.h)))
+        else:
+            check(self.L.bwaflow_index_build_gpu(int(device), _p(codes), len(codes), len(cl), _p(cl), C.byref(self.h)))
         self.view = self.L.bwaflow_built_index_view(self.h).contents
         self.ctg_off = np.concatenate([[0], np.cumsum(cl)])[:-1].astype(np.int64)
         self.ctg_len = cl.astype(np.int32)

@@ -15,20 +15,11 @@
 #include <atomic>
 #include <thread>
 #include <vector>
-#include "../../include/bwaflow_cuda.h"
+#include "built_index.h"
 
 namespace bwaflow {
 void set_error(const char *fmt, ...);
 }
-
-struct bwaflow_built_index {
-  std::vector<uint32_t> bwt;
-  std::vector<uint64_t> sa;
-  std::vector<uint8_t> pac;
-  std::vector<int64_t> ctg_offset;
-  std::vector<int32_t> ctg_len;
-  bwaflow_index_t view;
-};
 
 namespace {
 

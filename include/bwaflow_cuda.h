@@ -200,6 +200,10 @@ int bwaflow_hot_collect(bwaflow_hot_batch_t *b, const bwaflow_alnreg_t **regs, c
 typedef struct bwaflow_built_index bwaflow_built_index_t;
 int bwaflow_index_build(const uint8_t *codes, int64_t n_bases, int32_t n_contigs, const int64_t *contig_len,
                         int n_threads /* <1: all cores */, bwaflow_built_index_t **out);
+/* the same arrays built on GPU `device` (suffix sort, BWT, occurrence layout and SA sampling in HBM); needs about 12 bytes of
+ * device memory per suffix (2 * n_bases suffixes).  Bit-identical to bwaflow_index_build. */
+int bwaflow_index_build_gpu(int device, const uint8_t *codes, int64_t n_bases, int32_t n_contigs, const int64_t *contig_len,
+                            bwaflow_built_index_t **out);
 const bwaflow_index_t *bwaflow_built_index_view(const bwaflow_built_index_t *b);
 void bwaflow_built_index_free(bwaflow_built_index_t *b);
 
