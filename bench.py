@@ -2,10 +2,12 @@
 """bench.py -- hot-path throughput of the B200 backend (and, with --impl reference, of the reference's own CPU path).
 
 Metric: read pairs/s of the BWA-MEM per-read compute path (SMEM seeding -> chaining -> banded extension, i.e. kflow
-stages 2..4: reads in, mem_alnreg_t lists out) on BASELINE.json config[2]'s shape: a synthetic chr20-scale (64 Mbp)
-reference and 2x150 bp pairs at 1% substitutions.  One step = one pass of the hot path over one device batch
-(16 kflow records of 10 Mbp = 533,344 pairs by default).  Per rank the work is fixed (weak scaling): the index is
-replicated per GPU and every rank processes its own read shard; there is no data-path collective.
+stages 2..4: reads in, mem_alnreg_t lists out) on the configuration BASELINE.json's metric is quoted on (config[3]): a
+synthetic human-scale 3.1 Gbp reference in 24 contigs, FM-index (4.65 GB + 0.78 GB pac) replicated per GPU, and 2x150 bp
+pairs at 1% substitutions.  The index is built in HBM by the library's CUDA builder (seconds; bit-identical to `bwa index`,
+tests/test_index_build_gpu.py) before the timed region.  One step = one pass of the hot path over one device batch
+(16 kflow records of 10 Mbp = 533,344 pairs by default).  Per rank the work is fixed (weak scaling): every rank builds and
+holds its own index replica and processes its own read shard; there is no data-path collective.
 
   value  = pairs/s with the reads already resident in HBM when the timed region starts
   e2e    = pairs/s through the public stage API from pinned HOST buffers (H2D of the reads and D2H of the regions inside)
@@ -40,8 +42,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-mbp", type=float, default=64.0)
-    ap.add_argument("--contigs", type=int, default=4)
+    ap.add_argument("--ref-mbp", type=float, default=3100.0)
+    ap.add_argument("--contigs", type=int, default=24)
+    ap.add_argument("--host-index", action="store_true", help="build the index with the host builder (small references only)")
     ap.add_argument("--kflow-batches", type=int, default=16, help="10 Mbp records per device batch (= one step)")
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--sub-rate", type=float, default=0.01)
@@ -106,18 +109,11 @@ class ClockSampler:
 
 def make_workload(args, rank):
     from bwaflow_b200 import synth
-    ref = synth.make_reference(int(args.ref_mbp * 1e6), n_contigs=args.contigs, seed=64)
+    ref = synth.make_reference(int(args.ref_mbp * 1e6), n_contigs=args.contigs, seed=3100)
     pairs_per_record = -(-KFLOW_BATCH_BP // (2 * args.read_len))           # getKseqBatch: stop at >= 10 Mbp, even count
     n_pairs = pairs_per_record * args.kflow_batches
     reads = synth.simulate_pairs(ref, n_pairs, args.read_len, args.sub_rate, seed=3 + rank, first_id=rank * n_pairs)
     return ref, reads, n_pairs, pairs_per_record
-
-
-def shared_dir(args):
-    d = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(),
-                     "bwaflow_bench_%d_%d_%d" % (int(args.ref_mbp * 1000), args.contigs, os.getuid()))
-    os.makedirs(d, exist_ok=True)
-    return d
 
 
 def barrier_max(x, world):
@@ -145,20 +141,26 @@ def cpu_hot_path(R, reads, lo, hi):
     b.free()
 
 
-def run_reference_cpu(args, ref, reads, n_pairs_sample, built=None):
-    """Times the compiled reference's hot path (oracle/_ref) with one thread per host core over a bounded sample."""
+def build_index(args, ref, device):
+    """FM-index arrays for the run: the CUDA builder (default; the only way to have a 3.1 Gbp index in a bench run) or the host one."""
+    from bwaflow_b200 import capi
+    return capi.BuiltIndex(ref.concat(), ref.lengths, device=None if args.host_index else device)
+
+
+def run_reference_cpu(args, ref, reads, n_pairs_sample, built):
+    """Times the compiled reference's hot path (oracle/_ref) with one thread per host core over a bounded sample.  The reference
+    loads the index with its own bwa_idx_load from files in bwa's on-disk format, written from the arrays the builder produced
+    (`bwa index` itself would need hours for 3.1 Gbp; the arrays are bit-identical, tests/test_index_build*.py)."""
     from oracle import api
     from concurrent.futures import ThreadPoolExecutor
-    td = tempfile.mkdtemp(prefix="bwaflow_ref_")
+    import shutil
+    td = tempfile.mkdtemp(prefix="bwaflow_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     prefix = os.path.join(td, "ref")
-    if built is not None:
-        v = built.view
-        api.write_index_files(prefix, v.primary, list(v.L2), v.seq_len, built.bwt_array(), built.sa_array(), v.sa_intv,
-                              built.pac_array(), v.l_pac, ref.names, [int(x) for x in ref.lengths])
-    else:
-        ref.write_fasta(prefix + ".fa")
-        api.build_index(prefix + ".fa", prefix)
+    v = built.view
+    api.write_index_files(prefix, v.primary, list(v.L2), v.seq_len, built.bwt_array(), built.sa_array(), v.sa_intv,
+                          built.pac_array(), v.l_pac, ref.names, [int(x) for x in ref.lengths])
     R = api.Ref(prefix, paired=True)
+    shutil.rmtree(td, ignore_errors=True)
     cores = os.cpu_count() or 1
     n_reads = 2 * n_pairs_sample
     chunk = max(2, (n_reads // (cores * 4)) & ~1)
@@ -183,18 +185,21 @@ def main():
     if args.impl == "reference" and rank != 0:
         return
     ref, reads, n_pairs, pairs_per_record = make_workload(args, rank)
-    workload = {"workload": "C3 shape: synthetic %.0f Mbp reference (%d contigs, FM-index replicated per GPU), 2x%dbp pairs @%.0f%% subst"
+    workload = {"workload": "BASELINE config[3] shape: synthetic %.0f Mbp reference (%d contigs, FM-index replicated per GPU), 2x%dbp pairs @%.0f%% subst"
                             % (args.ref_mbp, args.contigs, args.read_len, args.sub_rate * 100),
                 "pairs_per_step_per_gpu": n_pairs, "kflow_records_per_step": args.kflow_batches,
-                "l2": "inputs larger than L2: %.0f MB of reads per step plus >1 GB of per-step interval/region scratch rewritten every step "
-                      "(the %.0f MB FM-index itself is smaller than the 126 MB L2, as it would be in a real run on this reference)"
-                      % (2 * n_pairs * args.read_len / 1e6, args.ref_mbp * 1.5)}
+                "l2": "inputs larger than L2: %.0f MB FM-index + sampled SA + pac (random access), %.0f MB of reads per step and >1 GB of "
+                      "per-step interval/region scratch rewritten every step, against a 126 MB L2"
+                      % (args.ref_mbp * 1.75, 2 * n_pairs * args.read_len / 1e6)}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = args.cpu_sample_pairs or n_pairs
-        R, one_pass, cores = run_reference_cpu(args, ref, reads, sample)
+        sample = args.cpu_sample_pairs or max(pairs_per_record, n_pairs // 4)
+        t0 = time.time()
+        built = build_index(args, ref, local)
+        workload["index_build_s"] = time.time() - t0
+        R, one_pass, cores = run_reference_cpu(args, ref, reads, sample, built)
         for _ in range(min(args.warmup, 1)):
             one_pass()
         ts = [one_pass() for _ in range(args.steps)]
@@ -211,39 +216,9 @@ def main():
 
     # ------------------------------------------------------------------ our arm
     from bwaflow_b200 import capi, stages
-    sd = shared_dir(args)
     t0 = time.time()
-    built = None
-    codes = ref.concat()
-    built = capi.BuiltIndex(codes, ref.lengths) if (world == 1 or rank == 0) else None
-    if world > 1:
-        # rank 0 builds, the others read the arrays from shared memory (replication, not sharding)
-        if rank == 0:
-            np.save(os.path.join(sd, "bwt.npy"), built.bwt_array())
-            np.save(os.path.join(sd, "sa.npy"), built.sa_array())
-            np.save(os.path.join(sd, "pac.npy"), built.pac_array())
-            v = built.view
-            json.dump({"primary": v.primary, "L2": list(v.L2), "seq_len": v.seq_len, "sa_intv": v.sa_intv, "l_pac": v.l_pac},
-                      open(os.path.join(sd, "meta.json"), "w"))
-        barrier(world)
-    if built is not None:
-        index, ctg_off, ctg_len, keep = built.index(), built.ctg_off, built.ctg_len, built
-    else:
-        meta = json.load(open(os.path.join(sd, "meta.json")))
-        bwt = np.load(os.path.join(sd, "bwt.npy"), mmap_mode="r")
-        sa = np.load(os.path.join(sd, "sa.npy"), mmap_mode="r")
-        pac = np.load(os.path.join(sd, "pac.npy"), mmap_mode="r")
-        bwt, sa, pac = np.ascontiguousarray(bwt), np.ascontiguousarray(sa), np.ascontiguousarray(pac)
-        index = capi.Index()
-        index.primary, index.seq_len, index.bwt_size, index.bwt = meta["primary"], meta["seq_len"], len(bwt), bwt.ctypes.data
-        for i in range(5):
-            index.L2[i] = meta["L2"][i]
-        index.n_sa, index.sa_intv, index.sa = len(sa), meta["sa_intv"], sa.ctypes.data
-        index.l_pac, index.pac, index.n_seqs = meta["l_pac"], pac.ctypes.data, len(ref.lengths)
-        ctg_off = np.ascontiguousarray(ref.offsets, dtype=np.int64)
-        ctg_len = np.ascontiguousarray(ref.lengths, dtype=np.int32)
-        index.ctg_offset, index.ctg_len = ctg_off.ctypes.data, ctg_len.ctypes.data
-        keep = (bwt, sa, pac, ctg_off, ctg_len)
+    built = build_index(args, ref, local)
+    index, keep = built.index(), built
     t_index = time.time() - t0
     ctx = capi.Context(local, index, keepalive=keep)
     nt4_np = reads.nt4()

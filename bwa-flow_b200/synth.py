@@ -16,15 +16,16 @@ _COMP = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
 class Reference:
     """A list of contigs, each a uint8 array of codes 0..3 (4 = N)."""
 
-    def __init__(self, names, contigs):
+    def __init__(self, names, contigs, whole=None):
         self.names = list(names)
         self.contigs = list(contigs)
         self.lengths = np.array([len(c) for c in contigs], dtype=np.int64)
         self.offsets = np.concatenate([[0], np.cumsum(self.lengths)])[:-1]
         self.total = int(self.lengths.sum())
+        self._whole = whole            # the contigs are views of this array when it is given
 
     def concat(self):
-        return np.concatenate(self.contigs)
+        return self._whole if self._whole is not None else np.concatenate(self.contigs)
 
     def write_fasta(self, path, width=80):
         with open(path, "wb") as f:
@@ -65,7 +66,7 @@ def make_reference(n_bp, n_contigs=1, seed=5, n_run_frac=0.0, repeat_copies=0, r
     bounds = np.linspace(0, n_bp, n_contigs + 1).astype(np.int64)
     contigs = [seq[bounds[i]:bounds[i + 1]] for i in range(n_contigs)]
     names = ["chr%d" % (i + 1) for i in range(n_contigs)]
-    return Reference(names, contigs)
+    return Reference(names, contigs, whole=seq)
 
 
 class ReadBatch:
