@@ -34,6 +34,7 @@ void fill_score(const bwaflow_opt_t &o, DevScore &s)
 } // namespace bwaflow
 
 using namespace bwaflow;
+namespace bwaflow { int densify_sa(bwaflow_ctx *c, int dense_shift, uint64_t n_sa, void **d_dense); }
 
 // bwa layout (4 x u64 counts + 8 x u32 symbols per 128 symbols, bwa/bwt.h:72-73) -> occ32 blocks (internal.cuh).
 // Pass 1, one thread per 64-symbol block: absolute suffix counts S1,S2,S3 (symbols >0, >1, >2 before the block).
@@ -182,7 +183,10 @@ int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt
   int r = bwaflow_ctx_set_opt(c, opt);
   if (r) { free(c); return r; }
 
+  if (const char *s = getenv("BWAFLOW_L2_FETCH")) BF_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(s)));
   if (idx) {
+    c->ix.occ_cs = 1;                           // streaming loads: random index sectors must not evict the per-lane lists from L2
+    if (const char *s = getenv("BWAFLOW_OCC_LOAD")) c->ix.occ_cs = strcmp(s, "ldg") != 0;
     BF_REQUIRE(idx->sa_intv > 0 && (idx->sa_intv & (idx->sa_intv - 1)) == 0, -22, "sa_intv must be a power of two");
     DevIndex &d = c->ix;
     d.primary = idx->primary; d.seq_len = idx->seq_len;
@@ -223,6 +227,20 @@ int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt
     }
     d.sa = (const uint64_t *)c->d_sa; d.pac = (const uint8_t *)c->d_pac;
     d.ctg_offset = (const int64_t *)c->d_ctg_off; d.ctg_len = (const int32_t *)c->d_ctg_len;
+    // Denser suffix-array sampling in HBM.  Default: the FULL suffix array (16 bytes per reference base, 49.6 GB of the 180 GB
+    // at 3.1 Gbp) instead of bwa's every 32nd row, so that a seed position is one read instead of a walk of ~16 dependent
+    // random index reads; BWAFLOW_SA_INTV=2,4,..,32 trades memory back.  bwt_sa values do not depend on the sampling.
+    int dense_intv = 1;
+    if (const char *s = getenv("BWAFLOW_SA_INTV")) dense_intv = atoi(s);
+    int dense_shift = 0;
+    while ((2 << dense_shift) <= dense_intv) ++dense_shift;
+    if (dense_intv >= 1 && dense_shift < d.sa_shift) {
+      void *d_dense = nullptr;
+      if ((r = densify_sa(c, dense_shift, idx->n_sa, &d_dense))) return r;
+      cudaFree(c->d_sa);
+      c->d_sa = d_dense;
+      d.sa = (const uint64_t *)d_dense; d.sa_shift = dense_shift;
+    }
     c->has_index = true;
   }
   *out = c;

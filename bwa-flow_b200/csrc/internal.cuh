@@ -36,6 +36,7 @@ struct DevIndex {
   // Same information as bwa's 64-byte/128-symbol blocks (bwa/bwt.h:72-73), re-laid out at upload: one 32-byte sector per
   // lookup and half the symbols to count.  sbt[j*5+t] = absolute count of symbols >= t before superblock j (t=0: its start).
   const uint4 *occ;
+  int occ_cs;              // load occ blocks with the streaming (evict-first) policy
   uint64_t sbt[8 * 5];
   const uint64_t *sa;
   int sa_shift;            // log2(sa_intv)
@@ -45,6 +46,10 @@ struct DevIndex {
   const int64_t *ctg_offset;
   const int32_t *ctg_len;
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint4 occ_ld(const DevIndex &ix, const uint4 *p) { return ix.occ_cs ? __ldcs(p) : __ldg(p); }
+#endif
 
 // Scoring as the extension kernels see it.  Matrix row t (target base) as 5 packed int8: lo = q0..q3, hi = q4.
 struct DevScore {

@@ -58,7 +58,7 @@ __device__ __forceinline__ void prefix_counts(const uint4 sy, int n, int c, int 
 __device__ __forceinline__ void occ_eq_gt(const DevIndex &ix, uint64_t k, int c, uint64_t *eq, uint64_t *gt)
 {
   const uint4 *b = ix.occ + ((k >> 6) << 1);
-  const uint4 hd = __ldg(b), sy = __ldg(b + 1);
+  const uint4 hd = occ_ld(ix, b), sy = occ_ld(ix, b + 1);
   int e, g;
   prefix_counts(sy, (int)(k & 63) + 1, c, &e, &g);
   const uint64_t *sb = ix.sbt + (k >> 31) * 5;
@@ -377,29 +377,66 @@ __global__ void __launch_bounds__(128) smem_p3_kernel(const SmemArgs a)
 }
 
 // bwt_sa, bwa/bwt.c:86-96 with bwt_invPsi :53-59 (symbol and its Occ come from the same occ32 block)
+// bwt_invPsi (bwa/bwt.c:53-59): the row of the suffix one position to the left; symbol and Occ come from the same occ32 block.
+__device__ __forceinline__ uint64_t inv_psi(const DevIndex &ix, uint64_t k)
+{
+  if (k == ix.primary) return 0;
+  const uint64_t x = k - (k > ix.primary);
+  const uint4 *b = ix.occ + ((x >> 6) << 1);
+  const uint4 hd = occ_ld(ix, b), sy = occ_ld(ix, b + 1);
+  const int r = (int)(x & 63);
+  const uint32_t word = (r >> 4) == 0 ? sy.x : (r >> 4) == 1 ? sy.y : (r >> 4) == 2 ? sy.z : sy.w;
+  const int c = (word >> ((~r & 15) << 1)) & 3;
+  int e, g;
+  prefix_counts(sy, r + 1, c, &e, &g);
+  const uint64_t *sb = ix.sbt + (x >> 31) * 5;
+  const uint32_t r0 = (uint32_t)(x & 0x7fffffffull) & ~63u;
+  const uint32_t lo_rel = c == 0 ? r0 : c == 1 ? hd.x : c == 2 ? hd.y : hd.z;
+  const uint32_t hi_rel = c == 0 ? hd.x : c == 1 ? hd.y : c == 2 ? hd.z : 0u;
+  return ix.L2[c] + (sb[c] + lo_rel) - (sb[c + 1] + hi_rel) + (uint64_t)e;
+}
+
+// bwt_sa (bwa/bwt.c:86-96) over the device-side sampling (every 2^sa_shift-th row; bwa_ctx_create may have made it denser than
+// bwa's 32, which does not change any value).  `blocks` counts the occ-block touches actually made.
 __device__ __forceinline__ uint64_t sa_lookup(const DevIndex &ix, uint64_t k, unsigned long long *blocks)
 {
   uint64_t steps = 0;
   const uint64_t mask = (1ull << ix.sa_shift) - 1;
   while (k & mask) {
     ++steps;
-    if (k == ix.primary) { k = 0; continue; }
-    const uint64_t x = k - (k > ix.primary);
-    const uint4 *b = ix.occ + ((x >> 6) << 1);
-    const uint4 hd = __ldg(b), sy = __ldg(b + 1);
-    const int r = (int)(x & 63);
-    const uint32_t word = (r >> 4) == 0 ? sy.x : (r >> 4) == 1 ? sy.y : (r >> 4) == 2 ? sy.z : sy.w;
-    const int c = (word >> ((~r & 15) << 1)) & 3;
-    int e, g;
-    prefix_counts(sy, r + 1, c, &e, &g);
-    const uint64_t *sb = ix.sbt + (x >> 31) * 5;
-    const uint32_t r0 = (uint32_t)(x & 0x7fffffffull) & ~63u;
-    const uint32_t lo_rel = c == 0 ? r0 : c == 1 ? hd.x : c == 2 ? hd.y : hd.z;
-    const uint32_t hi_rel = c == 0 ? hd.x : c == 1 ? hd.y : c == 2 ? hd.z : 0u;
-    k = ix.L2[c] + (sb[c] + lo_rel) - (sb[c + 1] + hi_rel) + (uint64_t)e;
-    ++*blocks;
+    k = inv_psi(ix, k);
   }
+  *blocks += steps;
   return steps + ix.sa[k >> ix.sa_shift];
+}
+
+// One thread per row sampled by bwa (every 2^ref_shift-th): walks invPsi until the next sampled row, handing its value minus
+// the number of steps to every row it passes whose index is a multiple of 2^dense_shift.  The walks partition all rows.
+__global__ void sa_densify_kernel(DevIndex ix, uint64_t n_sa, int dense_shift, uint64_t *dense)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_sa) return;
+  const uint64_t ref_mask = (1ull << ix.sa_shift) - 1, dmask = (1ull << dense_shift) - 1;
+  uint64_t r = j << ix.sa_shift, v = ix.sa[j];
+  dense[r >> dense_shift] = v;
+  if (j == 0) v = ix.seq_len;                  // sa[0] is stored as -1 == seq_len modulo the number of rows
+  for (;;) {
+    r = inv_psi(ix, r);
+    --v;
+    if ((r & ref_mask) == 0) break;
+    if ((r & dmask) == 0) dense[r >> dense_shift] = v;
+  }
+}
+
+int densify_sa(bwaflow_ctx *c, int dense_shift, uint64_t n_sa, void **d_dense)
+{
+  const uint64_t rows = c->ix.seq_len + 1;
+  const uint64_t n_dense = ((rows - 1) >> dense_shift) + 1;
+  BF_CUDA(cudaMalloc(d_dense, n_dense * 8));
+  sa_densify_kernel<<<(unsigned)((n_sa + 127) / 128), 128>>>(c->ix, n_sa, dense_shift, (uint64_t *)*d_dense);
+  BF_CUDA(cudaGetLastError());
+  BF_CUDA(cudaDeviceSynchronize());
+  return 0;
 }
 
 __global__ void sa_kernel(DevIndex ix, int64_t n, const uint64_t *k, uint64_t *out, unsigned long long *blocks)
