@@ -36,6 +36,30 @@ void fill_score(const bwaflow_opt_t &o, DevScore &s)
 using namespace bwaflow;
 namespace bwaflow { int densify_sa(bwaflow_ctx *c, int dense_shift, uint64_t n_sa, void **d_dense); }
 
+// forward + reverse complement text from the 2-bit pac, one thread per 32-symbol word
+__global__ void ctx_text_kernel(const uint8_t *pac, int64_t L, uint64_t *T, int64_t n_words)
+{
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  const int64_t n = 2 * L;
+  uint64_t v = 0;
+  for (int s = 0; s < 32; ++s) {
+    const int64_t p = w * 32 + s;
+    int c = 0;
+    if (p < L) c = (pac[p >> 2] >> ((~p & 3) << 1)) & 3;
+    else if (p < n) { const int64_t f = n - 1 - p; c = 3 - ((pac[f >> 2] >> ((~f & 3) << 1)) & 3); }
+    v = v << 2 | (uint64_t)c;
+  }
+  T[w] = v;
+}
+// isa[sa[r]] = r over all rows (row 0 = the '$' suffix = position n, stored in sa[0] as -1)
+__global__ void ctx_isa_kernel(const uint64_t *sa, int64_t n, uint64_t *isa)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n) return;
+  isa[r == 0 ? (uint64_t)n : sa[r]] = (uint64_t)r;
+}
+
 // bwa layout (4 x u64 counts + 8 x u32 symbols per 128 symbols, bwa/bwt.h:72-73) -> occ32 blocks (internal.cuh).
 // Pass 1, one thread per 64-symbol block: absolute suffix counts S1,S2,S3 (symbols >0, >1, >2 before the block).
 __global__ void occ32_count_kernel(const uint32_t *bwt, uint64_t n64, uint4 *occ, uint64_t *absS)
@@ -187,6 +211,7 @@ int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt
   if (idx) {
     c->ix.occ_cs = 1;                           // streaming loads: random index sectors must not evict the per-lane lists from L2
     if (const char *s = getenv("BWAFLOW_OCC_LOAD")) c->ix.occ_cs = strcmp(s, "ldg") != 0;
+    if (getenv("BWAFLOW_DEBUG_COUNT_TEXT_STEPS")) c->ix.occ_cs |= 2;
     BF_REQUIRE(idx->sa_intv > 0 && (idx->sa_intv & (idx->sa_intv - 1)) == 0, -22, "sa_intv must be a power of two");
     DevIndex &d = c->ix;
     d.primary = idx->primary; d.seq_len = idx->seq_len;
@@ -241,6 +266,21 @@ int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt
       c->d_sa = d_dense;
       d.sa = (const uint64_t *)d_dense; d.sa_shift = dense_shift;
     }
+    // With the full suffix array: the inverse suffix array and the 2-bit text, which let the seeding kernel extend an interval
+    // that has become unique by comparing bases against the text instead of walking the index (smem.cu, text-anchored mode).
+    d.text = nullptr; d.isa = nullptr;
+    int text_mode = 0;                          // opt-in: measured slower on the 3.1 Gbp index (only 18% of the extension steps run on unique intervals)
+    if (const char *s = getenv("BWAFLOW_TEXT_MODE")) text_mode = atoi(s);
+    if (text_mode && d.sa_shift == 0) {
+      const int64_t n = (int64_t)d.seq_len, n_words = (n + 31) / 32 + 4;
+      BF_CUDA(cudaMalloc(&c->d_text, n_words * 8));
+      BF_CUDA(cudaMalloc(&c->d_isa, (size_t)(n + 1) * 8));
+      ctx_text_kernel<<<(unsigned)((n_words + 255) / 256), 256>>>((const uint8_t *)c->d_pac, d.l_pac, (uint64_t *)c->d_text, n_words);
+      ctx_isa_kernel<<<(unsigned)((n + 1 + 255) / 256), 256>>>(d.sa, n, (uint64_t *)c->d_isa);
+      BF_CUDA(cudaGetLastError());
+      BF_CUDA(cudaDeviceSynchronize());
+      d.text = (const uint64_t *)c->d_text; d.isa = (const uint64_t *)c->d_isa;
+    }
     c->has_index = true;
   }
   *out = c;
@@ -292,7 +332,7 @@ void bwaflow_ctx_destroy(bwaflow_ctx_t *c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->d_bwt); cudaFree(c->d_sa); cudaFree(c->d_pac); cudaFree(c->d_ctg_off); cudaFree(c->d_ctg_len);
+  cudaFree(c->d_bwt); cudaFree(c->d_sa); cudaFree(c->d_text); cudaFree(c->d_isa); cudaFree(c->d_pac); cudaFree(c->d_ctg_off); cudaFree(c->d_ctg_len);
   free(c);
 }
 

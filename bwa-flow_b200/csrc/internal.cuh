@@ -40,6 +40,9 @@ struct DevIndex {
   uint64_t sbt[8 * 5];
   const uint64_t *sa;
   int sa_shift;            // log2(sa_intv)
+  // Text-anchored extension of unique intervals (smem.cu): present only with the full suffix array (sa_shift == 0).
+  const uint64_t *text;    // forward + reverse-complement text, 32 two-bit symbols per u64 (MSB first), zero padded
+  const uint64_t *isa;     // inverse suffix array: isa[p] = row of suffix p, p in [0, seq_len]
   int64_t l_pac;
   const uint8_t *pac;
   int n_seqs;
@@ -48,7 +51,7 @@ struct DevIndex {
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ uint4 occ_ld(const DevIndex &ix, const uint4 *p) { return ix.occ_cs ? __ldcs(p) : __ldg(p); }
+__device__ __forceinline__ uint4 occ_ld(const DevIndex &ix, const uint4 *p) { return (ix.occ_cs & 1) ? __ldcs(p) : __ldg(p); }
 #endif
 
 // Scoring as the extension kernels see it.  Matrix row t (target base) as 5 packed int8: lo = q0..q3, hi = q4.
@@ -71,7 +74,7 @@ struct bwaflow_ctx {
   bwaflow::DevIndex ix;
   bwaflow::Params par;
   // owned device allocations
-  void *d_bwt, *d_sa, *d_pac, *d_ctg_off, *d_ctg_len;
+  void *d_bwt, *d_sa, *d_pac, *d_ctg_off, *d_ctg_len, *d_text, *d_isa;
 };
 
 namespace bwaflow {

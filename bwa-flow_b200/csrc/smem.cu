@@ -82,7 +82,7 @@ __device__ __forceinline__ Intv extend1(const DevIndex &ix, const Intv ik, int i
   uint64_t ek, gk, el, gl;
   occ_eq_gt(ix, _k, c, &ek, &gk);
   occ_eq_gt(ix, _l, c, &el, &gl);
-  *blocks += (_k >> 7) != (_l >> 7) ? 2 : 1;
+  if (!(ix.occ_cs & 2)) *blocks += (_k >> 7) != (_l >> 7) ? 2 : 1;   // (bit 1 = developer switch: count text-anchored steps only)
   Intv o;
   const uint64_t acc = xg + (xf <= ix.primary && xf + ik.x2 - 1 >= ix.primary) + (gl - gk);
   const uint64_t nf = ix.L2[c] + 1 + ek;
@@ -95,6 +95,23 @@ __device__ __forceinline__ Intv set_intv(const DevIndex &ix, int c)
 { // bwt_set_intv, bwa/bwt.h:80
   Intv ik; ik.x0 = ix.L2[c] + 1; ik.x2 = ix.L2[c + 1] - ix.L2[c]; ik.x1 = ix.L2[3 - c] + 1; return ik;
 }
+
+// Text-anchored form of an interval that has become unique (x2 == 1): the pattern occurs exactly once in the
+// forward + reverse-complement text, at position x0 here; x1 holds a marker no row can equal (fields are 39 bits).
+// Extending such an interval needs no index walk: the next base either equals the text base next to the occurrence or
+// the extension fails (bwt_extend on a one-row interval computes exactly that), and its rows are recovered on demand from
+// the inverse suffix array: x[0] = isa[pos], x[1] = isa[n - pos - length] (the reverse complement occurs at the mirrored
+// position).  Only available with the full suffix array in HBM (DevIndex::isa).
+constexpr uint64_t TEXT_MARK = (1ull << 39) - 1;
+__device__ __forceinline__ bool is_text(const Intv &v) { return v.x1 == TEXT_MARK; }
+__device__ __forceinline__ Intv text_intv(uint64_t tpos) { Intv v; v.x0 = tpos; v.x1 = TEXT_MARK; v.x2 = 1; return v; }
+__device__ __forceinline__ Intv materialize(const DevIndex &ix, const Intv &v, int plen)
+{
+  if (!is_text(v)) return v;
+  Intv o; o.x0 = ix.isa[v.x0]; o.x1 = ix.isa[ix.seq_len - v.x0 - (uint64_t)plen]; o.x2 = 1;
+  return o;
+}
+constexpr int TEXT_CHUNK = 16;     // bases compared per trip of the warp loop by a lane in text-anchored mode
 
 struct SmemArgs {
   const uint8_t *bases; const int64_t *read_off; int64_t n_reads;
@@ -129,7 +146,7 @@ __device__ __forceinline__ int entry_pos(const uint4 e) { return (int)(e.w >> 21
 // shared memory (one row per lane); the 16-byte interval entries of the two lists are per-lane local arrays.
 enum { PH_F = 0, PH_BE = 1, PH_FE = 2, PH_P3 = 3 };
 enum { T_NONE = 0, T_FETCH, T_NEXT, T_F_DONE, T_B_SELECT, T_BE_DONE, T_FE_PICK, T_FE_FAIL, T_FE_REACHED, T_B_NEXT, T_CALL_DONE,
-       T_FINISH, T_EXIT };
+       T_FINISH, T_EXIT, T_TEXT /* like T_NONE, but the pending extension is a text comparison */ };
 
 #ifndef SMEM_MIN_BLOCKS
 #define SMEM_MIN_BLOCKS 6
@@ -159,8 +176,9 @@ __global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_k
   int phase = PH_F, cur = 0, c = 0;
   Intv ik = {0, 0, 0}, cand = {0, 0, 0}; int cand_beg = 0, cand_end = 0;
 
-  auto push_mem = [&](const Intv &v, int beg, int end) {
+  auto push_mem = [&](const Intv &tv, int beg, int end) {
     if (n_mem < a.cap) {
+      const Intv v = materialize(ix, tv, end - beg);
       bwaflow_intv_t o; o.x[0] = v.x0; o.x[1] = v.x1; o.x[2] = v.x2; o.info = (uint64_t)(uint32_t)beg << 32 | (uint32_t)end;
       mem[n_mem] = o;
     }
@@ -174,7 +192,7 @@ __global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_k
 
   for (;;) {
     // ---- transitions: run until this lane has an extension pending (or no reads are left)
-    while (ts != T_NONE && ts != T_EXIT) {
+    while (ts != T_NONE && ts != T_TEXT && ts != T_EXIT) {
       switch (ts) {
       case T_FETCH: {
         r = (int64_t)atomicAdd(a.ctl, 1);
@@ -271,13 +289,15 @@ __global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_k
         break;
       }
     }
-    if (__ballot_sync(full, ts == T_NONE) == 0) break;
+    if (ts == T_NONE && is_text(ik)) ts = T_TEXT;
+    if (__ballot_sync(full, ts == T_NONE || ts == T_TEXT) == 0) break;
     if (ts == T_NONE) {
       // ---- the one call site of bwt_extend, then the consume step of the four inner loops
-      const Intv o = extend1(ix, ik, phase == PH_BE, c, &blocks);
+      Intv o = extend1(ix, ik, phase == PH_BE, c, &blocks);
       const bool small = o.x2 < (uint64_t)mi;
+      const bool changed = o.x2 != ik.x2;
+      if (ix.isa && mi == 1 && o.x2 == 1) o = text_intv(ix.sa[o.x0]);   // unique from here on: anchor it to the text
       if (phase == PH_F) {                                   // :350-357
-        const bool changed = o.x2 != ik.x2;
         if (changed) push_fwd(ik, cur);
         if (changed && small) ts = T_F_DONE;
         else {
@@ -296,6 +316,42 @@ __global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_k
         else {
           ik = o; ++cur;
           if (cur == stop) ts = T_FE_REACHED; else c = 3 - q[cur];
+        }
+      }
+      if (ts == T_NONE && is_text(ik)) ts = T_TEXT;
+    }
+    if (ts == T_TEXT) {
+      // ---- the same three inner loops for a text-anchored interval: up to TEXT_CHUNK bases per trip, each step the exact
+      // outcome bwt_extend would have on the one-row interval.  Every step counts as one block touch of the reference.
+      const int64_t n_text = (int64_t)ix.seq_len;
+      int budget = TEXT_CHUNK;
+      int64_t wi = -1; uint64_t wv = 0;                       // cached text word
+      auto sym = [&](int64_t p) -> int {
+        if ((p >> 5) != wi) { wi = p >> 5; wv = __ldg(ix.text + wi); }
+        return (int)(wv >> ((~p & 31) << 1)) & 3;
+      };
+      if (phase == PH_BE) {
+        int64_t tp = (int64_t)ik.x0;
+        while (budget-- > 0) {
+          ++blocks;
+          if (!(tp > 0 && sym(tp - 1) == (int)q[cur])) { ts = T_BE_DONE; break; }
+          --tp; ik = text_intv((uint64_t)tp); ik_beg = cur; back[back_n++] = pack_entry(ik, 0); --cur;
+          if (!(cur >= 0 && q[cur] < 4)) { ts = T_BE_DONE; break; }
+        }
+      } else {
+        int64_t ti = (int64_t)ik.x0 + (cur - (phase == PH_F ? sx : sx - bk));
+        while (budget-- > 0) {
+          ++blocks;
+          const bool ok = ti < n_text && sym(ti) == (int)q[cur];
+          if (phase == PH_F) {
+            if (!ok) { push_fwd(ik, cur); ts = T_F_DONE; break; }
+            ++cur; ++ti;
+            if (!(cur < len && q[cur] < 4)) { push_fwd(ik, cur); ts = T_F_DONE; break; }
+          } else {
+            if (!ok) { ts = T_FE_FAIL; break; }
+            ++cur; ++ti;
+            if (cur == stop) { ts = T_FE_REACHED; break; }
+          }
         }
       }
     }
