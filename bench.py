@@ -238,6 +238,7 @@ def main():
 
     out = step_e2e()                       # first touch: allocations, local-memory setup, capacity growth
     n_regs = len(out["alnreg"])
+    cells = hp.rerun(counted=True)[2].cells   # the reference's executed DP cells for this batch (exact stage-4 kernel, untimed)
     for _ in range(args.warmup):
         step_resident()
     clocks = ClockSampler(local)
@@ -275,7 +276,6 @@ def main():
     k_c2a = float(np.mean([p.c2a_ms for p in parts]))
     blocks_smem = parts[-1].smem_blocks
     blocks_pos = parts[-1].seedpos_blocks
-    cells = parts[-1].cells
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

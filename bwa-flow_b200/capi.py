@@ -94,6 +94,7 @@ def lib():
             L.bwaflow_c2a_submit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
             L.bwaflow_c2a_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Timing)]
             L.bwaflow_c2a_rerun.argtypes = [C.c_void_p]
+            L.bwaflow_c2a_rerun_counted.argtypes = [C.c_void_p]
         if hasattr(L, "bwaflow_smem_batch_create"):
             L.bwaflow_smem_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
             L.bwaflow_smem_batch_destroy.argtypes = [C.c_void_p]
@@ -106,6 +107,7 @@ def lib():
         L.bwaflow_hot_batch_destroy.argtypes = [C.c_void_p]
         L.bwaflow_hot_submit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.bwaflow_hot_rerun.argtypes = [C.c_void_p]
+        L.bwaflow_hot_rerun_counted.argtypes = [C.c_void_p]
         L.bwaflow_hot_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(HotTiming)]
         L.bwaflow_stopwatch_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.bwaflow_stopwatch_start.argtypes = [C.c_void_p]
@@ -277,8 +279,8 @@ class C2ABatch:
         check(self.L.bwaflow_c2a_submit(self.h, self.n, _p(bases) if bases is not None else None, _p(read_off), _p(chains),
                                         _p(chain_off), _p(seeds), len(seeds)))
 
-    def rerun(self):
-        check(self.L.bwaflow_c2a_rerun(self.h))
+    def rerun(self, counted=False):
+        check(self.L.bwaflow_c2a_rerun_counted(self.h) if counted else self.L.bwaflow_c2a_rerun(self.h))
 
     def collect(self):
         regs, off = C.c_void_p(), C.c_void_p()
@@ -440,8 +442,8 @@ class HotBatch:
         self.n = len(read_off) - 1
         check(self.L.bwaflow_hot_submit(self.h, self.n, _p(bases), _p(read_off)))
 
-    def rerun(self):
-        check(self.L.bwaflow_hot_rerun(self.h))
+    def rerun(self, counted=False):
+        check(self.L.bwaflow_hot_rerun_counted(self.h) if counted else self.L.bwaflow_hot_rerun(self.h))
 
     def collect(self):
         regs, off = C.c_void_p(), C.c_void_p()

@@ -43,9 +43,24 @@ struct bwaflow_c2a_batch {
   int blocks[bwaflow::C2A_NCLASS];
   int refill;
   bool pending;
+  // speculative first-seed extension on the packed batch engine (chain2aln.cu)
+  bool spec;                        // enabled for this batch
+  bool count_cells;                 // this launch runs every read on the exact lane-per-read kernel and counts its DP cells
+  double cells_known;
+  bwaflow_ext_batch_t *xb;
+  bwaflow_ext_result_t *d_resL;     // left-flank results per chain (right-flank results stay in the extension batch)
+  int64_t *d_jsz, *d_joff;          // [2*(max_chains+1)] query / target bytes per chain job and their exclusive prefix
+  uint8_t *d_cflag;                 // per chain: 1 = no speculative result (pool overflow, unrepresentable job)
+  uint8_t *d_strag;                 // per read: 1 = must be redone by the exact kernel
+  uint8_t *d_skipped2;              // the replay's own copy of the per-seed "skipped" flags
 };
 
 namespace bwaflow {
+// ext.cu: an extension batch driven from the device side of another stage
+struct ExtDeviceView { bwaflow_ext_job_t *jobs; uint8_t *q, *t; bwaflow_ext_result_t *out; int64_t max_jobs, max_q, max_t; };
+ExtDeviceView ext_device_view(bwaflow_ext_batch_t *b);
+int ext_launch_device(bwaflow_ext_batch_t *b, int64_t n_jobs, cudaStream_t st);
+void ext_set_pair_classes(bwaflow_ext_batch_t *b, int n);   // qlen classes below n run on the packed engine
 // smem.cu: device-side halves of submit/collect (no interval D2H); used by the fused hot path
 int smem_launch(bwaflow_smem_batch *b);
 int smem_finish_device(bwaflow_smem_batch *b);                 // waits, regrows slots on overflow, compacts into d_out/d_off; sets n_intv

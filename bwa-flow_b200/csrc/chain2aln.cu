@@ -122,14 +122,16 @@ __global__ void c2a_gather_seeds(const bwaflow_seed_t *seeds, const uint32_t *va
   if (i < n) out[i] = seeds[vals[i]];
 }
 
+// `only` (optional): queue only the reads it marks; the others sort behind every class range and are never pulled
 __global__ void c2a_read_prep(const int64_t *read_off, const int64_t *chain_off, const int64_t *sbase, const bwaflow_seed_t *sseeds,
-                              int64_t n_reads, uint32_t *keys, uint32_t *vals, int *hist, int *err)
+                              int64_t n_reads, const uint8_t *only, uint32_t *keys, uint32_t *vals, int *hist, int *err)
 {
   __shared__ int sh[C2A_NCLASS];
   if (threadIdx.x < C2A_NCLASS) sh[threadIdx.x] = 0;
   __syncthreads();
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n_reads) {
+  if (r < n_reads && only && !only[r]) { keys[r] = 0; vals[r] = (uint32_t)r; }
+  else if (r < n_reads) {
     const int64_t lq = read_off[r + 1] - read_off[r];
     int c = 0;
     while (c < C2A_NCLASS - 1 && lq > c_c2a_qmax[c]) ++c;
@@ -140,7 +142,7 @@ __global__ void c2a_read_prep(const int64_t *read_off, const int64_t *chain_off,
     int64_t ns = sbase[chain_off[r + 1]] - sbase[chain_off[r]];
     const int flank = ns > 0 ? sseeds[sbase[chain_off[r]]].qbeg : 0;
     ns = ns > 0xFFF ? 0xFFF : ns;
-    keys[r] = (uint32_t)c << 24 | (uint32_t)ns << 12 | (uint32_t)(flank & 0xFFF);
+    keys[r] = 1u << 27 | (uint32_t)c << 24 | (uint32_t)ns << 12 | (uint32_t)(flank & 0xFFF);
     vals[r] = (uint32_t)r;
     atomicAdd(&sh[c], 1);
   }
@@ -330,6 +332,153 @@ __global__ void __launch_bounds__(THREADS) c2a_kernel(const C2AArgs a)
   if (cells) atomicAdd(a.cells, cells);
 }
 
+
+// ---- speculative first-seed extension -----------------------------------------------------------
+// The first seed of a chain (in processing order) is extended unless an earlier chain's region already contains it, and
+// what its extension computes depends only on the seed, the read and the chain's reference window -- not on the regions
+// produced so far.  So the left and the right flank of every chain's first seed are run ahead of time as two waves of
+// plain ksw_extend2 jobs on the packed batch engine (ext.cu), and c2a_replay_kernel then walks every read in the
+// reference's order consuming those results.  A read that needs anything else -- a second band try, a later seed of a
+// chain that is not contained, a job the packed form cannot hold -- is left to the exact lane-per-read kernel above.
+
+// side 0 = left flank (reversed query prefix vs reversed reference), 1 = right flank.  Flank sizes of chain c's first seed.
+__device__ __forceinline__ void spec_flank(int side, const bwaflow_seed_t &s, int lq, int64_t wlo, int64_t whi, int *qlen, int *tlen)
+{
+  if (side == 0) { *qlen = s.qbeg; *tlen = (int)(s.rbeg - wlo); }
+  else { *qlen = lq - (s.qbeg + s.len); *tlen = (int)(whi - (s.rbeg + s.len)); }
+  if (*tlen < 0) *tlen = 0;
+}
+
+__global__ void c2a_spec_size(int side, const bwaflow_chain_t *chains, int64_t n_chains, const int64_t *chain_read, const int64_t *read_off,
+                              const int64_t *sbase, const bwaflow_seed_t *sseeds, const int64_t *win, int64_t *jsz)
+{
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n_chains) return;
+  int qlen = 0, tlen = 0;
+  if (c < n_chains && chains[c].n_seeds > 0) {
+    const int64_t r = chain_read[c];
+    spec_flank(side, sseeds[sbase[c]], (int)(read_off[r + 1] - read_off[r]), win[2 * c], win[2 * c + 1], &qlen, &tlen);
+    if (qlen == 0) tlen = 0;                                  // no call at all (bwa/bwamem.c:753, 780)
+  }
+  jsz[c] = qlen; jsz[n_chains + 1 + c] = tlen;
+}
+
+// one warp per chain: job record and its query / target bytes
+__global__ void c2a_spec_fill(int side, const bwaflow_chain_t *chains, int64_t n_chains, const int64_t *chain_read, const int64_t *read_off,
+                              const uint8_t *bases, const int64_t *sbase, const bwaflow_seed_t *sseeds, const int64_t *win,
+                              const int64_t *joff, DevIndex ix, DevScore sc, C2AOpt o, const bwaflow_ext_result_t *resL,
+                              ExtDeviceView x, uint8_t *cflag)
+{
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= n_chains) return;
+  bwaflow_ext_job_t jb;
+  memset(&jb, 0, sizeof(jb));
+  jb.w = o.w; jb.h0 = 1; jb.zdrop = sc.zdrop;
+  const int ns = chains[c].n_seeds;
+  bool nospec = ns <= 0 || (side == 1 && cflag[c]);
+  int qlen = 0, tlen = 0;
+  const uint8_t *qp = nullptr; int qstep = 1; int64_t tpos = 0; int tstep = 1;
+  if (!nospec) {
+    const int64_t r = chain_read[c];
+    const int lq = (int)(read_off[r + 1] - read_off[r]);
+    const uint8_t *rd = bases + read_off[r];
+    const bwaflow_seed_t s = sseeds[sbase[c]];
+    spec_flank(side, s, lq, win[2 * c], win[2 * c + 1], &qlen, &tlen);
+    if (qlen == 0) tlen = 0;
+    if (side == 0) { jb.h0 = s.len * o.a; jb.end_bonus = o.pen_clip5; qp = rd + s.qbeg - 1; qstep = -1; tpos = s.rbeg - 1; tstep = -1; }
+    else { jb.h0 = s.qbeg ? resL[c].score : s.len * o.a; jb.end_bonus = o.pen_clip3; qp = rd + s.qbeg + s.len; tpos = s.rbeg + s.len; }
+    const int64_t qo = joff[c], to = joff[n_chains + 1 + c];
+    if (qo + qlen > x.max_q || to + tlen > x.max_t || jb.h0 <= 0 || jb.h0 + qlen * sc.smax > KSW_MAX_SCORE) nospec = true;
+    else { jb.q_off = qo; jb.t_off = to; }
+  }
+  if (nospec) { qlen = 0; tlen = 0; jb.h0 = 1; if (lane == 0) cflag[c] = 1; }
+  jb.qlen = qlen; jb.tlen = tlen;
+  if (lane == 0) x.jobs[c] = jb;
+  for (int j = lane; j < qlen; j += 32) x.q[jb.q_off + j] = qp[j * qstep];
+  for (int j = lane; j < tlen; j += 32) x.t[jb.t_off + j] = (uint8_t)ref_base(ix, tpos + (int64_t)j * tstep);
+}
+
+// One thread per read: mem_chain2aln's seed loop (bwa/bwamem.c:676-792) in the reference's order, with the two extensions of
+// a chain's first seed taken from the speculative waves.  Sets strag[r] (and leaves no regions) when the read needs more.
+__global__ void c2a_replay_kernel(C2AArgs a, int64_t n_reads, const uint8_t *cflag, const bwaflow_ext_result_t *resL,
+                                  const bwaflow_ext_result_t *resR, uint8_t *skipped, uint8_t *strag)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const C2AOpt o = a.o;
+  const int lq = (int)(a.read_off[r + 1] - a.read_off[r]);
+  bwaflow_alnreg_t *av = a.regs + a.sbase[a.chain_off[r]];
+  int n_av = 0;
+  bool bail = lq > c_c2a_qmax[C2A_NCLASS - 1];
+  for (int64_t ci = a.chain_off[r]; ci < a.chain_off[r + 1] && !bail; ++ci) {
+    const bwaflow_chain_t ch = a.chains[ci];
+    const int64_t s_base = a.sbase[ci];
+    const bwaflow_seed_t *sd = a.sseeds + s_base;
+    for (int p = 0; p < ch.n_seeds; ++p) {
+      const bwaflow_seed_t s = sd[p];
+      int i;
+      for (i = 0; i < n_av; ++i) {                             // :680-696
+        const bwaflow_alnreg_t *q = &av[i];
+        const int64_t prb = q->rb, pre = q->re; const int pqb = q->qb, pqe = q->qe;
+        if (s.rbeg < prb || s.rbeg + s.len > pre || s.qbeg < pqb || s.qbeg + s.len > pqe) continue;
+        if ((double)(s.len - q->seedlen0) > .1 * lq) continue;
+        const int pw = q->w;
+        int qd = s.qbeg - pqb; int64_t rdd = s.rbeg - prb;
+        int mg = max_gap(o, qd < rdd ? qd : (int)rdd);
+        int w = mg < pw ? mg : pw;
+        if (qd - rdd < w && rdd - qd < w) break;
+        qd = pqe - (s.qbeg + s.len); rdd = pre - (s.rbeg + s.len);
+        mg = max_gap(o, qd < rdd ? qd : (int)rdd);
+        w = mg < pw ? mg : pw;
+        if (qd - rdd < w && rdd - qd < w) break;
+      }
+      if (i < n_av) {                                          // :697-712
+        int e;
+        for (e = p - 1; e >= 0; --e) {
+          if (skipped[s_base + e]) continue;
+          const bwaflow_seed_t t = sd[e];
+          if ((double)t.len < s.len * .95) continue;
+          if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
+          if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
+        }
+        if (e < 0) { skipped[s_base + p] = 1; continue; }
+      }
+      if (p != 0 || cflag[ci]) { bail = true; break; }         // only first seeds were run ahead
+      const int wtest = (o.w >> 1) + (o.w >> 2);
+      int a_score, a_truesc, a_qb, a_qe; int64_t a_rb, a_re;
+      if (s.qbeg) {                                            // :724-751
+        const bwaflow_ext_result_t x = resL[ci];
+        if (!(x.max_off < wtest)) { bail = true; break; }      // would take the second band try
+        a_score = x.score;
+        if (x.gscore <= 0 || x.gscore <= a_score - o.pen_clip5) { a_qb = s.qbeg - x.qle; a_rb = s.rbeg - x.tle; a_truesc = a_score; }
+        else { a_qb = 0; a_rb = s.rbeg - x.gtle; a_truesc = x.gscore; }
+      } else { a_score = a_truesc = s.len * o.a; a_qb = 0; a_rb = s.rbeg; }
+      if (s.qbeg + s.len != lq) {                              // :755-779
+        const bwaflow_ext_result_t x = resR[ci];
+        const int sc0 = a_score;
+        if (!(x.score == sc0 || x.max_off < wtest)) { bail = true; break; }
+        a_score = x.score;
+        const int qe = s.qbeg + s.len;
+        if (x.gscore <= 0 || x.gscore <= a_score - o.pen_clip3) { a_qe = qe + x.qle; a_re = s.rbeg + s.len + x.tle; a_truesc += a_score - sc0; }
+        else { a_qe = lq; a_re = s.rbeg + s.len + x.gtle; a_truesc += x.gscore - sc0; }
+      } else { a_qe = lq; a_re = s.rbeg + s.len; }
+      int cov = 0;                                             // :783-792
+      for (int k = 0; k < ch.n_seeds; ++k) {
+        const bwaflow_seed_t t = sd[k];
+        if (t.qbeg >= a_qb && t.qbeg + t.len <= a_qe && t.rbeg >= a_rb && t.rbeg + t.len <= a_re) cov += t.len;
+      }
+      bwaflow_alnreg_t g;
+      memset(&g, 0, sizeof(g));
+      g.rb = a_rb; g.re = a_re; g.qb = a_qb; g.qe = a_qe; g.rid = ch.rid; g.score = a_score; g.truesc = a_truesc;
+      g.w = o.w; g.seedcov = cov; g.seedlen0 = s.len; g.frac_rep = ch.frac_rep;
+      av[n_av++] = g;
+    }
+  }
+  strag[r] = bail ? 1 : 0;
+  a.n_regs[r] = bail ? 0 : n_av;
+}
+
 __global__ void c2a_compact(const int64_t *chain_off, const int64_t *sbase, const int *n_regs, const int64_t *reg_off,
                             int64_t n_reads, const bwaflow_alnreg_t *regs, bwaflow_alnreg_t *out)
 {
@@ -382,18 +531,43 @@ int bwaflow::c2a_launch(bwaflow_c2a_batch *b)
       BF_CUDA(cudaMemsetAsync(b->d_skipped, 0, ns, st));
     }
   }
-  // read queue
-  c2a_read_prep<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(b->d_read_off, b->d_chain_off, b->d_sbase, b->d_sseeds, nr, b->d_rkeys[0], b->d_rvals[0], hist, err);
-  cub::DoubleBuffer<uint32_t> rk(b->d_rkeys[0], b->d_rkeys[1]), rv(b->d_rvals[0], b->d_rvals[1]);
-  tmp = b->tmp_bytes;
-  BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(b->d_tmp, tmp, rk, rv, (int)nr, 0, 27, st));
-  c2a_ranges_kernel<<<1, 1, 0, st>>>(hist, queue);
   C2AArgs a;
   a.bases = b->d_bases; a.read_off = b->d_read_off; a.chains = b->d_chains; a.chain_off = b->d_chain_off;
   a.sbase = b->d_sbase; a.sseeds = b->d_sseeds; a.win = b->d_win; a.skipped = b->d_skipped; a.regs = b->d_regs;
-  a.n_regs = b->d_nregs; a.order = rv.Current(); a.queue = queue; a.err = err;
+  a.n_regs = b->d_nregs; a.order = nullptr; a.queue = queue; a.err = err;
   a.cells = (unsigned long long *)(b->d_ctl + 3 * C2A_NCLASS + 2);
   a.refill = b->refill; a.ix = b->ctx->ix; a.sc = b->ctx->par.sc; a.o = o;
+  a.cls = 0; a.qmax = 0;
+  // speculative waves + replay; what is left goes to the exact kernel below
+  const uint8_t *only = nullptr;
+  if (b->spec && !b->count_cells && nc > 0 && ns > 0) {
+    const ExtDeviceView x = ext_device_view(b->xb);
+    for (int side = 0; side < 2; ++side) {
+      c2a_spec_size<<<(unsigned)((nc + 1 + 255) / 256), 256, 0, st>>>(side, b->d_chains, nc, b->d_chain_read, b->d_read_off, b->d_sbase,
+                                                                  b->d_sseeds, b->d_win, b->d_jsz);
+      for (int k = 0; k < 2; ++k) {
+        tmp = b->tmp_bytes;
+        BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_jsz + k * (nc + 1), b->d_joff + k * (nc + 1), (int)(nc + 1), st));
+      }
+      if (side == 0) BF_CUDA(cudaMemsetAsync(b->d_cflag, 0, nc, st));
+      c2a_spec_fill<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(side, b->d_chains, nc, b->d_chain_read, b->d_read_off, b->d_bases,
+                                                                   b->d_sbase, b->d_sseeds, b->d_win, b->d_joff, b->ctx->ix, b->ctx->par.sc, o,
+                                                                   b->d_resL, x, b->d_cflag);
+      int r = ext_launch_device(b->xb, nc, st);
+      if (r) return r;
+      if (side == 0) BF_CUDA(cudaMemcpyAsync(b->d_resL, x.out, nc * sizeof(bwaflow_ext_result_t), cudaMemcpyDeviceToDevice, st));
+    }
+    BF_CUDA(cudaMemsetAsync(b->d_skipped2, 0, ns, st));
+    c2a_replay_kernel<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(a, nr, b->d_cflag, b->d_resL, x.out, b->d_skipped2, b->d_strag);
+    only = b->d_strag;
+  }
+  // read queue
+  c2a_read_prep<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(b->d_read_off, b->d_chain_off, b->d_sbase, b->d_sseeds, nr, only, b->d_rkeys[0], b->d_rvals[0], hist, err);
+  cub::DoubleBuffer<uint32_t> rk(b->d_rkeys[0], b->d_rkeys[1]), rv(b->d_rvals[0], b->d_rvals[1]);
+  tmp = b->tmp_bytes;
+  BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(b->d_tmp, tmp, rk, rv, (int)nr, 0, 28, st));
+  c2a_ranges_kernel<<<1, 1, 0, st>>>(hist, queue);
+  a.order = rv.Current();
   for (int c = C2A_NCLASS - 1; c >= 0; --c) {
     a.cls = c; a.qmax = h_c2a_qmax[c];
     const size_t smem = (size_t)h_c2a_threads[c] * (h_c2a_qmax[c] + 1) * sizeof(uint32_t);
@@ -456,13 +630,29 @@ int bwaflow_c2a_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_
     cub::DoubleBuffer<uint64_t> sk(b->d_skeys[0], b->d_skeys[1]);
     cub::DoubleBuffer<uint32_t> sv(b->d_svals[0], b->d_svals[1]), rk(b->d_rkeys[0], b->d_rkeys[1]), rv(b->d_rvals[0], b->d_rvals[1]);
     BF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, sk, sv, (int)ms, 0, 64, b->stream));
-    BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, t2, rk, rv, (int)mr, 0, 27, b->stream));
+    BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, t2, rk, rv, (int)mr, 0, 28, b->stream));
     BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t3, b->d_nseeds, b->d_sbase, (int)(mc + 1), b->stream));
     BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t4, b->d_nseeds, b->d_sbase, (int)(mr + 1), b->stream));
   }
   b->tmp_bytes = max3(t1, t2, t3 > t4 ? t3 : t4) + 256;
   BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
   BF_CUDA(cudaMalloc(&b->d_skipped, ms));
+  BF_CUDA(cudaMalloc(&b->d_skipped2, ms));
+  BF_CUDA(cudaMalloc(&b->d_strag, mr));
+  BF_CUDA(cudaMalloc(&b->d_cflag, mc));
+  BF_CUDA(cudaMalloc(&b->d_jsz, 2 * (mc + 1) * 8));
+  BF_CUDA(cudaMalloc(&b->d_joff, 2 * (mc + 1) * 8));
+  BF_CUDA(cudaMalloc(&b->d_resL, mc * sizeof(bwaflow_ext_result_t)));
+  b->spec = true;
+  if (const char *s = getenv("BWAFLOW_C2A_SPEC")) b->spec = atoi(s) != 0;
+  if (b->spec) {
+    // byte pools of the speculative jobs: about twice the mean flank (44 / 131 bases at 2x150 bp) per chain; a chain whose
+    // job does not fit is simply not run ahead
+    int r = bwaflow_ext_batch_create(ctx, mc, 96 * mc + 4096, 288 * mc + 4096, &b->xb);
+    if (r) return r;
+    // first-seed flanks of weak chains are long and die early: with that mix the packed engine only pays up to qlen 63 (measured)
+    ext_set_pair_classes(b->xb, 2);
+  }
   BF_CUDA(cudaMalloc(&b->d_regs, ms * sizeof(bwaflow_alnreg_t)));
   BF_CUDA(cudaMalloc(&b->d_regs_out, ms * sizeof(bwaflow_alnreg_t)));
   BF_CUDA(cudaMallocHost(&b->h_regs, ms * sizeof(bwaflow_alnreg_t)));
@@ -497,6 +687,8 @@ void bwaflow_c2a_batch_destroy(bwaflow_c2a_batch_t *b)
   cudaFree(b->d_bases); cudaFree(b->d_read_off); cudaFree(b->d_chain_off); cudaFree(b->d_chains); cudaFree(b->d_seeds);
   cudaFree(b->d_sseeds); cudaFree(b->d_nseeds); cudaFree(b->d_sbase); cudaFree(b->d_chain_read); cudaFree(b->d_win);
   for (int i = 0; i < 2; ++i) { cudaFree(b->d_skeys[i]); cudaFree(b->d_svals[i]); cudaFree(b->d_rkeys[i]); cudaFree(b->d_rvals[i]); }
+  if (b->xb) bwaflow_ext_batch_destroy(b->xb);
+  cudaFree(b->d_skipped2); cudaFree(b->d_strag); cudaFree(b->d_cflag); cudaFree(b->d_jsz); cudaFree(b->d_joff); cudaFree(b->d_resL);
   cudaFree(b->d_tmp); cudaFree(b->d_skipped); cudaFree(b->d_regs); cudaFree(b->d_regs_out); cudaFreeHost(b->h_regs);
   cudaFree(b->d_nregs); cudaFree(b->d_nregs64); cudaFree(b->d_reg_off); cudaFreeHost(b->h_reg_off);
   cudaFree(b->d_ctl); cudaFreeHost(b->h_ctl);
@@ -537,21 +729,26 @@ int bwaflow_c2a_submit(bwaflow_c2a_batch_t *b, int64_t n_reads, const uint8_t *b
     if (n_seeds) BF_CUDA(cudaMemcpyAsync(b->d_seeds, seeds, n_seeds * sizeof(bwaflow_seed_t), cudaMemcpyHostToDevice, st));
   }
   BF_CUDA(cudaEventRecord(b->tm.ev[1], st));
+  b->count_cells = false; b->cells_known = 0.0;
   int r = c2a_launch(b);
   if (r) return r;
   return c2a_finish_queue(b);
 }
 
-int bwaflow_c2a_rerun(bwaflow_c2a_batch_t *b)
+static int c2a_rerun(bwaflow_c2a_batch_t *b, bool counted)
 {
   BF_REQUIRE(b, -22, "bwaflow_c2a_rerun: null batch");
   BF_CUDA(cudaSetDevice(b->ctx->device));
   BF_CUDA(cudaEventRecord(b->tm.ev[0], b->stream));
   BF_CUDA(cudaEventRecord(b->tm.ev[1], b->stream));
+  b->count_cells = counted;
   int r = c2a_launch(b);
   if (r) return r;
   return c2a_finish_queue(b);
 }
+
+int bwaflow_c2a_rerun(bwaflow_c2a_batch_t *b) { return c2a_rerun(b, false); }
+int bwaflow_c2a_rerun_counted(bwaflow_c2a_batch_t *b) { return c2a_rerun(b, true); }
 
 int bwaflow_c2a_collect(bwaflow_c2a_batch_t *b, const bwaflow_alnreg_t **regs, const int64_t **reg_off,
                         int64_t *n_regs, bwaflow_timing_t *t)
@@ -574,7 +771,8 @@ int bwaflow_c2a_collect(bwaflow_c2a_batch_t *b, const bwaflow_alnreg_t **regs, c
     cudaEventElapsedTime(&t->d2h_ms, b->tm.ev[2], b->tm.ev[3]);
     cudaEventElapsedTime(&t->total_ms, b->tm.ev[0], b->tm.ev[3]);
     t->n_launches = b->n_reads ? 10 + C2A_NCLASS + 16 : 0;
-    t->work_units = (double)*(unsigned long long *)(b->h_ctl + 2);
+    if (b->count_cells || !b->spec) b->cells_known = (double)*(unsigned long long *)(b->h_ctl + 2);
+    t->work_units = b->cells_known;        // DP cells the reference executes for this input (0 = not counted yet)
   }
   if (regs) *regs = b->h_regs;
   if (reg_off) *reg_off = b->h_reg_off;

@@ -14,6 +14,7 @@
 #include "internal.cuh"
 #include "ksw_lane.cuh"
 #include "ksw_pair.cuh"
+#include "batches.cuh"
 
 namespace bwaflow {
 
@@ -301,6 +302,29 @@ static int ext_launch(bwaflow_ext_batch *b)
   BF_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---- device-side use by another stage (chain2aln.cu): jobs and byte pools are written by kernels, results stay in HBM
+namespace bwaflow {
+ExtDeviceView ext_device_view(bwaflow_ext_batch *b)
+{
+  ExtDeviceView v;
+  v.jobs = b->d_jobs; v.q = b->d_q; v.t = b->d_t; v.out = b->d_out; v.max_jobs = b->max_jobs; v.max_q = b->max_q; v.max_t = b->max_t;
+  return v;
+}
+void ext_set_pair_classes(bwaflow_ext_batch *b, int n)
+{
+  if (!getenv("BWAFLOW_EXT_PAIR_CLASSES")) b->pair_classes = n < EXT_PAIR_CLASSES ? n : EXT_PAIR_CLASSES;
+}
+int ext_launch_device(bwaflow_ext_batch *b, int64_t n_jobs, cudaStream_t st)
+{
+  BF_REQUIRE(n_jobs >= 0 && n_jobs <= b->max_jobs, -7, "ext_launch_device: %lld jobs, capacity %lld", (long long)n_jobs, (long long)b->max_jobs);
+  cudaStream_t own = b->stream;
+  b->stream = st; b->n_jobs = n_jobs; b->count_cells = false;
+  const int r = ext_launch(b);
+  b->stream = own;
+  return r;
+}
+} // namespace bwaflow
 
 extern "C" {
 

@@ -91,6 +91,7 @@ struct bwaflow_hot_batch {
   bwaflow_chain_opt_t copt;
   int64_t n_intv, n_pos, n_chains, n_seeds;
   float ms_smem, ms_seedpos, ms_chain, ms_c2a, ms_h2d;
+  bool count_cells, new_input;
   double blocks_smem, blocks_pos;
   bool pending;
 };
@@ -192,6 +193,8 @@ static int hot_run(bwaflow_hot_batch *b)
   c->n_reads = nr; c->n_chains = n_chains; c->n_seeds = n_seeds;
   BF_CUDA(cudaEventRecord(c->tm.ev[0], st));
   BF_CUDA(cudaEventRecord(c->tm.ev[1], st));
+  c->count_cells = b->count_cells;
+  if (b->new_input) { c->cells_known = 0.0; b->new_input = false; }
   if ((r = c2a_launch(c))) return r;
   if ((r = c2a_finish_queue(c))) return r;
   BF_CUDA(cudaEventRecord(b->ev[5], st));
@@ -264,16 +267,21 @@ int bwaflow_hot_submit(bwaflow_hot_batch_t *b, int64_t n_reads, const uint8_t *b
     BF_CUDA(cudaMemcpyAsync(s->d_bases, bases, n_bases, cudaMemcpyHostToDevice, b->stream));
     BF_CUDA(cudaMemcpyAsync(s->d_read_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, b->stream));
   }
+  b->count_cells = false; b->new_input = true;
   return hot_run(b);
 }
 
-int bwaflow_hot_rerun(bwaflow_hot_batch_t *b)
+static int hot_rerun(bwaflow_hot_batch_t *b, bool counted)
 {
   BF_REQUIRE(b, -22, "bwaflow_hot_rerun: null batch");
   BF_CUDA(cudaSetDevice(b->ctx->device));
   BF_CUDA(cudaEventRecord(b->ev[0], b->stream));
+  b->count_cells = counted;
   return hot_run(b);
 }
+
+int bwaflow_hot_rerun(bwaflow_hot_batch_t *b) { return hot_rerun(b, false); }
+int bwaflow_hot_rerun_counted(bwaflow_hot_batch_t *b) { return hot_rerun(b, true); }
 
 int bwaflow_hot_collect(bwaflow_hot_batch_t *b, const bwaflow_alnreg_t **regs, const int64_t **reg_off, int64_t *n_regs,
                         bwaflow_hot_timing_t *t)

@@ -114,8 +114,8 @@ class FusedHotPath:
         return {"name": "RegionsRecord", "start_idx": rec["start_idx"], "batch_num": rec["batch_num"], "bases": rec["bases"],
                 "read_off": rec["read_off"], "chains": None, "alnreg": regs, "alnreg_off": reg_off}
 
-    def rerun(self):
-        self.batch.rerun()
+    def rerun(self, counted=False):
+        self.batch.rerun(counted)
         regs, reg_off, t = self.batch.collect()
         self.last = t
         return regs, reg_off, t

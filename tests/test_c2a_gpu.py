@@ -19,8 +19,15 @@ def _as(arr, dtype):
     return out
 
 
+@pytest.fixture(params=["speculative", "exact"])
+def c2a_mode(request, monkeypatch):
+    """Stage 4 with the speculative first-seed waves on the packed engine + replay (default) and on the lane-per-read kernel only."""
+    monkeypatch.setenv("BWAFLOW_C2A_SPEC", "1" if request.param == "speculative" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("case", ["c1", "c5"])
-def test_c2a_matches_golden(case, request):
+def test_c2a_matches_golden(case, request, c2a_mode):
     from bwaflow_b200 import capi
     ix = request.getfixturevalue("index_" + case)
     g = request.getfixturevalue("golden_" + case)
@@ -36,16 +43,20 @@ def test_c2a_matches_golden(case, request):
         bad = np.nonzero(regs[k] != exp[k])[0]
         assert len(bad) == 0, (k, bad[:5], regs[bad[:5]], exp[bad[:5]])
     assert regs.tobytes() == exp.tobytes()
-    assert t.work_units > 0
-    # a second pass over resident inputs gives the same answer (skip flags and queues are reset per launch)
+    # a second pass over resident inputs gives the same answer (skip flags and queues are reset per launch), and so does the
+    # cell-counting pass (every read on the exact kernel); the count is the reference's executed DP cells
     b.rerun()
     regs2, off2, _ = b.collect()
     assert regs2.tobytes() == exp.tobytes() and (off2 == off).all()
+    b.rerun(counted=True)
+    regs3, off3, t3 = b.collect()
+    assert regs3.tobytes() == exp.tobytes() and (off3 == off).all()
+    assert t3.work_units == float(g["cells_total"]) if "cells_total" in g else t3.work_units > 0
     b.close()
     ctx.close()
 
 
-def test_c2a_ragged_and_empty(index_c1, golden_c1):
+def test_c2a_ragged_and_empty(index_c1, golden_c1, c2a_mode):
     """Reads without chains, a batch of one read, and an empty batch."""
     from bwaflow_b200 import capi
     ix, g = index_c1, golden_c1
