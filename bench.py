@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--sub-rate", type=float, default=0.01)
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ext-microbench", action="store_true")
     return ap.parse_args()
 
 
@@ -131,6 +132,45 @@ def barrier(world):
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
+
+
+def ext_microbench(ctx, peak_gcups, n_jobs_target=10_000_000):
+    """BASELINE config[1]: ~10M ksw_extend2 jobs of the shape mem_chain2aln issues for 2x150 bp reads (150 bp queries split at a
+    seed, w=100, default scoring), through the SWTask-shaped batch API.  The jobs are synthesised (synth.extension_jobs, no aligner,
+    a few hundred thousand distinct jobs tiled); GCUPS counts the DP cells ksw_extend2 executes for them (exact kernel variant)."""
+    from bwaflow_b200 import capi, synth
+    ref = synth.make_reference(4_000_000, n_contigs=2, seed=2)
+    reads = synth.simulate_pairs(ref, 100_000, 150, 0.01, seed=7)
+    jobs, qp, tp = synth.extension_jobs(ref, reads)
+    n0 = len(jobs["qlen"])
+    rep = max(1, n_jobs_target // n0)
+    ej = np.zeros(n0 * rep, dtype=capi.EXT_JOB)
+    for k in ("qlen", "tlen", "w", "h0", "end_bonus", "zdrop"):
+        ej[k] = np.tile(jobs[k], rep)
+    ej["q_off"] = np.tile(jobs["q_off"], rep) + np.repeat(np.arange(rep, dtype=np.int64) * len(qp), n0)
+    ej["t_off"] = np.tile(jobs["t_off"], rep) + np.repeat(np.arange(rep, dtype=np.int64) * len(tp), n0)
+    qpp, tpp = np.tile(qp, rep), np.tile(tp, rep)
+    eb = capi.ExtBatch(ctx, len(ej), len(qpp) + 1, len(tpp) + 1)
+    eb.submit(ej, qpp, tpp)
+    res, t_e2e = eb.collect()
+    eb.rerun(counted=True)
+    res2, tc = eb.collect()
+    same = all((res2[k] == res[k]).all() for k in capi.EXT_RES.names) and all((res[k][:n0] == res[k][-n0:]).all() for k in capi.EXT_RES.names)
+    cells = tc.work_units
+    ks = []
+    for _ in range(5):
+        eb.rerun()
+        ks.append(eb.collect()[1].kernel_ms)
+    k_ms = float(np.mean(ks[1:]))
+    gc = cells / (k_ms * 1e-3) / 1e9
+    out = {"workload": "BASELINE config[1] shape: %d synthetic extension jobs (%d distinct), mean qlen %.1f tlen %.1f, w=100, default scoring"
+                       % (len(ej), n0, float(jobs["qlen"].mean()), float(jobs["tlen"].mean())),
+           "gcups": gc, "peak_gcups": peak_gcups, "frac": gc / peak_gcups, "cells": cells, "kernel_ms": k_ms,
+           "e2e_gcups": cells / (t_e2e.total_ms * 1e-3) / 1e9, "e2e_ms": t_e2e.total_ms,
+           "h2d_bytes": int(ej.nbytes + qpp.nbytes + tpp.nbytes), "d2h_bytes": int(res.nbytes), "jobs_per_s": len(ej) / (k_ms * 1e-3),
+           "variants_agree": bool(same)}
+    eb.close()
+    return out
 
 
 def cpu_hot_path(R, reads, lo, hi):
@@ -294,7 +334,7 @@ def main():
     dpx16, dpx32 = ctx.dpx_peak()
     gcups = cells / (k_c2a * 1e-3) / 1e9
     peak_gcups = dpx16 / 5.0 / 1e9
-    roofline_ext = {"kernel": "c2a_kernel (+prep/sort/compact)", "bound": "int-alu/dpx", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": gcups / peak_gcups,
+    roofline_ext = {"kernel": "stage 4: ext_pair_kernel / ext_kernel waves + c2a_replay + c2a_kernel (+prep/sort/compact)", "bound": "int-alu/dpx", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": gcups / peak_gcups,
                     "cells_per_launch": cells, "kernel_ms": k_c2a, "share_of_step": k_c2a / ms_step,
                     "peak_source": "measured DPX s16x2 issue rate %.3g lane-instr/s / 5 lane-instr per cell (SURVEY 8d); s32 rate %.3g" % (dpx16, dpx32)}
     h2d = int(bases.nbytes + read_off.nbytes)
@@ -310,6 +350,8 @@ def main():
             "counts": {"n_intv": parts[-1].n_intv, "n_pos": parts[-1].n_pos, "n_chains": parts[-1].n_chains,
                        "n_seeds": parts[-1].n_seeds, "n_regs": n_regs},
             "seedpos_gbs": blocks_pos * 64 / (k_pos * 1e-3) / 1e9 if k_pos > 0 else None}
+    if not args.no_ext_microbench:
+        line["ext_microbench"] = ext_microbench(ctx, peak_gcups)
     if world == 1 and not args.no_cpu_baseline:
         sample = args.cpu_sample_pairs or n_pairs
         R, one_pass, cores = run_reference_cpu(args, ref, reads, sample, built=built)
