@@ -355,7 +355,7 @@ def main():
     except Exception:
         pass
     smem_gbs = blocks_smem * 64 / (k_smem * 1e-3) / 1e9
-    roofline = {"kernel": "smem_kernel", "bound": "hbm", "achieved": smem_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": smem_gbs / hbm_peak,
+    roofline = {"kernel": "smem_kernel (+ smem_p3_kernel: the seeding stage, timed and counted together)", "bound": "hbm", "achieved": smem_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": smem_gbs / hbm_peak,
                 "traffic": traffic.get("smem_kernel"), "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback",
                 "algorithmic_bytes_per_launch": blocks_smem * 64, "kernel_ms": k_smem, "share_of_step": k_smem / ms_step_one}
     dpx16, dpx32 = ctx.dpx_peak()
