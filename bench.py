@@ -305,6 +305,9 @@ def main():
     for h in hps:
         out = step_e2e(h)                  # first touch: allocations, local-memory setup, capacity growth
     n_regs = len(out["alnreg"])
+    n_chk = min(reads.n, 100_000)          # kept for the parity check against the reference in the CPU-baseline leg
+    chk_off = np.array(out["alnreg_off"][:n_chk + 1], dtype=np.int64)
+    chk_regs = np.array(out["alnreg"][:chk_off[-1]])
     cells = hp.rerun(counted=True)[2].cells   # the reference's executed DP cells for this batch (exact stage-4 kernel, untimed)
     nw = len(hps)
     # ---- resident pass: one batch in flight, per-stage CUDA events on its stream -> value, breakdown and rooflines
@@ -383,6 +386,16 @@ def main():
         sample = args.cpu_sample_pairs or n_pairs
         R, one_pass, cores = run_reference_cpu(args, ref, reads, sample, built=built)
         sec = one_pass()
+        # full-scale parity: the reference's own regions for the first n_chk reads of the batch, byte for byte (untimed)
+        rb = R.batch(reads.slice(0, n_chk), 0)
+        rb.seq2chains()
+        rb.chains2regions()
+        r_regs, r_off = rb.regions()
+        same_off = bool((np.asarray(r_off) == chk_off).all())
+        line["parity_check"] = {"reads": int(n_chk), "regions": int(len(r_regs)), "offsets_identical": same_off,
+                                "regions_identical": bool(same_off and np.asarray(r_regs).tobytes() == chk_regs.tobytes()),
+                                "against": "oracle/_ref (the compiled reference: mem_seq2chain_wrapper + mem_chain2aln) on the same 3.1 Gbp index"}
+        rb.free()
         line["cpu_baseline"] = {"value": sample / sec, "unit": "pairs/s", "cores": cores, "kind": "reference",
                                 "sample": "%d pairs, stages 2+4 of the compiled reference (oracle/_ref: bwa/*.c + src/bwa_wrapper.cpp), "
                                           "one thread per core, %.1f s" % (sample, sec)}
