@@ -574,7 +574,7 @@ int bwaflow::smem_launch(bwaflow_smem_batch *b)
   const int grid = (int)(want < b->blocks_per_launch ? want : b->blocks_per_launch);
   // dynamic shared memory: per lane one row for the read (<= 256 bases) and one for the forward-list end coordinates
   // dynamic shared memory: per lane one row for the read (<= 256 bases) and one for the forward-list end coordinates
-  const int grid3 = (int)(want < (int64_t)b->ctx->n_sm * 8 ? want : (int64_t)b->ctx->n_sm * 8);
+  const int grid3 = (int)(want < (int64_t)b->ctx->n_sm * 10 ? want : (int64_t)b->ctx->n_sm * 10);   // 10 blocks per SM fit (48 registers, 21 KB)
   if (b->max_len < 160) {
     smem_kernel<160><<<grid, 128, 128 * (164 + SMEM_FEND), st>>>(a);
     smem_p3_kernel<160><<<grid3, 128, 128 * 164, st>>>(a);
