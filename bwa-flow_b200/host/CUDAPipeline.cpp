@@ -24,6 +24,21 @@ bwaflow_hot_batch_t *CUDABatchPool::take()
 }
 void CUDABatchPool::give(bwaflow_hot_batch_t *b) { free_.push(b); }
 
+void SeedPositionTable::put(uint64_t start_idx, Entry &&e)
+{
+  std::lock_guard<std::mutex> lk(m_);
+  tab_[start_idx] = std::move(e);
+}
+SeedPositionTable::Entry SeedPositionTable::take(uint64_t start_idx)
+{
+  std::lock_guard<std::mutex> lk(m_);
+  auto it = tab_.find(start_idx);
+  if (it == tab_.end()) throw std::runtime_error("ChainsPipe: no seed positions for this record");
+  Entry e = std::move(it->second);
+  tab_.erase(it);
+  return e;
+}
+
 // nst_nt4_table (bwa/bntseq.c:47-64): A,C,G,T (either case) -> 0..3, everything else 4
 static inline uint8_t nt4(char c)
 {
@@ -35,6 +50,8 @@ void SeqsToChainsCUDA::compute(int wid)
   (void)wid;
   std::vector<uint8_t> bases;
   std::vector<int64_t> off;
+  bwaflow_smem_batch_t *smem = nullptr;                        // interval mode: this worker's SMemTask
+  if (!pool_) check(bwaflow_smem_batch_create(ctx_, max_reads_, max_bases_, &smem));
   for (;;) {
     SeqsRecord rec = SeqsRecord();
     bool ready = this->getInput(rec);
@@ -50,26 +67,93 @@ void SeqsToChainsCUDA::compute(int wid)
       bases.insert(bases.end(), (uint8_t *)s->seq, (uint8_t *)s->seq + s->l_seq);
       off.push_back((int64_t)bases.size());
     }
-    bwaflow_hot_batch_t *task = pool_->take();
-    check(bwaflow_hot_submit(task, rec.batch_num, bases.data(), off.data()));
     ChainsRecord out;
     out.start_idx = rec.start_idx; out.batch_num = rec.batch_num; out.seqs = rec.seqs;
-    out.chains = NULL; out.bwtintvs = NULL; out.bwtintv_nums = NULL; out.alnreg = NULL;
-    out.chain_ref = (mem_chainref_t **)task;                   // the chains stay in HBM; the handle travels in the unused field
-    out.tag = 1;
+    out.chains = NULL; out.bwtintvs = NULL; out.bwtintv_nums = NULL; out.alnreg = NULL; out.chain_ref = NULL;
+    if (pool_) {
+      bwaflow_hot_batch_t *task = pool_->take();
+      check(bwaflow_hot_submit(task, rec.batch_num, bases.data(), off.data()));
+      out.chain_ref = (mem_chainref_t **)task;                 // the chains stay in HBM; the handle travels in the unused field
+      out.tag = 1;
+    } else {
+      check(bwaflow_smem_submit(smem, rec.batch_num, bases.data(), off.data()));
+      const bwaflow_intv_t *iv; const int64_t *ivoff; int64_t n_intv;
+      check(bwaflow_smem_collect(smem, &iv, &ivoff, &n_intv, nullptr));
+      out.bwtintvs = (bwtintv_t **)malloc(rec.batch_num * sizeof(bwtintv_t *));
+      out.bwtintv_nums = (size_t *)malloc(rec.batch_num * sizeof(size_t));
+      for (int i = 0; i < rec.batch_num; ++i) {                // ownership moves downstream, as FPGAPipeline.cpp:716-719
+        const size_t k = (size_t)(ivoff[i + 1] - ivoff[i]);
+        out.bwtintv_nums[i] = k;
+        out.bwtintvs[i] = (bwtintv_t *)malloc((k ? k : 1) * sizeof(bwtintv_t));
+        memcpy(out.bwtintvs[i], iv + ivoff[i], k * sizeof(bwtintv_t));             // bwaflow_intv_t == bwtintv_t (32 bytes)
+      }
+      const int64_t *pos, *poff; int64_t n_pos;
+      check(bwaflow_smem_seed_positions(smem, &pos, &poff, &n_pos, nullptr));
+      SeedPositionTable::Entry e;
+      e.pos.assign(pos, pos + n_pos); e.pos_off.assign(poff, poff + n_intv + 1);
+      pos_->put(rec.start_idx, std::move(e));
+      out.tag = 0;
+    }
     this->pushOutput(out);
   }
+  if (smem) bwaflow_smem_batch_destroy(smem);
 }
 
+// tag == 1: pass through (src/Pipeline.cpp:409).  tag == 0: intervals -> chains on the host (src/Pipeline.cpp:410-438:
+// mem_chain_postprocess + mem_chain_flt + mem_flt_chained_seeds), here through bwaflow_chain_build with the seed positions the
+// device already looked up; the interval lists are freed as the reference does (:436-437).
 ChainsRecord ChainsPipe::compute(ChainsRecord const &record)
 {
-  if (record.tag == 1) return record;                          // src/Pipeline.cpp:409
-  throw std::runtime_error("ChainsPipe: tag 0 records (host chaining) are produced by the bwaflow_smem_* variant of stage 2");
+  if (record.tag == 1) return record;
+  if (!ctg_ || !pos_) throw std::runtime_error("ChainsPipe: interval-mode records need the contig table and the seed-position table");
+  ChainsRecord out = record;
+  const int n = record.batch_num;
+  std::vector<int64_t> read_off(1, 0), intv_off(1, 0);
+  std::vector<bwaflow_intv_t> intv;
+  for (int i = 0; i < n; ++i) {
+    read_off.push_back(read_off.back() + record.seqs[i].l_seq);
+    const bwaflow_intv_t *p = (const bwaflow_intv_t *)record.bwtintvs[i];
+    intv.insert(intv.end(), p, p + record.bwtintv_nums[i]);
+    intv_off.push_back((int64_t)intv.size());
+    free(record.bwtintvs[i]);
+  }
+  free(record.bwtintvs); free(record.bwtintv_nums);
+  out.bwtintvs = NULL; out.bwtintv_nums = NULL;
+  SeedPositionTable::Entry sp = pos_->take(record.start_idx);
+  bwaflow_chain_result_t *res = nullptr;
+  bwaflow_chain_opt_t copt;
+  bwaflow_chain_opt_default(&copt);                            // from aux->opt in a bwa-flow build (w, max_chain_gap, mask_level, drop_ratio ..)
+  check(bwaflow_chain_build(&copt, ctg_->l_pac, ctg_->n_seqs, ctg_->offset, ctg_->len, nullptr, n, read_off.data(), intv.data(),
+                            intv_off.data(), sp.pos.data(), sp.pos_off.data(), 1, &res));
+  const bwaflow_chain_t *ch; const bwaflow_seed_t *sd; const int64_t *coff; int64_t n_ch, n_sd;
+  bwaflow_chain_result_view(res, &ch, &n_ch, &sd, &n_sd, &coff);
+  out.chains = (mem_chain_v *)malloc(n * sizeof(mem_chain_v));                  // as SeqsToChains::compute (Pipeline.cpp:344)
+  for (int i = 0; i < n; ++i) {
+    mem_chain_v &v = out.chains[i];
+    v.n = v.m = (size_t)(coff[i + 1] - coff[i]);
+    v.a = (mem_chain_t *)malloc((v.n ? v.n : 1) * sizeof(mem_chain_t));
+    for (size_t j = 0; j < v.n; ++j) {
+      const bwaflow_chain_t &f = ch[coff[i] + j];
+      mem_chain_t &c = v.a[j];
+      memset(&c, 0, sizeof(c));
+      c.n = c.m = f.n_seeds; c.rid = f.rid; c.frac_rep = f.frac_rep; c.pos = f.pos;
+      c.w = f.flags & 0x1FFFFFFFu; c.kept = (f.flags >> 29) & 3u; c.is_alt = f.flags >> 31;
+      c.seeds = (mem_seed_t *)malloc((f.n_seeds ? f.n_seeds : 1) * sizeof(mem_seed_t));
+      for (int k = 0; k < f.n_seeds; ++k) {
+        const bwaflow_seed_t &s = sd[f.seed_off + k];
+        c.seeds[k].rbeg = s.rbeg; c.seeds[k].qbeg = s.qbeg; c.seeds[k].len = s.len; c.seeds[k].score = s.score;
+      }
+    }
+  }
+  bwaflow_chain_result_free(res);
+  return out;
 }
 
 void ChainsToRegionsCUDA::compute(int wid)
 {
   (void)wid;
+  bwaflow_c2a_batch_t *c2a = nullptr;                          // interval mode: this worker's SWTask, created on first use
+  int64_t c2a_chains = 0, c2a_seeds = 0;
   for (;;) {
     ChainsRecord rec = ChainsRecord();
     bool ready = this->getInput(rec);
@@ -80,7 +164,34 @@ void ChainsToRegionsCUDA::compute(int wid)
     if (!ready && !(ready = this->getInput(rec))) break;
     bwaflow_hot_batch_t *task = (bwaflow_hot_batch_t *)rec.chain_ref;
     const bwaflow_alnreg_t *regs; const int64_t *roff; int64_t n_regs;
-    check(bwaflow_hot_collect(task, &regs, &roff, &n_regs, nullptr));
+    if (rec.tag == 1) check(bwaflow_hot_collect(task, &regs, &roff, &n_regs, nullptr));
+    else {                                                     // mem_chain_v lists -> flat SoA -> bwaflow_c2a_*, then free the chains
+      std::vector<uint8_t> bases; std::vector<int64_t> off(1, 0), coff(1, 0);
+      std::vector<bwaflow_chain_t> ch; std::vector<bwaflow_seed_t> sd;
+      for (int i = 0; i < rec.batch_num; ++i) {
+        bases.insert(bases.end(), (uint8_t *)rec.seqs[i].seq, (uint8_t *)rec.seqs[i].seq + rec.seqs[i].l_seq);
+        off.push_back((int64_t)bases.size());
+        for (size_t j = 0; j < rec.chains[i].n; ++j) {         // mem_chain_t -> flat (src/bwa_wrapper.h:64-77)
+          const mem_chain_t &c = rec.chains[i].a[j];
+          bwaflow_chain_t f;
+          f.pos = c.pos; f.n_seeds = c.n; f.rid = c.rid; f.frac_rep = c.frac_rep;
+          f.flags = (uint32_t)c.w | (uint32_t)c.kept << 29 | (uint32_t)c.is_alt << 31; f.seed_off = (int64_t)sd.size();
+          for (int k = 0; k < c.n; ++k) { bwaflow_seed_t s; s.rbeg = c.seeds[k].rbeg; s.qbeg = c.seeds[k].qbeg; s.len = c.seeds[k].len; s.score = c.seeds[k].score; s._pad = 0; sd.push_back(s); }
+          ch.push_back(f);
+          free(c.seeds);
+        }
+        coff.push_back((int64_t)ch.size());
+        free(rec.chains[i].a);                                 // Pipeline.cpp:526-530
+      }
+      free(rec.chains);
+      if (!c2a || (int64_t)ch.size() > c2a_chains || (int64_t)sd.size() > c2a_seeds) {
+        if (c2a) bwaflow_c2a_batch_destroy(c2a);
+        c2a_chains = (int64_t)ch.size() * 2 + 1024; c2a_seeds = (int64_t)sd.size() * 2 + 1024;
+        check(bwaflow_c2a_batch_create(ctx_, max_reads_, max_bases_, c2a_chains, c2a_seeds, &c2a));
+      }
+      check(bwaflow_c2a_submit(c2a, rec.batch_num, bases.data(), off.data(), ch.data(), coff.data(), sd.data(), (int64_t)sd.size()));
+      check(bwaflow_c2a_collect(c2a, &regs, &roff, &n_regs, nullptr));
+    }
     RegionsRecord out;
     out.start_idx = rec.start_idx; out.batch_num = rec.batch_num; out.seqs = rec.seqs; out.chains = NULL;
     out.alnreg = (mem_alnreg_v *)malloc(rec.batch_num * sizeof(mem_alnreg_v));    // ownership moves downstream (Pipeline.cpp:516-544)
@@ -90,7 +201,8 @@ void ChainsToRegionsCUDA::compute(int wid)
       out.alnreg[i].a = (mem_alnreg_t *)malloc((k ? k : 1) * sizeof(mem_alnreg_t));
       memcpy(out.alnreg[i].a, regs + roff[i], k * sizeof(mem_alnreg_t));           // bwaflow_alnreg_t == mem_alnreg_t (88 bytes)
     }
-    pool_->give(task);
+    if (rec.tag == 1) pool_->give(task);
     this->pushOutput(out);
   }
+  if (c2a) bwaflow_c2a_batch_destroy(c2a);
 }

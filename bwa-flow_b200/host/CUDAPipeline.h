@@ -3,6 +3,7 @@
 // "Fast mode": stage 2 submits the whole hot path (bwaflow_hot_submit) and pushes a ChainsRecord with tag = 1 whose chain_ref
 // carries the device batch; ChainsPipe passes tag == 1 records through (src/Pipeline.cpp:409); stage 4 collects the regions.
 #pragma once
+#include <map>
 #include "kflow_shim.h"      // <kflow/MapPartitionStage.h> etc. in a bwa-flow build
 #include "records.h"         // "Pipeline.h" in a bwa-flow build
 #include "../../include/bwaflow_cuda.h"
@@ -21,28 +22,61 @@ class CUDABatchPool {
   std::vector<bwaflow_hot_batch_t *> all_;
 };
 
+// "Interval mode" (the FPGA flow: SMemTask results go through ChainsPipe on the host, tag = 0): the seed positions the device
+// computed for a record (bwaflow_smem_seed_positions, the bwt_sa loop of mem_chain_postprocess) wait here for ChainsPipe.
+class SeedPositionTable {
+ public:
+  struct Entry { std::vector<int64_t> pos, pos_off; };
+  void put(uint64_t start_idx, Entry &&e);
+  Entry take(uint64_t start_idx);
+
+ private:
+  std::mutex m_;
+  std::map<uint64_t, Entry> tab_;
+};
+
+// What the host chaining needs from bntseq_t (bwa/bntseq.h:56-64)
+struct ContigTable { int64_t l_pac; int32_t n_seqs; const int64_t *offset; const int32_t *len; };
+
 class SeqsToChainsCUDA : public kestrelFlow::MapPartitionStage<SeqsRecord, ChainsRecord, INPUT_DEPTH, COMPUTE_DEPTH> {
  public:
+  // fast mode: the whole hot path is submitted here, chains stay in HBM (tag = 1)
   SeqsToChainsCUDA(int n_workers, CUDABatchPool *pool)
-      : kestrelFlow::MapPartitionStage<SeqsRecord, ChainsRecord, INPUT_DEPTH, COMPUTE_DEPTH>(n_workers, false), pool_(pool) {}
+      : kestrelFlow::MapPartitionStage<SeqsRecord, ChainsRecord, INPUT_DEPTH, COMPUTE_DEPTH>(n_workers, false), pool_(pool), ctx_(nullptr), pos_(nullptr),
+        max_reads_(0), max_bases_(0) {}
+  // interval mode: SMEM intervals per read as SeqsToChainsFPGA returns them (tag = 0, src/fpga/FPGAPipeline.cpp:765-788)
+  SeqsToChainsCUDA(int n_workers, bwaflow_ctx_t *ctx, SeedPositionTable *pos, int64_t max_reads, int64_t max_bases)
+      : kestrelFlow::MapPartitionStage<SeqsRecord, ChainsRecord, INPUT_DEPTH, COMPUTE_DEPTH>(n_workers, false), pool_(nullptr), ctx_(ctx), pos_(pos),
+        max_reads_(max_reads), max_bases_(max_bases) {}
   void compute(int wid);
 
  private:
   CUDABatchPool *pool_;
+  bwaflow_ctx_t *ctx_;
+  SeedPositionTable *pos_;
+  int64_t max_reads_, max_bases_;
 };
 
 class ChainsPipe : public kestrelFlow::MapStage<ChainsRecord, ChainsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH> {
  public:
-  ChainsPipe(int n = 1) : kestrelFlow::MapStage<ChainsRecord, ChainsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH>(n, false) {}
+  ChainsPipe(int n = 1, const ContigTable *ctg = nullptr, SeedPositionTable *pos = nullptr)
+      : kestrelFlow::MapStage<ChainsRecord, ChainsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH>(n, false), ctg_(ctg), pos_(pos) {}
   ChainsRecord compute(ChainsRecord const &record);
+
+ private:
+  const ContigTable *ctg_;
+  SeedPositionTable *pos_;
 };
 
 class ChainsToRegionsCUDA : public kestrelFlow::MapPartitionStage<ChainsRecord, RegionsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH> {
  public:
-  ChainsToRegionsCUDA(int n_workers, CUDABatchPool *pool)
-      : kestrelFlow::MapPartitionStage<ChainsRecord, RegionsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH>(n_workers, false), pool_(pool) {}
+  ChainsToRegionsCUDA(int n_workers, CUDABatchPool *pool, bwaflow_ctx_t *ctx = nullptr, int64_t max_reads = 0, int64_t max_bases = 0)
+      : kestrelFlow::MapPartitionStage<ChainsRecord, RegionsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH>(n_workers, false), pool_(pool), ctx_(ctx),
+        max_reads_(max_reads), max_bases_(max_bases) {}
   void compute(int wid);
 
  private:
   CUDABatchPool *pool_;
+  bwaflow_ctx_t *ctx_;
+  int64_t max_reads_, max_bases_;
 };

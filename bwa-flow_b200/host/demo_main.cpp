@@ -49,8 +49,9 @@ class RegionsSink : public kestrelFlow::SinkStage<RegionsRecord, COMPUTE_DEPTH> 
 
 int main(int argc, char **argv)
 {
-  if (argc < 3) { fprintf(stderr, "usage: %s case.bin regions.bin [n_workers]\n", argv[0]); return 2; }
+  if (argc < 3) { fprintf(stderr, "usage: %s case.bin regions.bin [n_workers] [fast|intervals]\n", argv[0]); return 2; }
   const int n_workers = argc > 3 ? atoi(argv[3]) : 2;
+  const bool fast = !(argc > 4 && !strcmp(argv[4], "intervals"));
   FILE *f = fopen(argv[1], "rb");
   if (!f) { perror(argv[1]); return 2; }
   CaseHeader h;
@@ -79,11 +80,14 @@ int main(int argc, char **argv)
   }
   int rc = 0;
   try {
-    CUDABatchPool pool(ctx, 2 * n_workers, h.reads_per_record, max_rec_bases + 16);
+    CUDABatchPool pool(ctx, fast ? 2 * n_workers : 0, h.reads_per_record, max_rec_bases + 16);
+    SeedPositionTable seed_pos;
+    ContigTable ctg = {h.l_pac, (int32_t)h.n_seqs, coff.data(), clen.data()};
     ReadsSource src(&seqs, (int)h.reads_per_record);
-    SeqsToChainsCUDA seq2chain_cuda_stage(n_workers, &pool);
-    ChainsPipe chainpipe_stage(1);
-    ChainsToRegionsCUDA chain2reg_cuda_stage(n_workers, &pool);
+    SeqsToChainsCUDA seq2chain_fast(n_workers, &pool), seq2chain_intv(n_workers, ctx, &seed_pos, h.reads_per_record, max_rec_bases + 16);
+    SeqsToChainsCUDA &seq2chain_cuda_stage = fast ? seq2chain_fast : seq2chain_intv;
+    ChainsPipe chainpipe_stage(1, &ctg, &seed_pos);
+    ChainsToRegionsCUDA chain2reg_cuda_stage(n_workers, fast ? &pool : nullptr, ctx, h.reads_per_record, max_rec_bases + 16);
     RegionsSink sink;
     kestrelFlow::Pipeline compute_flow(5, n_workers);
     compute_flow.addStage(0, &src);

@@ -13,8 +13,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("case,per_record,workers", [("c1", 400, 2), ("c1", 97, 3), ("c5", 2000, 1)])
-def test_cpp_stage_classes_match_golden(case, per_record, workers, request, tmp_path):
+@pytest.mark.parametrize("case,per_record,workers,mode", [("c1", 400, 2, "fast"), ("c1", 97, 3, "fast"), ("c5", 2000, 1, "fast"),
+                                                          ("c1", 250, 2, "intervals"), ("c5", 300, 2, "intervals")])
+def test_cpp_stage_classes_match_golden(case, per_record, workers, mode, request, tmp_path):
+    """fast = chains stay in HBM (tag 1); intervals = the FPGA flow: SMEM intervals to the host, ChainsPipe chains them, stage 4
+    takes mem_chain_v lists (tag 0)."""
     from bwaflow_b200 import capi
     g = request.getfixturevalue("golden_" + case)
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "bwa-flow_b200", "host")], check=True)
@@ -35,7 +38,7 @@ def test_cpp_stage_classes_match_golden(case, per_record, workers, request, tmp_
         off.tofile(f)
         bases.tofile(f)
     out = str(tmp_path / "regions.bin")
-    r = subprocess.run([os.path.join(ROOT, "bwa-flow_b200", "cuda_stage_demo"), path, out, str(workers)], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(ROOT, "bwa-flow_b200", "cuda_stage_demo"), path, out, str(workers), mode], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     raw = open(out, "rb").read()
     n = struct.unpack_from("<q", raw, 0)[0]
