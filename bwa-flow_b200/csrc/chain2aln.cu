@@ -770,7 +770,10 @@ int bwaflow_c2a_collect(bwaflow_c2a_batch_t *b, const bwaflow_alnreg_t **regs, c
     cudaEventElapsedTime(&t->kernel_ms, b->tm.ev[1], b->tm.ev[2]);
     cudaEventElapsedTime(&t->d2h_ms, b->tm.ev[2], b->tm.ev[3]);
     cudaEventElapsedTime(&t->total_ms, b->tm.ev[0], b->tm.ev[3]);
-    t->n_launches = b->n_reads ? 10 + C2A_NCLASS + 16 : 0;
+    // kernels per launch of this stage (cub calls counted by the kernels they run): prep 6 + seed sort 10 + gather 1 +
+    // read queue 8 + C2A_NCLASS exact kernels + compaction 4 = 37; the speculative waves add 2 x (size 1 + scans 4 + fill 1 +
+    // extension batch: key 1 + sort 6 + ranges 1 + 8 class kernels + deferred queue 1) + replay 1 = 45
+    t->n_launches = b->n_reads ? 29 + C2A_NCLASS + ((b->spec && !b->count_cells) ? 45 : 0) : 0;
     if (b->count_cells || !b->spec) b->cells_known = (double)*(unsigned long long *)(b->h_ctl + 2);
     t->work_units = b->cells_known;        // DP cells the reference executes for this input (0 = not counted yet)
   }

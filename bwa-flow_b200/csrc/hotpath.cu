@@ -304,7 +304,7 @@ int bwaflow_hot_collect(bwaflow_hot_batch_t *b, const bwaflow_alnreg_t **regs, c
     t->seedpos_blocks = (double)(unsigned long long)b->h_tot[2];
     t->cells = ct.work_units;
     t->n_intv = b->n_intv; t->n_pos = b->n_pos; t->n_chains = b->n_chains; t->n_seeds = b->n_seeds;
-    t->n_launches = 5 + 3 + 8 + ct.n_launches;
+    t->n_launches = 6 + 4 + 8 + ct.n_launches;     // seeding 6, seed positions 4, chaining 8 (scans = 2 kernels each), stage 4
   }
   return 0;
 }
