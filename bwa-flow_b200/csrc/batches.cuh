@@ -61,6 +61,7 @@ struct ExtDeviceView { bwaflow_ext_job_t *jobs; uint8_t *q, *t; bwaflow_ext_resu
 ExtDeviceView ext_device_view(bwaflow_ext_batch_t *b);
 int ext_launch_device(bwaflow_ext_batch_t *b, int64_t n_jobs, cudaStream_t st);
 void ext_set_pair_classes(bwaflow_ext_batch_t *b, int n);   // qlen classes below n run on the packed engine
+void ext_set_order_rows(bwaflow_ext_batch_t *b, int on);    // queue order by estimated lifetime first (see ext_key_kernel)
 // smem.cu: device-side halves of submit/collect (no interval D2H); used by the fused hot path
 int smem_launch(bwaflow_smem_batch *b);
 int smem_finish_device(bwaflow_smem_batch *b);                 // waits, regrows slots on overflow, compacts into d_out/d_off; sets n_intv

@@ -650,8 +650,9 @@ int bwaflow_c2a_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_
     // job does not fit is simply not run ahead
     int r = bwaflow_ext_batch_create(ctx, mc, 96 * mc + 4096, 288 * mc + 4096, &b->xb);
     if (r) return r;
-    // first-seed flanks of weak chains are long and die early: with that mix the packed engine only pays up to qlen 63 (measured)
-    ext_set_pair_classes(b->xb, 2);
+    // first-seed flanks of weak chains are long and die early: with that mix the packed engine only pays up to qlen 95 (measured)
+    ext_set_pair_classes(b->xb, 3);
+    ext_set_order_rows(b->xb, 1);
   }
   BF_CUDA(cudaMalloc(&b->d_regs, ms * sizeof(bwaflow_alnreg_t)));
   BF_CUDA(cudaMalloc(&b->d_regs_out, ms * sizeof(bwaflow_alnreg_t)));

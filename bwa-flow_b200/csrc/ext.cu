@@ -43,7 +43,7 @@ struct ExtArgs {
   PairConsts pc;
 };
 
-__global__ void ext_key_kernel(const bwaflow_ext_job_t *jobs, int64_t n, uint32_t *keys, uint32_t *vals, int *hist, int *err)
+__global__ void ext_key_kernel(const bwaflow_ext_job_t *jobs, int64_t n, uint32_t *keys, uint32_t *vals, int *hist, int *err, int order_rows)
 {
   __shared__ int sh[EXT_NCLASS];
   if (threadIdx.x < EXT_NCLASS) sh[threadIdx.x] = 0;
@@ -54,9 +54,18 @@ __global__ void ext_key_kernel(const bwaflow_ext_job_t *jobs, int64_t n, uint32_
     int c = 0;
     while (c < EXT_NCLASS - 1 && qlen > c_ext_qmax[c]) ++c;
     if (qlen > c_ext_qmax[EXT_NCLASS - 1] || qlen < 0 || tlen < 0) { atomicExch(err, 1); }
-    // queue order inside a class: widest rows first (qlen), then most rows (tlen): the lanes of a warp then walk rows of
-    // the same width and finish at about the same time
-    keys[i] = (uint32_t)c << 24 | (uint32_t)(qlen & 0x3FF) << 14 | (uint32_t)(tlen > 0x3FFF ? 0x3FFF : tlen);
+    // queue order inside a class.  order_rows == 0 (raw job batches): widest rows first (qlen), then most rows (tlen): the lanes of
+    // a warp then walk rows of the same width and finish at about the same time.  order_rows == 1 (the first-seed waves of
+    // stage 4, a mix of strong seeds and weak chains): by estimated lifetime first -- an extension that starts from a small
+    // h0 dies within about 2*h0 rows whatever its target length, every mismatch costing more than a match gains -- then by
+    // width, so that a warp's lanes free up together (stage 4: 11.3 -> 8.9 ms; raw batches of long-lived jobs lose 5% with it).
+    if (order_rows) {
+      const int h0 = jobs[i].h0;
+      int rows = 2 * (h0 > 0 ? h0 : 0) + 8;
+      rows = rows < tlen ? rows : tlen;
+      keys[i] = (uint32_t)c << 24 | (uint32_t)(rows > 0x3FFF ? 0x3FFF : rows) << 10 | (uint32_t)(qlen & 0x3FF);
+    } else
+      keys[i] = (uint32_t)c << 24 | (uint32_t)(qlen & 0x3FF) << 14 | (uint32_t)(tlen > 0x3FFF ? 0x3FFF : tlen);
     vals[i] = (uint32_t)i;
     atomicAdd(&sh[c], 1);
   }
@@ -243,7 +252,7 @@ struct bwaflow_ext_batch {
   bwaflow_ext_result_t *d_out, *h_out;
   int *h_err;                       // err | pad | cells (u64)
   int blocks[EXT_NCLASS], blocks_pair[EXT_NCLASS];
-  int refill, refill_pair, pair_sync, pair_classes;
+  int refill, refill_pair, pair_sync, pair_classes, order_rows;
   bool use_pair, multi_stream;
   double cells_known;
   bool count_cells;            // this launch runs the cell-counting (EXACT) variant of the packed kernel
@@ -263,7 +272,7 @@ static int ext_launch(bwaflow_ext_batch *b)
   int *hist = b->d_ctl + CTL_HIST, *queue = b->d_ctl + CTL_QUEUE, *err = b->d_ctl + CTL_ERR;
   BF_CUDA(cudaMemsetAsync(b->d_ctl, 0, CTL_INTS * sizeof(int), b->stream));
   if (n == 0) return 0;
-  ext_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_jobs, n, b->d_keys[0], b->d_vals[0], hist, err);
+  ext_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_jobs, n, b->d_keys[0], b->d_vals[0], hist, err, b->order_rows);
   cub::DoubleBuffer<uint32_t> keys(b->d_keys[0], b->d_keys[1]), vals(b->d_vals[0], b->d_vals[1]);
   size_t tmp = b->tmp_bytes;
   BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(b->d_tmp, tmp, keys, vals, (int)n, 0, 27, b->stream));
@@ -315,6 +324,10 @@ void ext_set_pair_classes(bwaflow_ext_batch *b, int n)
 {
   if (!getenv("BWAFLOW_EXT_PAIR_CLASSES")) b->pair_classes = n < EXT_PAIR_CLASSES ? n : EXT_PAIR_CLASSES;
 }
+void ext_set_order_rows(bwaflow_ext_batch *b, int on)
+{
+  if (!getenv("BWAFLOW_EXT_ORDER_ROWS")) b->order_rows = on;
+}
 int ext_launch_device(bwaflow_ext_batch *b, int64_t n_jobs, cudaStream_t st)
 {
   BF_REQUIRE(n_jobs >= 0 && n_jobs <= b->max_jobs, -7, "ext_launch_device: %lld jobs, capacity %lld", (long long)n_jobs, (long long)b->max_jobs);
@@ -341,6 +354,8 @@ int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_q
   b->refill_pair = 16;
   if (const char *s = getenv("BWAFLOW_EXT_REFILL_PAIR")) b->refill_pair = atoi(s) > 0 ? atoi(s) : 16;
   b->pair_sync = 0;
+  b->order_rows = 0;
+  if (const char *s = getenv("BWAFLOW_EXT_ORDER_ROWS")) b->order_rows = atoi(s) != 0;
   b->pair_classes = EXT_PAIR_CLASSES;
   if (const char *s = getenv("BWAFLOW_EXT_PAIR_CLASSES")) b->pair_classes = atoi(s) < EXT_PAIR_CLASSES ? atoi(s) : EXT_PAIR_CLASSES;
   if (const char *s = getenv("BWAFLOW_EXT_PAIR_SYNC")) b->pair_sync = atoi(s) != 0;
