@@ -313,9 +313,10 @@ def main():
     # ---- resident pass: one batch in flight, per-stage CUDA events on its stream -> value, breakdown and rooflines
     # (more batches in flight only add contention here: there is no copy to hide; measured 8.8 / 8.7 / 8.5 M pairs/s at 1 / 2 / 3)
     run_steps(step_resident, args.warmup, 1)
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local)          # rank 0 samples its own GPU; one nvidia-smi poller per box, not one per rank
     barrier(world)
-    clocks.start()
+    if rank == 0:
+        clocks.start()
     sw.start()
     parts = run_steps(step_resident, args.steps, 1)
     ms_res = sw.stop()
@@ -328,7 +329,7 @@ def main():
     sw.start()
     run_steps(step_e2e, args.steps, nw)
     ms_e2e = sw.stop()
-    clk = clocks.stop()
+    clk = clocks.stop() if rank == 0 else None
     barrier(world)
     ms_e2e = barrier_max(ms_e2e, world)
 

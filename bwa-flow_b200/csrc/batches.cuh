@@ -50,6 +50,7 @@ struct bwaflow_c2a_batch {
   bwaflow_ext_batch_t *xb;
   bwaflow_ext_result_t *d_resL;     // left-flank results per chain (right-flank results stay in the extension batch)
   int64_t *d_jsz, *d_joff;          // [2*(max_chains+1)] query / target bytes per chain job and their exclusive prefix
+  void *d_jdesc;                    // per chain: 32-byte job descriptor of the current wave (chain2aln.cu SpecDesc)
   uint8_t *d_cflag;                 // per chain: 1 = no speculative result (pool overflow, unrepresentable job)
   uint8_t *d_strag;                 // per read: 1 = must be redone by the exact kernel
   uint8_t *d_skipped2;              // the replay's own copy of the per-seed "skipped" flags

@@ -349,54 +349,59 @@ __device__ __forceinline__ void spec_flank(int side, const bwaflow_seed_t &s, in
   if (*tlen < 0) *tlen = 0;
 }
 
+// What c2a_spec_fill needs to know about chain c's job, gathered by one thread per chain so that the warp-per-chain fill kernel
+// starts from two loads instead of a chain of six dependent ones (it is latency-bound: 1.7M warps with little work each).
+struct SpecDesc { int64_t q_src, tpos; int32_t qlen, tlen, h0; int8_t qstep, tstep, nospec, end_bonus; };
+static_assert(sizeof(SpecDesc) == 32, "SpecDesc is allocated as 32 bytes per chain");
+
 __global__ void c2a_spec_size(int side, const bwaflow_chain_t *chains, int64_t n_chains, const int64_t *chain_read, const int64_t *read_off,
-                              const int64_t *sbase, const bwaflow_seed_t *sseeds, const int64_t *win, int64_t *jsz)
+                              const int64_t *sbase, const bwaflow_seed_t *sseeds, const int64_t *win, DevScore sc, C2AOpt o,
+                              const bwaflow_ext_result_t *resL, const uint8_t *cflag, SpecDesc *desc, int64_t *jsz)
 {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c > n_chains) return;
-  int qlen = 0, tlen = 0;
-  if (c < n_chains && chains[c].n_seeds > 0) {
+  SpecDesc d;
+  memset(&d, 0, sizeof(d));
+  d.nospec = 1; d.h0 = 1; d.qstep = d.tstep = 1;
+  if (c < n_chains && chains[c].n_seeds > 0 && !(side == 1 && cflag[c])) {
     const int64_t r = chain_read[c];
-    spec_flank(side, sseeds[sbase[c]], (int)(read_off[r + 1] - read_off[r]), win[2 * c], win[2 * c + 1], &qlen, &tlen);
+    const int64_t ro = read_off[r];
+    const int lq = (int)(read_off[r + 1] - ro);
+    const bwaflow_seed_t s = sseeds[sbase[c]];
+    int qlen, tlen;
+    spec_flank(side, s, lq, win[2 * c], win[2 * c + 1], &qlen, &tlen);
     if (qlen == 0) tlen = 0;                                  // no call at all (bwa/bwamem.c:753, 780)
+    d.qlen = qlen; d.tlen = tlen;
+    if (side == 0) { d.h0 = s.len * o.a; d.end_bonus = (int8_t)o.pen_clip5; d.q_src = ro + s.qbeg - 1; d.qstep = -1; d.tpos = s.rbeg - 1; d.tstep = -1; }
+    else { d.h0 = s.qbeg ? resL[c].score : s.len * o.a; d.end_bonus = (int8_t)o.pen_clip3; d.q_src = ro + s.qbeg + s.len; d.tpos = s.rbeg + s.len; }
+    d.nospec = d.h0 <= 0 || d.h0 + qlen * sc.smax > KSW_MAX_SCORE || o.pen_clip5 > 127 || o.pen_clip3 > 127;
   }
-  jsz[c] = qlen; jsz[n_chains + 1 + c] = tlen;
+  if (d.nospec) { d.qlen = 0; d.tlen = 0; d.h0 = 1; }
+  if (c < n_chains) desc[c] = d;
+  jsz[c] = d.qlen; jsz[n_chains + 1 + c] = d.tlen;
 }
 
 // one warp per chain: job record and its query / target bytes
-__global__ void c2a_spec_fill(int side, const bwaflow_chain_t *chains, int64_t n_chains, const int64_t *chain_read, const int64_t *read_off,
-                              const uint8_t *bases, const int64_t *sbase, const bwaflow_seed_t *sseeds, const int64_t *win,
-                              const int64_t *joff, DevIndex ix, DevScore sc, C2AOpt o, const bwaflow_ext_result_t *resL,
-                              ExtDeviceView x, uint8_t *cflag)
+__global__ void c2a_spec_fill(int side, int64_t n_chains, const SpecDesc *desc, const uint8_t *bases, const int64_t *joff, DevIndex ix,
+                              DevScore sc, C2AOpt o, ExtDeviceView x, uint8_t *cflag)
 {
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= n_chains) return;
-  bwaflow_ext_job_t jb;
-  memset(&jb, 0, sizeof(jb));
-  jb.w = o.w; jb.h0 = 1; jb.zdrop = sc.zdrop;
-  const int ns = chains[c].n_seeds;
-  bool nospec = ns <= 0 || (side == 1 && cflag[c]);
-  int qlen = 0, tlen = 0;
-  const uint8_t *qp = nullptr; int qstep = 1; int64_t tpos = 0; int tstep = 1;
-  if (!nospec) {
-    const int64_t r = chain_read[c];
-    const int lq = (int)(read_off[r + 1] - read_off[r]);
-    const uint8_t *rd = bases + read_off[r];
-    const bwaflow_seed_t s = sseeds[sbase[c]];
-    spec_flank(side, s, lq, win[2 * c], win[2 * c + 1], &qlen, &tlen);
-    if (qlen == 0) tlen = 0;
-    if (side == 0) { jb.h0 = s.len * o.a; jb.end_bonus = o.pen_clip5; qp = rd + s.qbeg - 1; qstep = -1; tpos = s.rbeg - 1; tstep = -1; }
-    else { jb.h0 = s.qbeg ? resL[c].score : s.len * o.a; jb.end_bonus = o.pen_clip3; qp = rd + s.qbeg + s.len; tpos = s.rbeg + s.len; }
-    const int64_t qo = joff[c], to = joff[n_chains + 1 + c];
-    if (qo + qlen > x.max_q || to + tlen > x.max_t || jb.h0 <= 0 || jb.h0 + qlen * sc.smax > KSW_MAX_SCORE) nospec = true;
-    else { jb.q_off = qo; jb.t_off = to; }
+  SpecDesc d = desc[c];
+  const int64_t qo = joff[c], to = joff[n_chains + 1 + c];
+  if (!d.nospec && (qo + d.qlen > x.max_q || to + d.tlen > x.max_t)) { d.nospec = 1; d.qlen = 0; d.tlen = 0; d.h0 = 1; }
+  if (lane == 0) {
+    bwaflow_ext_job_t jb;
+    memset(&jb, 0, sizeof(jb));
+    jb.w = o.w; jb.zdrop = sc.zdrop; jb.h0 = d.h0; jb.end_bonus = d.end_bonus; jb.qlen = d.qlen; jb.tlen = d.tlen;
+    if (!d.nospec) { jb.q_off = qo; jb.t_off = to; }
+    x.jobs[c] = jb;
+    if (d.nospec) cflag[c] = 1;
   }
-  if (nospec) { qlen = 0; tlen = 0; jb.h0 = 1; if (lane == 0) cflag[c] = 1; }
-  jb.qlen = qlen; jb.tlen = tlen;
-  if (lane == 0) x.jobs[c] = jb;
-  for (int j = lane; j < qlen; j += 32) x.q[jb.q_off + j] = qp[j * qstep];
-  for (int j = lane; j < tlen; j += 32) x.t[jb.t_off + j] = (uint8_t)ref_base(ix, tpos + (int64_t)j * tstep);
+  const uint8_t *qp = bases + d.q_src;
+  for (int j = lane; j < d.qlen; j += 32) x.q[qo + j] = qp[j * d.qstep];
+  for (int j = lane; j < d.tlen; j += 32) x.t[to + j] = (uint8_t)ref_base(ix, d.tpos + (int64_t)j * d.tstep);
 }
 
 // One thread per read: mem_chain2aln's seed loop (bwa/bwamem.c:676-792) in the reference's order, with the two extensions of
@@ -543,16 +548,16 @@ int bwaflow::c2a_launch(bwaflow_c2a_batch *b)
   if (b->spec && !b->count_cells && nc > 0 && ns > 0) {
     const ExtDeviceView x = ext_device_view(b->xb);
     for (int side = 0; side < 2; ++side) {
+      if (side == 0) BF_CUDA(cudaMemsetAsync(b->d_cflag, 0, nc, st));
       c2a_spec_size<<<(unsigned)((nc + 1 + 255) / 256), 256, 0, st>>>(side, b->d_chains, nc, b->d_chain_read, b->d_read_off, b->d_sbase,
-                                                                  b->d_sseeds, b->d_win, b->d_jsz);
+                                                                  b->d_sseeds, b->d_win, b->ctx->par.sc, o, b->d_resL, b->d_cflag,
+                                                                  (SpecDesc *)b->d_jdesc, b->d_jsz);
       for (int k = 0; k < 2; ++k) {
         tmp = b->tmp_bytes;
         BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_jsz + k * (nc + 1), b->d_joff + k * (nc + 1), (int)(nc + 1), st));
       }
-      if (side == 0) BF_CUDA(cudaMemsetAsync(b->d_cflag, 0, nc, st));
-      c2a_spec_fill<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(side, b->d_chains, nc, b->d_chain_read, b->d_read_off, b->d_bases,
-                                                                   b->d_sbase, b->d_sseeds, b->d_win, b->d_joff, b->ctx->ix, b->ctx->par.sc, o,
-                                                                   b->d_resL, x, b->d_cflag);
+      c2a_spec_fill<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(side, nc, (const SpecDesc *)b->d_jdesc, b->d_bases, b->d_joff, b->ctx->ix,
+                                                                   b->ctx->par.sc, o, x, b->d_cflag);
       int r = ext_launch_device(b->xb, nc, st);
       if (r) return r;
       if (side == 0) BF_CUDA(cudaMemcpyAsync(b->d_resL, x.out, nc * sizeof(bwaflow_ext_result_t), cudaMemcpyDeviceToDevice, st));
@@ -643,6 +648,7 @@ int bwaflow_c2a_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_
   BF_CUDA(cudaMalloc(&b->d_jsz, 2 * (mc + 1) * 8));
   BF_CUDA(cudaMalloc(&b->d_joff, 2 * (mc + 1) * 8));
   BF_CUDA(cudaMalloc(&b->d_resL, mc * sizeof(bwaflow_ext_result_t)));
+  BF_CUDA(cudaMalloc(&b->d_jdesc, mc * 32));
   b->spec = true;
   if (const char *s = getenv("BWAFLOW_C2A_SPEC")) b->spec = atoi(s) != 0;
   if (b->spec) {
@@ -689,7 +695,7 @@ void bwaflow_c2a_batch_destroy(bwaflow_c2a_batch_t *b)
   cudaFree(b->d_sseeds); cudaFree(b->d_nseeds); cudaFree(b->d_sbase); cudaFree(b->d_chain_read); cudaFree(b->d_win);
   for (int i = 0; i < 2; ++i) { cudaFree(b->d_skeys[i]); cudaFree(b->d_svals[i]); cudaFree(b->d_rkeys[i]); cudaFree(b->d_rvals[i]); }
   if (b->xb) bwaflow_ext_batch_destroy(b->xb);
-  cudaFree(b->d_skipped2); cudaFree(b->d_strag); cudaFree(b->d_cflag); cudaFree(b->d_jsz); cudaFree(b->d_joff); cudaFree(b->d_resL);
+  cudaFree(b->d_skipped2); cudaFree(b->d_strag); cudaFree(b->d_cflag); cudaFree(b->d_jsz); cudaFree(b->d_joff); cudaFree(b->d_resL); cudaFree(b->d_jdesc);
   cudaFree(b->d_tmp); cudaFree(b->d_skipped); cudaFree(b->d_regs); cudaFree(b->d_regs_out); cudaFreeHost(b->h_regs);
   cudaFree(b->d_nregs); cudaFree(b->d_nregs64); cudaFree(b->d_reg_off); cudaFreeHost(b->h_reg_off);
   cudaFree(b->d_ctl); cudaFreeHost(b->h_ctl);
