@@ -43,7 +43,7 @@ struct ExtArgs {
   PairConsts pc;
 };
 
-__global__ void ext_key_kernel(const bwaflow_ext_job_t *jobs, int64_t n, uint32_t *keys, uint32_t *vals, int *hist, int *err, int order_rows)
+__global__ void ext_key_kernel(const bwaflow_ext_job_t *jobs, int64_t n, uint32_t *keys, uint32_t *vals, int *hist, int *err, int order_rows, int zdrop)
 {
   __shared__ int sh[EXT_NCLASS];
   if (threadIdx.x < EXT_NCLASS) sh[threadIdx.x] = 0;
@@ -54,6 +54,7 @@ __global__ void ext_key_kernel(const bwaflow_ext_job_t *jobs, int64_t n, uint32_
     int c = 0;
     while (c < EXT_NCLASS - 1 && qlen > c_ext_qmax[c]) ++c;
     if (qlen > c_ext_qmax[EXT_NCLASS - 1] || qlen < 0 || tlen < 0) { atomicExch(err, 1); }
+    if (jobs[i].zdrop != zdrop) atomicExch(err, 4);        // mem_chain2aln passes opt->zdrop to every call; so does the context
     // queue order inside a class.  order_rows == 0 (raw job batches): widest rows first (qlen), then most rows (tlen): the lanes of
     // a warp then walk rows of the same width and finish at about the same time.  order_rows == 1 (the first-seed waves of
     // stage 4, a mix of strong seeds and weak chains): by estimated lifetime first -- an extension that starts from a small
@@ -272,7 +273,7 @@ static int ext_launch(bwaflow_ext_batch *b)
   int *hist = b->d_ctl + CTL_HIST, *queue = b->d_ctl + CTL_QUEUE, *err = b->d_ctl + CTL_ERR;
   BF_CUDA(cudaMemsetAsync(b->d_ctl, 0, CTL_INTS * sizeof(int), b->stream));
   if (n == 0) return 0;
-  ext_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_jobs, n, b->d_keys[0], b->d_vals[0], hist, err, b->order_rows);
+  ext_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_jobs, n, b->d_keys[0], b->d_vals[0], hist, err, b->order_rows, b->ctx->par.sc.zdrop);
   cub::DoubleBuffer<uint32_t> keys(b->d_keys[0], b->d_keys[1]), vals(b->d_vals[0], b->d_vals[1]);
   size_t tmp = b->tmp_bytes;
   BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(b->d_tmp, tmp, keys, vals, (int)n, 0, 27, b->stream));
@@ -492,6 +493,7 @@ int bwaflow_ext_collect(bwaflow_ext_batch_t *b, const bwaflow_ext_result_t **out
     t->work_units = b->cells_known;                      // DP cells the reference executes for these jobs (0 = not counted yet)
   }
   BF_REQUIRE(*b->h_err != 1, -34, "extension job with qlen > %d (or negative length)", h_ext_qmax[EXT_NCLASS - 1]);
+  BF_REQUIRE(*b->h_err != 4, -22, "extension job whose zdrop differs from the context's (bwaflow_ctx_set_opt): ksw_extend2 is always called with opt->zdrop (bwa/bwamem.c:734,762)");
   BF_REQUIRE(*b->h_err != 2, -34, "extension job whose scores may exceed %d (h0 + qlen*max_mat) or with h0 <= 0", KSW_MAX_SCORE);
   if (out) *out = b->h_out;
   return 0;

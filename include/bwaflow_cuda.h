@@ -44,7 +44,8 @@ typedef struct {
 } bwaflow_alnreg_t;
 
 /* One ksw_extend2 call (bwa/ksw.c:380): query = qpool[q_off..+qlen) codes 0..4, target = tpool[t_off..+tlen)
- * codes 0..3(4).  w is the caller's (unclamped) band; the clamp of ksw.c:399-407 happens on the device. */
+ * codes 0..3(4).  w is the caller's (unclamped) band; the clamp of ksw.c:399-407 happens on the device.  zdrop must equal the
+ * context's opt.zdrop (mem_chain2aln passes opt->zdrop to every call, bwa/bwamem.c:734,762); other values are rejected. */
 typedef struct { int32_t qlen, tlen, w, h0, end_bonus, zdrop; int64_t q_off, t_off; } bwaflow_ext_job_t;
 /* its six outputs: return value, *_qle, *_tle, *_gtle, *_gscore, *_max_off (bwa/ksw.c:473-478) */
 typedef struct { int32_t score, qle, tle, gtle, gscore, max_off; } bwaflow_ext_result_t;

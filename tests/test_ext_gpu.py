@@ -83,7 +83,7 @@ def _random_jobs(rng, n, qmax, mat, opt, zdrops=(0, 10, 100), ws=(1, 5, 100, 200
                     out.append(x)
             out = (out + list(rng.integers(0, 4, 40)))[:tl]
             t = np.array(out + [0] * (tl - len(out)), dtype=np.uint8)[:tl]
-        w, zd = int(rng.choice(ws)), int(rng.choice(zdrops))
+        w, zd = int(rng.choice(ws)), int(opt.zdrop)      # ksw_extend2 always gets opt->zdrop; the batch rejects anything else
         h0, eb = int(rng.integers(1, 200)), int(rng.choice([0, 5]))
         jobs[i] = (ql, tl, w, h0, eb, zd, qo, to)
         qs.append(q)
@@ -166,6 +166,20 @@ def test_ext_rejects_oversized_jobs(ctx):
     jobs[0] = (2000, 10, 100, 20, 5, 100, 0, 0)
     b = capi.ExtBatch(ctx, 1, 4096, 4096)
     b.submit(jobs, np.zeros(2000, np.uint8), np.zeros(10, np.uint8))
+    with pytest.raises(capi.BwaflowError):
+        b.collect()
+    b.close()
+
+
+def test_ext_rejects_foreign_zdrop(ctx):
+    """A job's zdrop must be the context's (mem_chain2aln passes opt->zdrop to every call); a different value is an error, not a
+    silently different result."""
+    from bwaflow_b200 import capi
+    jobs = np.zeros(2, dtype=capi.EXT_JOB)
+    jobs[0] = (4, 4, 100, 20, 5, 100, 0, 0)
+    jobs[1] = (4, 4, 100, 20, 5, 37, 4, 4)
+    b = capi.ExtBatch(ctx, 2, 64, 64)
+    b.submit(jobs, np.zeros(8, np.uint8), np.zeros(8, np.uint8))
     with pytest.raises(capi.BwaflowError):
         b.collect()
     b.close()
