@@ -305,6 +305,7 @@ def main():
     for h in hps:
         out = step_e2e(h)                  # first touch: allocations, local-memory setup, capacity growth
     n_regs = len(out["alnreg"])
+    n_exact_reads = hps[-1].batch.exact_reads()
     n_chk = min(reads.n, 100_000)          # kept for the parity check against the reference in the CPU-baseline leg
     chk_off = np.array(out["alnreg_off"][:n_chk + 1], dtype=np.int64)
     chk_regs = np.array(out["alnreg"][:chk_off[-1]])
@@ -379,7 +380,7 @@ def main():
             "breakdown_ms": {"smem_stage": k_smem, "seedpos_stage": k_pos, "device_chaining": k_chain, "c2a_stage": k_c2a,
                              "step": ms_step, "e2e_step": ms_e2e / args.steps, "index_build_s": t_index},
             "counts": {"n_intv": parts[-1].n_intv, "n_pos": parts[-1].n_pos, "n_chains": parts[-1].n_chains,
-                       "n_seeds": parts[-1].n_seeds, "n_regs": n_regs},
+                       "n_seeds": parts[-1].n_seeds, "n_regs": n_regs, "stage4_reads_on_exact_kernel": n_exact_reads},
             "seedpos_gbs": blocks_pos * 64 / (k_pos * 1e-3) / 1e9 if k_pos > 0 else None}
     if not args.no_ext_microbench:
         line["ext_microbench"] = ext_microbench(ctx, peak_gcups)

@@ -95,6 +95,7 @@ def lib():
             L.bwaflow_c2a_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Timing)]
             L.bwaflow_c2a_rerun.argtypes = [C.c_void_p]
             L.bwaflow_c2a_rerun_counted.argtypes = [C.c_void_p]
+            L.bwaflow_c2a_exact_reads.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         if hasattr(L, "bwaflow_smem_batch_create"):
             L.bwaflow_smem_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
             L.bwaflow_smem_batch_destroy.argtypes = [C.c_void_p]
@@ -108,6 +109,7 @@ def lib():
         L.bwaflow_hot_submit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.bwaflow_hot_rerun.argtypes = [C.c_void_p]
         L.bwaflow_hot_rerun_counted.argtypes = [C.c_void_p]
+        L.bwaflow_hot_exact_reads.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.bwaflow_hot_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(HotTiming)]
         L.bwaflow_stopwatch_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.bwaflow_stopwatch_start.argtypes = [C.c_void_p]
@@ -279,6 +281,12 @@ class C2ABatch:
         check(self.L.bwaflow_c2a_submit(self.h, self.n, _p(bases) if bases is not None else None, _p(read_off), _p(chains),
                                         _p(chain_off), _p(seeds), len(seeds)))
 
+    def exact_reads(self):
+        """Reads of the last collected launch that stage 4 ran on its exact lane-per-read kernel."""
+        n = C.c_int64()
+        check(self.L.bwaflow_c2a_exact_reads(self.h, C.byref(n)))
+        return n.value
+
     def rerun(self, counted=False):
         check(self.L.bwaflow_c2a_rerun_counted(self.h) if counted else self.L.bwaflow_c2a_rerun(self.h))
 
@@ -441,6 +449,11 @@ class HotBatch:
         self._keep = (bases, read_off)
         self.n = len(read_off) - 1
         check(self.L.bwaflow_hot_submit(self.h, self.n, _p(bases), _p(read_off)))
+
+    def exact_reads(self):
+        n = C.c_int64()
+        check(self.L.bwaflow_hot_exact_reads(self.h, C.byref(n)))
+        return n.value
 
     def rerun(self, counted=False):
         check(self.L.bwaflow_hot_rerun_counted(self.h) if counted else self.L.bwaflow_hot_rerun(self.h))

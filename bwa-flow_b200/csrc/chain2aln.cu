@@ -481,6 +481,7 @@ __global__ void c2a_replay_kernel(C2AArgs a, int64_t n_reads, const uint8_t *cfl
     }
   }
   strag[r] = bail ? 1 : 0;
+  if (bail) atomicAdd(a.err + 1, 1);                       // reads left to the exact kernel (reported, not an error)
   a.n_regs[r] = bail ? 0 : n_av;
 }
 
@@ -752,6 +753,13 @@ static int c2a_rerun(bwaflow_c2a_batch_t *b, bool counted)
   int r = c2a_launch(b);
   if (r) return r;
   return c2a_finish_queue(b);
+}
+
+int bwaflow_c2a_exact_reads(bwaflow_c2a_batch_t *b, int64_t *n_exact)
+{
+  BF_REQUIRE(b && n_exact && !b->pending, -22, "bwaflow_c2a_exact_reads: call after collect");
+  *n_exact = (b->spec && !b->count_cells) ? (int64_t)b->h_ctl[1] : b->n_reads;
+  return 0;
 }
 
 int bwaflow_c2a_rerun(bwaflow_c2a_batch_t *b) { return c2a_rerun(b, false); }

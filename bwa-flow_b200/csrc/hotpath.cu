@@ -280,6 +280,12 @@ static int hot_rerun(bwaflow_hot_batch_t *b, bool counted)
   return hot_run(b);
 }
 
+int bwaflow_hot_exact_reads(bwaflow_hot_batch_t *b, int64_t *n_exact)
+{
+  BF_REQUIRE(b && b->c && n_exact, -22, "bwaflow_hot_exact_reads: call after collect");
+  return bwaflow_c2a_exact_reads(b->c, n_exact);
+}
+
 int bwaflow_hot_rerun(bwaflow_hot_batch_t *b) { return hot_rerun(b, false); }
 int bwaflow_hot_rerun_counted(bwaflow_hot_batch_t *b) { return hot_rerun(b, true); }
 

@@ -43,6 +43,9 @@ def test_c2a_matches_golden(case, request, c2a_mode):
         bad = np.nonzero(regs[k] != exp[k])[0]
         assert len(bad) == 0, (k, bad[:5], regs[bad[:5]], exp[bad[:5]])
     assert regs.tobytes() == exp.tobytes()
+    n_exact = b.exact_reads()
+    assert n_exact == ix.reads.n if c2a_mode == "exact" else 0 <= n_exact < ix.reads.n
+    print("%s/%s: %d of %d reads on the exact kernel" % (case, c2a_mode, n_exact, ix.reads.n))
     # a second pass over resident inputs gives the same answer (skip flags and queues are reset per launch), and so does the
     # cell-counting pass (every read on the exact kernel); the count is the reference's executed DP cells
     b.rerun()
