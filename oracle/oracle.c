@@ -6,7 +6,7 @@
  * load this file's library; the product path (bwa-flow_b200/, include/) never
  * does and fails loudly without its CUDA library.
  *
- * Parity is PINNED: tests/test_oracle_vs_ref.py checks every function here
+ * Parity is PINNED: tests/test_oracle_golden.py checks every function here
  * against oracle/_ref (the reference's own bwa/ *.c + src/bwa_wrapper.cpp
  * compiled in place) and against the committed fixtures in tests/golden/
  * that oracle/_ref produced (tests/golden/make_golden.py).
