@@ -34,7 +34,7 @@ void fill_score(const bwaflow_opt_t &o, DevScore &s)
 } // namespace bwaflow
 
 using namespace bwaflow;
-namespace bwaflow { int densify_sa(bwaflow_ctx *c, int dense_shift, uint64_t n_sa, void **d_dense); }
+namespace bwaflow { int densify_sa(bwaflow_ctx *c, int dense_shift, uint64_t n_sa, void **d_dense); int build_kmer_table(bwaflow_ctx *c, int K, void **d_tab); }
 
 // forward + reverse complement text from the 2-bit pac, one thread per 32-symbol word
 __global__ void ctx_text_kernel(const uint8_t *pac, int64_t L, uint64_t *T, int64_t n_words)
@@ -266,6 +266,14 @@ int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt
       c->d_sa = d_dense;
       d.sa = (const uint64_t *)d_dense; d.sa_shift = dense_shift;
     }
+    // K-mer jump table for pass 3 of the seeding (512 MB at K = 12; BWAFLOW_KMER_K=0 disables, <= 13)
+    d.kmer_tab = nullptr; d.kmer_k = 0;
+    int kmer_k = 12;
+    if (const char *s = getenv("BWAFLOW_KMER_K")) kmer_k = atoi(s);
+    if (kmer_k >= 2 && kmer_k <= 13) {
+      if ((r = build_kmer_table(c, kmer_k, &c->d_kmer))) return r;
+      d.kmer_tab = (const uint4 *)c->d_kmer; d.kmer_k = kmer_k;
+    }
     // With the full suffix array: the inverse suffix array and the 2-bit text, which let the seeding kernel extend an interval
     // that has become unique by comparing bases against the text instead of walking the index (smem.cu, text-anchored mode).
     d.text = nullptr; d.isa = nullptr;
@@ -332,7 +340,7 @@ void bwaflow_ctx_destroy(bwaflow_ctx_t *c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->d_bwt); cudaFree(c->d_sa); cudaFree(c->d_text); cudaFree(c->d_isa); cudaFree(c->d_pac); cudaFree(c->d_ctg_off); cudaFree(c->d_ctg_len);
+  cudaFree(c->d_bwt); cudaFree(c->d_sa); cudaFree(c->d_text); cudaFree(c->d_isa); cudaFree(c->d_kmer); cudaFree(c->d_pac); cudaFree(c->d_ctg_off); cudaFree(c->d_ctg_len);
   free(c);
 }
 

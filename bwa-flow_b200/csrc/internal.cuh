@@ -40,6 +40,9 @@ struct DevIndex {
   uint64_t sbt[8 * 5];
   const uint64_t *sa;
   int sa_shift;            // log2(sa_intv)
+  // K-mer jump table of the pass-3 seeding kernel (smem.cu): entry v = the interval of the K-mer with code v after K-1 forward
+  // extensions from bwt_set_intv, exactly as bwt_seed_strategy1 computes it step by step, as {x0, x1} {x2, block touches}.
+  const uint4 *kmer_tab; int kmer_k;
   // Text-anchored extension of unique intervals (smem.cu): present only with the full suffix array (sa_shift == 0).
   const uint64_t *text;    // forward + reverse-complement text, 32 two-bit symbols per u64 (MSB first), zero padded
   const uint64_t *isa;     // inverse suffix array: isa[p] = row of suffix p, p in [0, seq_len]
@@ -74,7 +77,7 @@ struct bwaflow_ctx {
   bwaflow::DevIndex ix;
   bwaflow::Params par;
   // owned device allocations
-  void *d_bwt, *d_sa, *d_pac, *d_ctg_off, *d_ctg_len, *d_text, *d_isa;
+  void *d_bwt, *d_sa, *d_pac, *d_ctg_off, *d_ctg_len, *d_text, *d_isa, *d_kmer;
 };
 
 namespace bwaflow {

@@ -405,6 +405,17 @@ __global__ void __launch_bounds__(128) smem_p3_kernel(const SmemArgs a)
         continue;
       }
       px = x; ik = set_intv(ix, q[x]); cur = x + 1;          // bwa/bwt.c:364-366
+      if (ix.kmer_tab && ix.kmer_k <= msl && x + ix.kmer_k <= len) {
+        // the first K-1 extensions cannot emit (cur - px < min_seed_len): take their result from the K-mer table
+        uint64_t code = 0; bool acgt = true;
+        for (int t = 0; t < ix.kmer_k; ++t) { const uint32_t b = q[x + t]; acgt &= b < 4; code = code << 2 | (b & 3); }
+        if (acgt) {
+          const uint4 e0 = __ldg(ix.kmer_tab + 2 * code), e1 = __ldg(ix.kmer_tab + 2 * code + 1);
+          ik.x0 = (uint64_t)e0.y << 32 | e0.x; ik.x1 = (uint64_t)e0.w << 32 | e0.z; ik.x2 = (uint64_t)e1.y << 32 | e1.x;
+          blocks += e1.z;
+          cur = x + ix.kmer_k;
+        }
+      }
       if (cur >= len) { x = len; continue; }
       if (q[cur] > 3) { x = cur + 1; continue; }
       c = 3 - q[cur]; pending = true;
@@ -482,6 +493,31 @@ __global__ void sa_densify_kernel(DevIndex ix, uint64_t n_sa, int dense_shift, u
     if ((r & ref_mask) == 0) break;
     if ((r & dmask) == 0) dense[r >> dense_shift] = v;
   }
+}
+
+// One thread per K-mer: the K-1 forward extensions bwt_seed_strategy1 (bwa/bwt.c:364-376) makes before it can emit anything
+// (no seed shorter than min_seed_len + 1 > K is ever emitted), so that pass 3 starts every seed from one table read.
+__global__ void kmer_table_kernel(DevIndex ix, int K, uint4 *tab)
+{
+  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >> (2 * K)) return;
+  unsigned long long blocks = 0;
+  Intv ik = set_intv(ix, (int)(v >> (2 * (K - 1))) & 3);
+  for (int i = 1; i < K; ++i) ik = extend1(ix, ik, 0, 3 - ((int)(v >> (2 * (K - 1 - i))) & 3), &blocks);
+  tab[2 * v] = make_uint4((uint32_t)ik.x0, (uint32_t)(ik.x0 >> 32), (uint32_t)ik.x1, (uint32_t)(ik.x1 >> 32));
+  tab[2 * v + 1] = make_uint4((uint32_t)ik.x2, (uint32_t)(ik.x2 >> 32), (uint32_t)blocks, 0u);
+}
+
+int build_kmer_table(bwaflow_ctx *c, int K, void **d_tab)
+{
+  const uint64_t n = 1ull << (2 * K);
+  BF_CUDA(cudaMalloc(d_tab, n * 32));
+  DevIndex ix = c->ix;
+  ix.occ_cs &= ~2;                                         // count block touches normally
+  kmer_table_kernel<<<(unsigned)((n + 127) / 128), 128>>>(ix, K, (uint4 *)*d_tab);
+  BF_CUDA(cudaGetLastError());
+  BF_CUDA(cudaDeviceSynchronize());
+  return 0;
 }
 
 int densify_sa(bwaflow_ctx *c, int dense_shift, uint64_t n_sa, void **d_dense)

@@ -15,8 +15,15 @@ def _ctx(ix, **opt_over):
     return capi.Context(0, index, opt, keepalive=keep)
 
 
+@pytest.fixture(params=["12", "5", "0"])
+def kmer_k(request, monkeypatch):
+    """Pass 3 starts every seed from a K-mer table entry (default K = 12); 0 = step by step as bwt_seed_strategy1 does."""
+    monkeypatch.setenv("BWAFLOW_KMER_K", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("case", ["c1", "c5"])
-def test_smem_matches_golden(case, request):
+def test_smem_matches_golden(case, request, kmer_k):
     from bwaflow_b200 import capi
     ix = request.getfixturevalue("index_" + case)
     g = request.getfixturevalue("golden_" + case)
@@ -52,7 +59,7 @@ def test_sa_lookup_known_answers(index_c1, golden_c1):
     ctx.close()
 
 
-def test_smem_edge_reads(index_c1):
+def test_smem_edge_reads(index_c1, kmer_k):
     """All-N reads, reads shorter than min_seed_len, N-riddled reads, exact reference substrings (both strands),
     a highly repetitive read, mixed lengths in one batch; checked against the oracle restatement."""
     from bwaflow_b200 import capi
