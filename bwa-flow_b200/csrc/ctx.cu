@@ -266,11 +266,11 @@ int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt
       c->d_sa = d_dense;
       d.sa = (const uint64_t *)d_dense; d.sa_shift = dense_shift;
     }
-    // K-mer jump table for pass 3 of the seeding (512 MB at K = 12; BWAFLOW_KMER_K=0 disables, <= 13)
+    // K-mer jump table for pass 3 of the seeding (4^K entries of 32 bytes; BWAFLOW_KMER_K=0 disables, at most 14)
     d.kmer_tab = nullptr; d.kmer_k = 0;
-    int kmer_k = 12;
+    int kmer_k = d.seq_len >= (1ull << 32) ? 14 : 12;         // 8.6 GB / 0.5 GB: the bigger table only pays on a human-scale index
     if (const char *s = getenv("BWAFLOW_KMER_K")) kmer_k = atoi(s);
-    if (kmer_k >= 2 && kmer_k <= 13) {
+    if (kmer_k >= 2 && kmer_k <= 14) {
       if ((r = build_kmer_table(c, kmer_k, &c->d_kmer))) return r;
       d.kmer_tab = (const uint4 *)c->d_kmer; d.kmer_k = kmer_k;
     }

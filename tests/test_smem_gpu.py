@@ -15,7 +15,7 @@ def _ctx(ix, **opt_over):
     return capi.Context(0, index, opt, keepalive=keep)
 
 
-@pytest.fixture(params=["12", "5", "0"])
+@pytest.fixture(params=["14", "12", "5", "0"])
 def kmer_k(request, monkeypatch):
     """Pass 3 starts every seed from a K-mer table entry (default K = 12); 0 = step by step as bwt_seed_strategy1 does."""
     monkeypatch.setenv("BWAFLOW_KMER_K", request.param)
