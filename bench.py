@@ -148,12 +148,16 @@ def ext_microbench(ctx, peak_gcups, n_jobs_target=10_000_000):
     jobs, qp, tp = synth.extension_jobs(ref, reads)
     n0 = len(jobs["qlen"])
     rep = max(1, n_jobs_target // n0)
-    ej = np.zeros(n0 * rep, dtype=capi.EXT_JOB)
+    # pinned host staging, as the FPGA tasks map their buffers (src/fpga/SWTask.cpp:30-60)
+    ej = capi.pinned((n0 * rep,), capi.EXT_JOB)
+    ej[:] = np.zeros(1, dtype=capi.EXT_JOB)[0]
     for k in ("qlen", "tlen", "w", "h0", "end_bonus", "zdrop"):
         ej[k] = np.tile(jobs[k], rep)
     ej["q_off"] = np.tile(jobs["q_off"], rep) + np.repeat(np.arange(rep, dtype=np.int64) * len(qp), n0)
     ej["t_off"] = np.tile(jobs["t_off"], rep) + np.repeat(np.arange(rep, dtype=np.int64) * len(tp), n0)
-    qpp, tpp = np.tile(qp, rep), np.tile(tp, rep)
+    qpp, tpp = capi.pinned((len(qp) * rep,), np.uint8), capi.pinned((len(tp) * rep,), np.uint8)
+    qpp.reshape(rep, -1)[:] = qp
+    tpp.reshape(rep, -1)[:] = tp
     eb = capi.ExtBatch(ctx, len(ej), len(qpp) + 1, len(tpp) + 1)
     eb.submit(ej, qpp, tpp)
     res, t_e2e = eb.collect()
