@@ -102,6 +102,8 @@ def lib():
             L.bwaflow_smem_submit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
             L.bwaflow_smem_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Timing)]
             L.bwaflow_smem_rerun.argtypes = [C.c_void_p]
+            L.bwaflow_smem_rerun_counted.argtypes = [C.c_void_p]
+            L.bwaflow_smem_set_anchored.argtypes = [C.c_void_p, C.c_int]
             L.bwaflow_smem_seed_positions.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Timing)]
             L.bwaflow_sa_lookup.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.bwaflow_hot_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ChainOpt), C.c_void_p, C.POINTER(C.c_void_p)]
@@ -303,6 +305,9 @@ class C2ABatch:
             self.h = C.c_void_p()
 
 
+ANCHORED = (1 << 39) - 1
+
+
 class SmemBatch:
     """SMemTask-shaped batch: reads -> sorted bwtintv_t lists (+ seed positions for chaining)."""
 
@@ -319,8 +324,13 @@ class SmemBatch:
         self.n = len(read_off) - 1
         check(self.L.bwaflow_smem_submit(self.h, self.n, _p(bases), _p(read_off)))
 
-    def rerun(self):
-        check(self.L.bwaflow_smem_rerun(self.h))
+    def rerun(self, counted=False):
+        """counted: the kernel instances that add up the reference's occ-block touches (timing.work_units)."""
+        check(self.L.bwaflow_smem_rerun_counted(self.h) if counted else self.L.bwaflow_smem_rerun(self.h))
+
+    def set_anchored(self, on):
+        """Unique intervals may come back as {text position, ANCHORED, 1} (the hot path's internal form)."""
+        check(self.L.bwaflow_smem_set_anchored(self.h, 1 if on else 0))
 
     def collect(self):
         a, off = C.c_void_p(), C.c_void_p()

@@ -21,6 +21,10 @@ struct bwaflow_smem_batch {
   // seed positions
   int64_t *d_pcnt, *d_poff, *h_poff, *d_pos, *h_pos; int64_t pos_cap, hpos_cap;
   int blocks_per_launch;
+  // smem_fast.cu
+  uint64_t *d_packed; int fast_blocks_per_sm, sweep_blocks_per_sm, x_min;
+  bool want_rows;                   // intervals leave the device as BWT rows (interval API): no text-anchored entries
+  bool count_blocks;                // this launch counts the reference's occ-block touches (exact instances)
   bool pending;
 };
 
@@ -63,6 +67,14 @@ ExtDeviceView ext_device_view(bwaflow_ext_batch_t *b);
 int ext_launch_device(bwaflow_ext_batch_t *b, int64_t n_jobs, cudaStream_t st);
 void ext_set_pair_classes(bwaflow_ext_batch_t *b, int n);   // qlen classes below n run on the packed engine
 void ext_set_order_rows(bwaflow_ext_batch_t *b, int on);    // queue order by estimated lifetime first (see ext_key_kernel)
+// smem_fast.cu
+struct SmemArgs;
+int smem_fast_launch(bwaflow_smem_batch *b, const SmemArgs &a, bool text, bool count);
+int smem_fast_setup(bwaflow_smem_batch *b);
+// smem_sweep.cu
+int smem_sweep_launch(bwaflow_smem_batch *b, const SmemArgs &a, bool text);
+int smem_sweep_setup(bwaflow_smem_batch *b);
+int build_level_tables(bwaflow_ctx *c, int K, void **d_tab);
 // smem.cu: device-side halves of submit/collect (no interval D2H); used by the fused hot path
 int smem_launch(bwaflow_smem_batch *b);
 int smem_finish_device(bwaflow_smem_batch *b);                 // waits, regrows slots on overflow, compacts into d_out/d_off; sets n_intv

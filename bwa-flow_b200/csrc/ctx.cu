@@ -34,7 +34,7 @@ void fill_score(const bwaflow_opt_t &o, DevScore &s)
 } // namespace bwaflow
 
 using namespace bwaflow;
-namespace bwaflow { int densify_sa(bwaflow_ctx *c, int dense_shift, uint64_t n_sa, void **d_dense); int build_kmer_table(bwaflow_ctx *c, int K, void **d_tab); }
+namespace bwaflow { int densify_sa(bwaflow_ctx *c, int dense_shift, uint64_t n_sa, void **d_dense); int build_level_tables(bwaflow_ctx *c, int K, void **d_tab); }
 
 // forward + reverse complement text from the 2-bit pac, one thread per 32-symbol word
 __global__ void ctx_text_kernel(const uint8_t *pac, int64_t L, uint64_t *T, int64_t n_words)
@@ -52,14 +52,6 @@ __global__ void ctx_text_kernel(const uint8_t *pac, int64_t L, uint64_t *T, int6
   }
   T[w] = v;
 }
-// isa[sa[r]] = r over all rows (row 0 = the '$' suffix = position n, stored in sa[0] as -1)
-__global__ void ctx_isa_kernel(const uint64_t *sa, int64_t n, uint64_t *isa)
-{
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r > n) return;
-  isa[r == 0 ? (uint64_t)n : sa[r]] = (uint64_t)r;
-}
-
 // bwa layout (4 x u64 counts + 8 x u32 symbols per 128 symbols, bwa/bwt.h:72-73) -> occ32 blocks (internal.cuh).
 // Pass 1, one thread per 64-symbol block: absolute suffix counts S1,S2,S3 (symbols >0, >1, >2 before the block).
 __global__ void occ32_count_kernel(const uint32_t *bwt, uint64_t n64, uint4 *occ, uint64_t *absS)
@@ -187,25 +179,14 @@ int bwaflow_ctx_set_opt(bwaflow_ctx_t *ctx, const bwaflow_opt_t *opt)
   return 0;
 }
 
-int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt_t *opt, bwaflow_ctx_t **out)
+static int ctx_init(bwaflow_ctx_t *c, int device, const cudaDeviceProp &prop, const bwaflow_index_t *idx, const bwaflow_opt_t *opt)
 {
-  BF_REQUIRE(out, -22, "bwaflow_ctx_create: out is null");
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n == 0) { cudaGetLastError(); set_error("no CUDA device available (this backend has no CPU fallback)"); return -19; }
-  BF_REQUIRE(device >= 0 && device < n, -19, "device %d out of range (have %d)", device, n);
-  BF_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  BF_CUDA(cudaGetDeviceProperties(&prop, device));
-  BF_REQUIRE(prop.major >= 10, -19, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-
-  bwaflow_ctx_t *c = (bwaflow_ctx_t *)calloc(1, sizeof(bwaflow_ctx_t));
   c->device = device;
   c->n_sm = prop.multiProcessorCount;
   bwaflow_opt_t def;
   if (!opt) { bwaflow_opt_default(&def); opt = &def; }
   int r = bwaflow_ctx_set_opt(c, opt);
-  if (r) { free(c); return r; }
+  if (r) return r;
 
   if (const char *s = getenv("BWAFLOW_L2_FETCH")) BF_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(s)));
   if (idx) {
@@ -266,31 +247,57 @@ int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt
       c->d_sa = d_dense;
       d.sa = (const uint64_t *)d_dense; d.sa_shift = dense_shift;
     }
-    // K-mer jump table for pass 3 of the seeding (4^K entries of 32 bytes; BWAFLOW_KMER_K=0 disables, at most 14)
-    d.kmer_tab = nullptr; d.kmer_k = 0;
-    int kmer_k = d.seq_len >= (1ull << 32) ? 14 : 12;         // 8.6 GB / 0.5 GB: the bigger table only pays on a human-scale index
-    if (const char *s = getenv("BWAFLOW_KMER_K")) kmer_k = atoi(s);
-    if (kmer_k >= 2 && kmer_k <= 14) {
-      if ((r = build_kmer_table(c, kmer_k, &c->d_kmer))) return r;
-      d.kmer_tab = (const uint4 *)c->d_kmer; d.kmer_k = kmer_k;
+    // Level tables of the seeding kernels (smem_fast.cu): intervals of all patterns of 1..K bases, 16 bytes each.  K follows the
+    // index size (about log4(rows) - 1: the deepest level whose patterns still occur several times), at most 15
+    // (22.9 GB on a human-scale index).  BWAFLOW_KMER_K overrides; 0 disables.  If the tables do not fit, K shrinks.
+    d.ktab = nullptr; d.ktab_k = 0;
+    int kk = 0;
+    while ((4ull << (2 * kk)) <= d.seq_len) ++kk;          // floor(log4(seq_len))
+    kk = kk - 1 > 15 ? 15 : kk - 1;
+    if (const char *s = getenv("BWAFLOW_KMER_K")) kk = atoi(s);
+    if (kk > 15) kk = 15;
+    for (; kk >= 2; --kk) {
+      size_t free_b = 0, total_b = 0;
+      BF_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      const uint64_t need = (((1ull << (2 * (kk + 1))) - 4) / 3) * 16;
+      if (need + (24ull << 30) > free_b && need > (1ull << 30)) continue;   // leave room for the batches
+      if ((r = build_level_tables(c, kk, &c->d_ktab))) return r;
+      d.ktab = (const uint4 *)c->d_ktab; d.ktab_k = kk;
+      break;
     }
-    // With the full suffix array: the inverse suffix array and the 2-bit text, which let the seeding kernel extend an interval
-    // that has become unique by comparing bases against the text instead of walking the index (smem.cu, text-anchored mode).
-    d.text = nullptr; d.isa = nullptr;
-    int text_mode = 0;                          // opt-in: measured slower on the 3.1 Gbp index (only 18% of the extension steps run on unique intervals)
+    // The 2-bit text (with the full suffix array only): unique intervals are extended by comparing bases against it.
+    d.text = nullptr;
+    int text_mode = 1;
     if (const char *s = getenv("BWAFLOW_TEXT_MODE")) text_mode = atoi(s);
     if (text_mode && d.sa_shift == 0) {
       const int64_t n = (int64_t)d.seq_len, n_words = (n + 31) / 32 + 4;
       BF_CUDA(cudaMalloc(&c->d_text, n_words * 8));
-      BF_CUDA(cudaMalloc(&c->d_isa, (size_t)(n + 1) * 8));
       ctx_text_kernel<<<(unsigned)((n_words + 255) / 256), 256>>>((const uint8_t *)c->d_pac, d.l_pac, (uint64_t *)c->d_text, n_words);
-      ctx_isa_kernel<<<(unsigned)((n + 1 + 255) / 256), 256>>>(d.sa, n, (uint64_t *)c->d_isa);
       BF_CUDA(cudaGetLastError());
       BF_CUDA(cudaDeviceSynchronize());
-      d.text = (const uint64_t *)c->d_text; d.isa = (const uint64_t *)c->d_isa;
+      d.text = (const uint64_t *)c->d_text;
     }
     c->has_index = true;
   }
+  return 0;
+}
+
+int bwaflow_ctx_create(int device, const bwaflow_index_t *idx, const bwaflow_opt_t *opt, bwaflow_ctx_t **out)
+{
+  BF_REQUIRE(out, -22, "bwaflow_ctx_create: out is null");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { cudaGetLastError(); set_error("no CUDA device available (this backend has no CPU fallback)"); return -19; }
+  BF_REQUIRE(device >= 0 && device < n, -19, "device %d out of range (have %d)", device, n);
+  BF_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BF_CUDA(cudaGetDeviceProperties(&prop, device));
+  BF_REQUIRE(prop.major >= 10, -19, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+  bwaflow_ctx_t *c = (bwaflow_ctx_t *)calloc(1, sizeof(bwaflow_ctx_t));
+  BF_REQUIRE(c, -12, "bwaflow_ctx_create: out of host memory");
+  const int r = ctx_init(c, device, prop, idx, opt);
+  if (r) { bwaflow_ctx_destroy(c); cudaGetLastError(); return r; }      // one cleanup path: everything uploaded so far is released
   *out = c;
   return 0;
 }
@@ -340,7 +347,7 @@ void bwaflow_ctx_destroy(bwaflow_ctx_t *c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->d_bwt); cudaFree(c->d_sa); cudaFree(c->d_text); cudaFree(c->d_isa); cudaFree(c->d_kmer); cudaFree(c->d_pac); cudaFree(c->d_ctg_off); cudaFree(c->d_ctg_len);
+  cudaFree(c->d_bwt); cudaFree(c->d_sa); cudaFree(c->d_text); cudaFree(c->d_ktab); cudaFree(c->d_pac); cudaFree(c->d_ctg_off); cudaFree(c->d_ctg_len);
   free(c);
 }
 

@@ -141,6 +141,7 @@ static int hot_run(bwaflow_hot_batch *b)
   int r;
   // ---- stage 2
   BF_CUDA(cudaEventRecord(b->ev[1], st));
+  s->want_rows = false; s->count_blocks = b->count_cells;   // rows are not needed downstream: text-anchored seeds carry positions
   if ((r = smem_launch(s))) return r;
   BF_CUDA(cudaMemcpyAsync(s->h_off, s->d_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st));
   BF_CUDA(cudaMemcpyAsync(s->h_ctl, s->d_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));

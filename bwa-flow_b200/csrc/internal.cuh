@@ -40,12 +40,12 @@ struct DevIndex {
   uint64_t sbt[8 * 5];
   const uint64_t *sa;
   int sa_shift;            // log2(sa_intv)
-  // K-mer jump table of the pass-3 seeding kernel (smem.cu): entry v = the interval of the K-mer with code v after K-1 forward
-  // extensions from bwt_set_intv, exactly as bwt_seed_strategy1 computes it step by step, as {x0, x1} {x2, block touches}.
-  const uint4 *kmer_tab; int kmer_k;
-  // Text-anchored extension of unique intervals (smem.cu): present only with the full suffix array (sa_shift == 0).
-  const uint64_t *text;    // forward + reverse-complement text, 32 two-bit symbols per u64 (MSB first), zero padded
-  const uint64_t *isa;     // inverse suffix array: isa[p] = row of suffix p, p in [0, seq_len]
+  // Level tables of the seeding kernels (smem_fast.cu): the bidirectional interval of every pattern of 1..ktab_k bases as a
+  // 16-byte packed entry (fmindex.cuh), level L at entry offset (4^L - 4) / 3, code = the pattern's bases MSB first.
+  const uint4 *ktab; int ktab_k;
+  // Forward + reverse-complement text, 32 two-bit symbols per u64 (MSB first), zero padded: lets the seeding kernel extend
+  // an interval that has become unique by comparing bases (smem_fast.cu); used only with the full suffix array (sa_shift == 0).
+  const uint64_t *text;
   int64_t l_pac;
   const uint8_t *pac;
   int n_seqs;
@@ -77,7 +77,7 @@ struct bwaflow_ctx {
   bwaflow::DevIndex ix;
   bwaflow::Params par;
   // owned device allocations
-  void *d_bwt, *d_sa, *d_pac, *d_ctg_off, *d_ctg_len, *d_text, *d_isa, *d_kmer;
+  void *d_bwt, *d_sa, *d_pac, *d_ctg_off, *d_ctg_len, *d_text, *d_ktab;
 };
 
 namespace bwaflow {

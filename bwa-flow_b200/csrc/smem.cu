@@ -17,126 +17,11 @@
 #include <stdlib.h>
 #include "internal.cuh"
 #include "batches.cuh"
+#include "fmindex.cuh"
+#include "smem_args.cuh"
 
 namespace bwaflow {
 
-struct Intv { uint64_t x0, x1, x2; };
-
-__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, int sh)
-{ // PTX shl clamps shift amounts above 31 (result 0); C++ << would be undefined there
-  uint32_t r;
-  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(sh));
-  return r;
-}
-
-// Among the first n symbols (1..64) of an occ32 block, whose 64 two-bit symbols are the four 32-bit words of `sy`
-// (16 symbols each, MSB first): how many equal base c (*eq) and how many are greater than c (*gt).  32-bit
-// single-instruction logic; the per-word prefix mask is one clamped shift.  POPC runs on the narrow XU pipe, so the
-// masks of two words (which only use even bit positions) are interleaved before counting: 2+2 popcounts.
-__device__ __forceinline__ void prefix_counts(const uint4 sy, int n, int c, int *eq, int *gt)
-{
-  const uint32_t w[4] = {sy.x, sy.y, sy.z, sy.w};
-  const uint32_t ODD = 0x55555555u;
-  const uint32_t cpat = (uint32_t)c * ODD;                       // c in every 2-bit field
-  const uint32_t g_or = c == 0 ? ~0u : 0u, g_hi = c == 1 ? ~0u : 0u, g_and = c == 2 ? ~0u : 0u;
-  const int base = 32 - 2 * n;                                   // word j keeps its top 2*clamp(n-16j,0,16) bits
-  uint32_t e[4], g[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t keep = shl_clamp(ODD, max(base + 32 * j, 0));   // even bit of every kept symbol
-    const uint32_t x = w[j] ^ cpat, lo = w[j], hi = w[j] >> 1;
-    e[j] = ~(x | x >> 1) & keep;
-    g[j] = (((hi | lo) & g_or) | (hi & g_hi) | (hi & lo & g_and)) & keep;
-  }
-  *eq = __popc(e[0] | e[1] << 1) + __popc(e[2] | e[3] << 1);
-  *gt = __popc(g[0] | g[1] << 1) + __popc(g[2] | g[3] << 1);
-}
-
-// Occ(c, k) and Occ(>c, k) over BWT rows [0, k] (k already adjusted for the '$' row): one 32-byte occ32 block.
-// Header S1,S2,S3 = symbols >0,>1,>2 before the block (relative to its superblock); S0 = the block start, S4 = 0:
-//   Occ(>c) = S[c+1] + gt,   Occ(c) = S[c] - S[c+1] + eq.
-__device__ __forceinline__ void occ_eq_gt(const DevIndex &ix, uint64_t k, int c, uint64_t *eq, uint64_t *gt)
-{
-  const uint4 *b = ix.occ + ((k >> 6) << 1);
-  const uint4 hd = occ_ld(ix, b), sy = occ_ld(ix, b + 1);
-  int e, g;
-  prefix_counts(sy, (int)(k & 63) + 1, c, &e, &g);
-  const uint64_t *sb = ix.sbt + (k >> 31) * 5;
-  const uint32_t r0 = (uint32_t)(k & 0x7fffffffull) & ~63u;    // block start relative to the superblock
-  const uint32_t lo_rel = c == 0 ? r0 : c == 1 ? hd.x : c == 2 ? hd.y : hd.z;        // S[c]
-  const uint32_t hi_rel = c == 0 ? hd.x : c == 1 ? hd.y : c == 2 ? hd.z : 0u;        // S[c+1]
-  const uint64_t Sc = sb[c] + lo_rel, Sc1 = sb[c + 1] + hi_rel;
-  *gt = Sc1 + (uint64_t)g;
-  *eq = Sc - Sc1 + (uint64_t)e;
-}
-
-// ok[c] of bwt_extend (bwa/bwt.c:262-275) for the one base c the caller wants: Occ of c and of all bases > c at both
-// ends of the interval (the part of bwt_2occ4, bwa/bwt.c:189-220, that is consumed).  Straight-line code: all lanes of
-// the warp run the two lookups together.  `blocks` counts touches of the REFERENCE's 64-byte blocks (the algorithmic
-// unit of SURVEY 8d: one if both ends share a 128-symbol block, else two), not of our 32-byte device blocks.
-__device__ __forceinline__ Intv extend1(const DevIndex &ix, const Intv ik, int is_back, int c, unsigned long long *blocks)
-{
-  const uint64_t xf = is_back ? ik.x0 : ik.x1, xg = is_back ? ik.x1 : ik.x0;
-  const uint64_t k = xf - 1, l = xf - 1 + ik.x2;
-  const uint64_t _k = k - (k >= ix.primary), _l = l - (l >= ix.primary);
-  uint64_t ek, gk, el, gl;
-  occ_eq_gt(ix, _k, c, &ek, &gk);
-  occ_eq_gt(ix, _l, c, &el, &gl);
-  if (!(ix.occ_cs & 2)) *blocks += (_k >> 7) != (_l >> 7) ? 2 : 1;   // (bit 1 = developer switch: count text-anchored steps only)
-  Intv o;
-  const uint64_t acc = xg + (xf <= ix.primary && xf + ik.x2 - 1 >= ix.primary) + (gl - gk);
-  const uint64_t nf = ix.L2[c] + 1 + ek;
-  o.x2 = el - ek;
-  if (is_back) { o.x0 = nf; o.x1 = acc; } else { o.x1 = nf; o.x0 = acc; }
-  return o;
-}
-
-__device__ __forceinline__ Intv set_intv(const DevIndex &ix, int c)
-{ // bwt_set_intv, bwa/bwt.h:80
-  Intv ik; ik.x0 = ix.L2[c] + 1; ik.x2 = ix.L2[c + 1] - ix.L2[c]; ik.x1 = ix.L2[3 - c] + 1; return ik;
-}
-
-// Text-anchored form of an interval that has become unique (x2 == 1): the pattern occurs exactly once in the
-// forward + reverse-complement text, at position x0 here; x1 holds a marker no row can equal (fields are 39 bits).
-// Extending such an interval needs no index walk: the next base either equals the text base next to the occurrence or
-// the extension fails (bwt_extend on a one-row interval computes exactly that), and its rows are recovered on demand from
-// the inverse suffix array: x[0] = isa[pos], x[1] = isa[n - pos - length] (the reverse complement occurs at the mirrored
-// position).  Only available with the full suffix array in HBM (DevIndex::isa).
-constexpr uint64_t TEXT_MARK = (1ull << 39) - 1;
-__device__ __forceinline__ bool is_text(const Intv &v) { return v.x1 == TEXT_MARK; }
-__device__ __forceinline__ Intv text_intv(uint64_t tpos) { Intv v; v.x0 = tpos; v.x1 = TEXT_MARK; v.x2 = 1; return v; }
-__device__ __forceinline__ Intv materialize(const DevIndex &ix, const Intv &v, int plen)
-{
-  if (!is_text(v)) return v;
-  Intv o; o.x0 = ix.isa[v.x0]; o.x1 = ix.isa[ix.seq_len - v.x0 - (uint64_t)plen]; o.x2 = 1;
-  return o;
-}
-constexpr int TEXT_CHUNK = 16;     // bases compared per trip of the warp loop by a lane in text-anchored mode
-
-struct SmemArgs {
-  const uint8_t *bases; const int64_t *read_off; int64_t n_reads;
-  bwaflow_intv_t *slots; int cap;            // per-read output slot of `cap` intervals
-  int *counts;                               // per-read interval count (or cap+1 on overflow)
-  int *ctl;                                  // [0] queue head, [1] overflow flag, [2] too-long flag, [3] pass-3 queue head
-  unsigned long long *blocks;                // occ-block touches (64 B each)
-  DevIndex ix;
-  int min_seed_len, split_len, split_width, max_mem_intv;
-};
-
-// One list entry of bwt_smem1a_new packed into 16 bytes: three 39-bit interval fields and an 11-bit query coordinate
-// (seq_len < 2^39, reads < 2^11); a single 128-bit local-memory access instead of four.
-__device__ __forceinline__ uint4 pack_entry(const Intv &v, int pos)
-{
-  const uint64_t lo = v.x0 | v.x1 << 39, hi = v.x1 >> 25 | v.x2 << 14 | (uint64_t)pos << 53;
-  return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
-}
-__device__ __forceinline__ Intv unpack_entry(const uint4 e, int *pos)
-{
-  const uint64_t lo = (uint64_t)e.y << 32 | e.x, hi = (uint64_t)e.w << 32 | e.z, m = (1ull << 39) - 1;
-  Intv v; v.x0 = lo & m; v.x1 = (lo >> 39 | hi << 25) & m; v.x2 = (hi >> 14) & m; *pos = (int)(hi >> 53);
-  return v;
-}
-__device__ __forceinline__ int entry_pos(const uint4 e) { return (int)(e.w >> 21); }
 
 // One read per lane.  Every trip of the warp loop performs ONE interval extension for every live lane at a single
 // convergent call site (the expensive part: index loads + popcounts), followed by a short consume step for the four
@@ -146,7 +31,7 @@ __device__ __forceinline__ int entry_pos(const uint4 e) { return (int)(e.w >> 21
 // shared memory (one row per lane); the 16-byte interval entries of the two lists are per-lane local arrays.
 enum { PH_F = 0, PH_BE = 1, PH_FE = 2, PH_P3 = 3 };
 enum { T_NONE = 0, T_FETCH, T_NEXT, T_F_DONE, T_B_SELECT, T_BE_DONE, T_FE_PICK, T_FE_FAIL, T_FE_REACHED, T_B_NEXT, T_CALL_DONE,
-       T_FINISH, T_EXIT, T_TEXT /* like T_NONE, but the pending extension is a text comparison */ };
+       T_FINISH, T_EXIT };
 
 #ifndef SMEM_MIN_BLOCKS
 #define SMEM_MIN_BLOCKS 6
@@ -178,7 +63,7 @@ __global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_k
 
   auto push_mem = [&](const Intv &tv, int beg, int end) {
     if (n_mem < a.cap) {
-      const Intv v = materialize(ix, tv, end - beg);
+      const Intv v = tv;
       bwaflow_intv_t o; o.x[0] = v.x0; o.x[1] = v.x1; o.x[2] = v.x2; o.info = (uint64_t)(uint32_t)beg << 32 | (uint32_t)end;
       mem[n_mem] = o;
     }
@@ -192,7 +77,7 @@ __global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_k
 
   for (;;) {
     // ---- transitions: run until this lane has an extension pending (or no reads are left)
-    while (ts != T_NONE && ts != T_TEXT && ts != T_EXIT) {
+    while (ts != T_NONE && ts != T_EXIT) {
       switch (ts) {
       case T_FETCH: {
         r = (int64_t)atomicAdd(a.ctl, 1);
@@ -289,14 +174,12 @@ __global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_k
         break;
       }
     }
-    if (ts == T_NONE && is_text(ik)) ts = T_TEXT;
-    if (__ballot_sync(full, ts == T_NONE || ts == T_TEXT) == 0) break;
+    if (__ballot_sync(full, ts == T_NONE) == 0) break;
     if (ts == T_NONE) {
       // ---- the one call site of bwt_extend, then the consume step of the four inner loops
-      Intv o = extend1(ix, ik, phase == PH_BE, c, &blocks);
+      const Intv o = extend1(ix, ik, phase == PH_BE, c, &blocks);
       const bool small = o.x2 < (uint64_t)mi;
       const bool changed = o.x2 != ik.x2;
-      if (ix.isa && mi == 1 && o.x2 == 1) o = text_intv(ix.sa[o.x0]);   // unique from here on: anchor it to the text
       if (phase == PH_F) {                                   // :350-357
         if (changed) push_fwd(ik, cur);
         if (changed && small) ts = T_F_DONE;
@@ -316,42 +199,6 @@ __global__ void __launch_bounds__(128, MAXL <= 256 ? SMEM_MIN_BLOCKS : 1) smem_k
         else {
           ik = o; ++cur;
           if (cur == stop) ts = T_FE_REACHED; else c = 3 - q[cur];
-        }
-      }
-      if (ts == T_NONE && is_text(ik)) ts = T_TEXT;
-    }
-    if (ts == T_TEXT) {
-      // ---- the same three inner loops for a text-anchored interval: up to TEXT_CHUNK bases per trip, each step the exact
-      // outcome bwt_extend would have on the one-row interval.  Every step counts as one block touch of the reference.
-      const int64_t n_text = (int64_t)ix.seq_len;
-      int budget = TEXT_CHUNK;
-      int64_t wi = -1; uint64_t wv = 0;                       // cached text word
-      auto sym = [&](int64_t p) -> int {
-        if ((p >> 5) != wi) { wi = p >> 5; wv = __ldg(ix.text + wi); }
-        return (int)(wv >> ((~p & 31) << 1)) & 3;
-      };
-      if (phase == PH_BE) {
-        int64_t tp = (int64_t)ik.x0;
-        while (budget-- > 0) {
-          ++blocks;
-          if (!(tp > 0 && sym(tp - 1) == (int)q[cur])) { ts = T_BE_DONE; break; }
-          --tp; ik = text_intv((uint64_t)tp); ik_beg = cur; back[back_n++] = pack_entry(ik, 0); --cur;
-          if (!(cur >= 0 && q[cur] < 4)) { ts = T_BE_DONE; break; }
-        }
-      } else {
-        int64_t ti = (int64_t)ik.x0 + (cur - (phase == PH_F ? sx : sx - bk));
-        while (budget-- > 0) {
-          ++blocks;
-          const bool ok = ti < n_text && sym(ti) == (int)q[cur];
-          if (phase == PH_F) {
-            if (!ok) { push_fwd(ik, cur); ts = T_F_DONE; break; }
-            ++cur; ++ti;
-            if (!(cur < len && q[cur] < 4)) { push_fwd(ik, cur); ts = T_F_DONE; break; }
-          } else {
-            if (!ok) { ts = T_FE_FAIL; break; }
-            ++cur; ++ti;
-            if (cur == stop) { ts = T_FE_REACHED; break; }
-          }
         }
       }
     }
@@ -405,17 +252,6 @@ __global__ void __launch_bounds__(128) smem_p3_kernel(const SmemArgs a)
         continue;
       }
       px = x; ik = set_intv(ix, q[x]); cur = x + 1;          // bwa/bwt.c:364-366
-      if (ix.kmer_tab && ix.kmer_k <= msl && x + ix.kmer_k <= len) {
-        // the first K-1 extensions cannot emit (cur - px < min_seed_len): take their result from the K-mer table
-        uint64_t code = 0; bool acgt = true;
-        for (int t = 0; t < ix.kmer_k; ++t) { const uint32_t b = q[x + t]; acgt &= b < 4; code = code << 2 | (b & 3); }
-        if (acgt) {
-          const uint4 e0 = __ldg(ix.kmer_tab + 2 * code), e1 = __ldg(ix.kmer_tab + 2 * code + 1);
-          ik.x0 = (uint64_t)e0.y << 32 | e0.x; ik.x1 = (uint64_t)e0.w << 32 | e0.z; ik.x2 = (uint64_t)e1.y << 32 | e1.x;
-          blocks += e1.z;
-          cur = x + ix.kmer_k;
-        }
-      }
       if (cur >= len) { x = len; continue; }
       if (q[cur] > 3) { x = cur + 1; continue; }
       c = 3 - q[cur]; pending = true;
@@ -443,39 +279,6 @@ __global__ void __launch_bounds__(128) smem_p3_kernel(const SmemArgs a)
   if (blocks) atomicAdd(a.blocks, blocks);
 }
 
-// bwt_sa, bwa/bwt.c:86-96 with bwt_invPsi :53-59 (symbol and its Occ come from the same occ32 block)
-// bwt_invPsi (bwa/bwt.c:53-59): the row of the suffix one position to the left; symbol and Occ come from the same occ32 block.
-__device__ __forceinline__ uint64_t inv_psi(const DevIndex &ix, uint64_t k)
-{
-  if (k == ix.primary) return 0;
-  const uint64_t x = k - (k > ix.primary);
-  const uint4 *b = ix.occ + ((x >> 6) << 1);
-  const uint4 hd = occ_ld(ix, b), sy = occ_ld(ix, b + 1);
-  const int r = (int)(x & 63);
-  const uint32_t word = (r >> 4) == 0 ? sy.x : (r >> 4) == 1 ? sy.y : (r >> 4) == 2 ? sy.z : sy.w;
-  const int c = (word >> ((~r & 15) << 1)) & 3;
-  int e, g;
-  prefix_counts(sy, r + 1, c, &e, &g);
-  const uint64_t *sb = ix.sbt + (x >> 31) * 5;
-  const uint32_t r0 = (uint32_t)(x & 0x7fffffffull) & ~63u;
-  const uint32_t lo_rel = c == 0 ? r0 : c == 1 ? hd.x : c == 2 ? hd.y : hd.z;
-  const uint32_t hi_rel = c == 0 ? hd.x : c == 1 ? hd.y : c == 2 ? hd.z : 0u;
-  return ix.L2[c] + (sb[c] + lo_rel) - (sb[c + 1] + hi_rel) + (uint64_t)e;
-}
-
-// bwt_sa (bwa/bwt.c:86-96) over the device-side sampling (every 2^sa_shift-th row; bwa_ctx_create may have made it denser than
-// bwa's 32, which does not change any value).  `blocks` counts the occ-block touches actually made.
-__device__ __forceinline__ uint64_t sa_lookup(const DevIndex &ix, uint64_t k, unsigned long long *blocks)
-{
-  uint64_t steps = 0;
-  const uint64_t mask = (1ull << ix.sa_shift) - 1;
-  while (k & mask) {
-    ++steps;
-    k = inv_psi(ix, k);
-  }
-  *blocks += steps;
-  return steps + ix.sa[k >> ix.sa_shift];
-}
 
 // One thread per row sampled by bwa (every 2^ref_shift-th): walks invPsi until the next sampled row, handing its value minus
 // the number of steps to every row it passes whose index is a multiple of 2^dense_shift.  The walks partition all rows.
@@ -493,31 +296,6 @@ __global__ void sa_densify_kernel(DevIndex ix, uint64_t n_sa, int dense_shift, u
     if ((r & ref_mask) == 0) break;
     if ((r & dmask) == 0) dense[r >> dense_shift] = v;
   }
-}
-
-// One thread per K-mer: the K-1 forward extensions bwt_seed_strategy1 (bwa/bwt.c:364-376) makes before it can emit anything
-// (no seed shorter than min_seed_len + 1 > K is ever emitted), so that pass 3 starts every seed from one table read.
-__global__ void kmer_table_kernel(DevIndex ix, int K, uint4 *tab)
-{
-  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >> (2 * K)) return;
-  unsigned long long blocks = 0;
-  Intv ik = set_intv(ix, (int)(v >> (2 * (K - 1))) & 3);
-  for (int i = 1; i < K; ++i) ik = extend1(ix, ik, 0, 3 - ((int)(v >> (2 * (K - 1 - i))) & 3), &blocks);
-  tab[2 * v] = make_uint4((uint32_t)ik.x0, (uint32_t)(ik.x0 >> 32), (uint32_t)ik.x1, (uint32_t)(ik.x1 >> 32));
-  tab[2 * v + 1] = make_uint4((uint32_t)ik.x2, (uint32_t)(ik.x2 >> 32), (uint32_t)blocks, 0u);
-}
-
-int build_kmer_table(bwaflow_ctx *c, int K, void **d_tab)
-{
-  const uint64_t n = 1ull << (2 * K);
-  BF_CUDA(cudaMalloc(d_tab, n * 32));
-  DevIndex ix = c->ix;
-  ix.occ_cs &= ~2;                                         // count block touches normally
-  kmer_table_kernel<<<(unsigned)((n + 127) / 128), 128>>>(ix, K, (uint4 *)*d_tab);
-  BF_CUDA(cudaGetLastError());
-  BF_CUDA(cudaDeviceSynchronize());
-  return 0;
 }
 
 int densify_sa(bwaflow_ctx *c, int dense_shift, uint64_t n_sa, void **d_dense)
@@ -575,7 +353,8 @@ __global__ void seedpos_kernel(DevIndex ix, const bwaflow_intv_t *intv, int64_t 
     while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
     const bwaflow_intv_t p = intv[lo];
     const uint64_t step = p.x[2] > (uint64_t)max_occ ? p.x[2] / max_occ : 1;
-    pos[t] = (int64_t)sa_lookup(ix, p.x[0] + (uint64_t)(t - off[lo]) * step, &nb);
+    pos[t] = p.x[1] == TEXT_MARK ? (int64_t)p.x[0]                    // text-anchored interval (smem_fast.cu): x[0] is the position
+                                 : (int64_t)sa_lookup(ix, p.x[0] + (uint64_t)(t - off[lo]) * step, &nb);
   }
   if (nb) atomicAdd(blocks, nb);
 }
@@ -606,20 +385,29 @@ int bwaflow::smem_launch(bwaflow_smem_batch *b)
   a.counts = b->d_counts; a.ctl = b->d_ctl; a.blocks = (unsigned long long *)(b->d_ctl + 4); a.ix = b->ctx->ix;
   a.min_seed_len = o.min_seed_len; a.split_len = (int)(o.min_seed_len * o.split_factor + .499);
   a.split_width = o.split_width; a.max_mem_intv = o.max_mem_intv;
-  int64_t want = (nr + 127) / 128;
-  const int grid = (int)(want < b->blocks_per_launch ? want : b->blocks_per_launch);
-  // dynamic shared memory: per lane one row for the read (<= 256 bases) and one for the forward-list end coordinates
-  // dynamic shared memory: per lane one row for the read (<= 256 bases) and one for the forward-list end coordinates
-  const int grid3 = (int)(want < (int64_t)b->ctx->n_sm * 10 ? want : (int64_t)b->ctx->n_sm * 10);   // 10 blocks per SM fit (48 registers, 21 KB)
-  if (b->max_len < 160) {
-    smem_kernel<160><<<grid, 128, 128 * (164 + SMEM_FEND), st>>>(a);
-    smem_p3_kernel<160><<<grid3, 128, 128 * 164, st>>>(a);
-  } else if (b->max_len < 256) {
-    smem_kernel<256><<<grid, 128, 128 * (260 + SMEM_FEND), st>>>(a);
-    smem_p3_kernel<256><<<grid3, 128, 128 * 260, st>>>(a);
+  a.packed = b->d_packed; a.x_min = b->x_min;
+  const bool count = b->count_blocks;
+  if (b->max_len < 256 && !getenv("BWAFLOW_SMEM_LEGACY")) {
+    // reads shorter than 256 bases: table / text-anchored kernels (smem_fast.cu).  Text anchoring needs the full suffix
+    // array and yields positions instead of rows, so the interval API (want_rows) and the counting runs go without it.
+    const bool text = !b->want_rows && !count && a.ix.text && a.ix.sa_shift == 0;
+    int r = smem_fast_launch(b, a, text, count);
+    if (r) return r;
   } else {
-    smem_kernel<1024><<<grid, 128, 0, st>>>(a);
-    smem_p3_kernel<1024><<<grid3, 128, 0, st>>>(a);
+    int64_t want = (nr + 127) / 128;
+    const int grid = (int)(want < b->blocks_per_launch ? want : b->blocks_per_launch);
+    const int grid3 = (int)(want < (int64_t)b->ctx->n_sm * 10 ? want : (int64_t)b->ctx->n_sm * 10);
+    // dynamic shared memory: per lane one row for the read (<= 256 bases) and one for the forward-list end coordinates
+    if (b->max_len < 160) {
+      smem_kernel<160><<<grid, 128, 128 * (164 + SMEM_FEND), st>>>(a);
+      smem_p3_kernel<160><<<grid3, 128, 128 * 164, st>>>(a);
+    } else if (b->max_len < 256) {
+      smem_kernel<256><<<grid, 128, 128 * (260 + SMEM_FEND), st>>>(a);
+      smem_p3_kernel<256><<<grid3, 128, 128 * 260, st>>>(a);
+    } else {
+      smem_kernel<1024><<<grid, 128, 0, st>>>(a);
+      smem_p3_kernel<1024><<<grid3, 128, 0, st>>>(a);
+    }
   }
   smem_compact_counts<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(b->d_counts, nr, b->cap, b->d_cnt64);
   size_t tmp = b->tmp_bytes;
@@ -715,7 +503,7 @@ int bwaflow_smem_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max
   BF_REQUIRE(max_reads > 0 && max_reads < (1LL << 31) - 1, -22, "max_reads out of range");
   BF_CUDA(cudaSetDevice(ctx->device));
   bwaflow_smem_batch *b = (bwaflow_smem_batch *)calloc(1, sizeof(*b));
-  b->ctx = ctx; b->max_reads = max_reads; b->max_bases = max_bases;
+  b->ctx = ctx; b->max_reads = max_reads; b->max_bases = max_bases; b->want_rows = true;
   BF_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   if (b->tm.init()) return -5;
   BF_CUDA(cudaMalloc(&b->d_bases, max_bases + 16));
@@ -746,6 +534,7 @@ int bwaflow_smem_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max
   if (per_sm > 8) per_sm = 8;
   if (const char *s = getenv("BWAFLOW_SMEM_BLOCKS_PER_SM")) per_sm = atoi(s) > 0 ? atoi(s) : per_sm;
   b->blocks_per_launch = per_sm * ctx->n_sm;
+  if ((r = smem_fast_setup(b))) return r;
   *out = b;
   return 0;
 }
@@ -758,7 +547,7 @@ void bwaflow_smem_batch_destroy(bwaflow_smem_batch_t *b)
   cudaFree(b->d_bases); cudaFree(b->d_read_off); cudaFree(b->d_counts); cudaFree(b->d_cnt64); cudaFree(b->d_off);
   cudaFreeHost(b->h_off); cudaFree(b->d_ctl); cudaFreeHost(b->h_ctl); cudaFree(b->d_slots); cudaFree(b->d_out);
   cudaFreeHost(b->h_out); cudaFree(b->d_tmp); cudaFree(b->d_pcnt); cudaFree(b->d_poff); cudaFreeHost(b->h_poff);
-  cudaFree(b->d_pos); cudaFreeHost(b->h_pos);
+  cudaFree(b->d_pos); cudaFreeHost(b->h_pos); cudaFree(b->d_packed);
   b->tm.destroy();
   cudaStreamDestroy(b->stream);
   free(b);
@@ -776,6 +565,7 @@ int bwaflow_smem_submit(bwaflow_smem_batch_t *b, int64_t n_reads, const uint8_t 
   for (int64_t i = 0; i < n_reads; ++i) { const int64_t l = read_off[i + 1] - read_off[i]; max_len = l > max_len ? l : max_len; }
   BF_REQUIRE(max_len < 1024, -34, "read of %lld bases: the seeding kernel supports reads shorter than 1024", (long long)max_len);
   b->n_reads = n_reads; b->max_len = max_len;
+  b->count_blocks = false;
   BF_CUDA(cudaEventRecord(b->tm.ev[0], b->stream));
   if (n_reads) {
     BF_CUDA(cudaMemcpyAsync(b->d_bases, bases, n_bases, cudaMemcpyHostToDevice, b->stream));
@@ -787,16 +577,27 @@ int bwaflow_smem_submit(bwaflow_smem_batch_t *b, int64_t n_reads, const uint8_t 
   return smem_queue_tail(b);
 }
 
-int bwaflow_smem_rerun(bwaflow_smem_batch_t *b)
+static int smem_rerun(bwaflow_smem_batch_t *b, bool counted)
 {
   BF_REQUIRE(b, -22, "bwaflow_smem_rerun: null batch");
   BF_CUDA(cudaSetDevice(b->ctx->device));
+  b->count_blocks = counted;
   BF_CUDA(cudaEventRecord(b->tm.ev[0], b->stream));
   BF_CUDA(cudaEventRecord(b->tm.ev[1], b->stream));
   int r = smem_launch(b);
   if (r) return r;
   return smem_queue_tail(b);
 }
+
+int bwaflow_smem_set_anchored(bwaflow_smem_batch_t *b, int on)
+{
+  BF_REQUIRE(b, -22, "bwaflow_smem_set_anchored: null batch");
+  b->want_rows = !on;
+  return 0;
+}
+
+int bwaflow_smem_rerun(bwaflow_smem_batch_t *b) { return smem_rerun(b, false); }
+int bwaflow_smem_rerun_counted(bwaflow_smem_batch_t *b) { return smem_rerun(b, true); }
 
 int bwaflow_smem_collect(bwaflow_smem_batch_t *b, const bwaflow_intv_t **intv, const int64_t **intv_off,
                          int64_t *n_intv, bwaflow_timing_t *t)

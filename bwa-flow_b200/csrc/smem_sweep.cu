@@ -1,0 +1,264 @@
+// Stage 2, the production seeding kernel: passes 1 and 2 of mem_collect_intv_new (src/bwa_wrapper.cpp:207-226) for reads
+// shorter than 256 bases, one read per lane.
+//
+// What bwt_smem1a_new (src/bwa_wrapper.cpp:325-450) computes.  Its forward sweep from x records the ends e_0 < e_1 < .. at which
+// the interval of q[x, e) changes size.  Its backward loop then visits these forward matches shortest first and, for
+// each, finds how far the match extends to the left with an interval of at least min_intv rows -- either by extending
+// it base by base ("back-enlarge", :371-386) or by re-extending the saved leftward trail of an earlier match to the right
+// ("forward-enlarge", :403-417, which tries the trail entries longest first and takes the first that survives).  Interval
+// sizes only shrink when a pattern grows on either side, so both routes return the same thing: the leftmost begin b with
+// |I(q[b, e_i))| >= min_intv (not crossing an N or the read start), together with the interval of q[b, e_i) -- which is a
+// property of the pattern, not of the route.  Which route the reference takes (its `stop - start >= 3` rule) changes its
+// cost, never its output.  The candidate/emit logic (:392-400, :418-427, :431-443) consumes only (b, e_i, interval).
+//
+// This kernel computes exactly that function per forward match, by the cheapest exact means:
+//   T  patterns of at most K bases: one 16-byte read of the level tables (ctx.cu; intervals of all 1..K-mers);
+//   X  longer, non-unique patterns: bwt_extend on the occ32 index (fmindex.cuh);
+//   A  unique intervals with min_intv == 1 (template TEXT, needs the full suffix array): anchored in the 2-bit text, extended
+//      by comparing up to 32 bases per step; emitted as {text position, TEXT_MARK, 1} (the hot path needs only positions).
+// A short forward match [x, e) starts from the table entry of the K bases ending at e (its begin cannot lie to the left of the
+// previous match's begin, another consequence of monotonicity, so the window is clipped there) and is extended to the left on the
+// index; if that window is already too rare, the begin is found by walking the table levels down.  A long forward match
+// starts from its own stored interval.  Per forward match this is ~1 table read and 2-3 index steps instead of the
+// reference's ~15-30 bwt_extend calls; the reference's call count is still what the roofline is stated in, and is
+// produced by the exact step-by-step instances (smem_fast.cu, COUNT) which replay the reference's route.
+#include <string.h>
+#include <stdlib.h>
+#include "internal.cuh"
+#include "batches.cuh"
+#include "fmindex.cuh"
+#include "smem_args.cuh"
+#include "smem_rows.cuh"
+
+namespace bwaflow {
+
+enum { SK_T = 0, SK_X = 1, SK_A = 2 };
+enum { SM_F = 0, SM_W = 1, SM_S = 2, SM_B = 3 };          // forward sweep | window lookup | level walk | leftward extension
+enum { S_NONE = 0, S_FETCH, S_NEXT, S_ENTRY, S_ENTRY_DONE, S_CALL_DONE, S_FINISH, S_EXIT };
+
+#ifndef SWEEP_MIN_BLOCKS
+#define SWEEP_MIN_BLOCKS 6
+#endif
+
+template <int MAXL, bool TEXT>
+__global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const SmemArgs a)
+{
+  using R = Row<MAXL>;
+  extern __shared__ uint64_t s_rows[];
+  LaneRead<MAXL> q;
+  q.bind(s_rows + (size_t)threadIdx.x * (R::ROW_BYTES / 8));
+  uint8_t *fend = (uint8_t *)q.q2 + R::PACK_BYTES;           // ends of the forward matches (first 64; later ones are stored entries)
+  uint4 fwd_l[MAXL];                                         // intervals of forward matches longer than K
+  const DevIndex &ix = a.ix;
+  const unsigned full = 0xffffffffu;
+  const int msl = a.min_seed_len, K = ix.ktab ? ix.ktab_k : 0;
+
+  int ts = S_FETCH, kind = SK_T, mode = SM_F;
+  int64_t r = -1; bwaflow_intv_t *mem = nullptr; int n_mem = 0;
+  int pass = 1, x = 0, k2 = 0, old_n = 0;
+  int sx = 0, mi = 1, nb = 0, fwd_n = 0, fwd_ns = 0, fi = 0, f_end = 0, lb = 0, sL = 0;
+  int pb = 0, pe = 0;
+  Intv ik = {0, 0, 0}, cand = {0, 0, 0}; int cand_beg = 0, cand_end = 0;
+
+  auto tab = [&](int b, int L) -> Intv { int d; return unpack_entry(__ldg(ix.ktab + ktab_base(L) + q.code(b, L)), &d); };
+  auto get_end = [&](int k) -> int { return k < 64 ? (int)fend[k] : entry_pos(fwd_l[k - fwd_ns]); };
+  auto push_fwd = [&](const Intv &v, int end) {
+    if (fwd_n < 64) fend[fwd_n] = (uint8_t)end;
+    if (end - sx > K) fwd_l[fwd_n - fwd_ns] = pack_entry(v, end); else ++fwd_ns;
+    ++fwd_n;
+  };
+  auto push_mem = [&](const Intv &v, int beg, int end) {
+    if (n_mem < a.cap) {
+      bwaflow_intv_t o; o.x[0] = v.x0; o.x[1] = v.x1; o.x[2] = v.x2; o.info = (uint64_t)(uint32_t)beg << 32 | (uint32_t)end;
+      mem[n_mem] = o;
+    }
+    ++n_mem;
+  };
+  // kind of the next step for the pattern [pb, pe) growing by one base
+  auto set_kind = [&]() { kind = (TEXT && is_text(ik)) ? SK_A : (pe - pb + 1 <= K ? SK_T : SK_X); ts = S_NONE; };
+
+  for (;;) {
+    while (ts != S_NONE && ts != S_EXIT) {
+      switch (ts) {
+      case S_FETCH: {
+        r = (int64_t)atomicAdd(a.ctl, 1);
+        if (r >= a.n_reads) { ts = S_EXIT; break; }
+        const int len = (int)(a.read_off[r + 1] - a.read_off[r]);
+        mem = a.slots + r * a.cap; n_mem = 0; pass = 1; x = 0;
+        if (len >= MAXL) { atomicExch(a.ctl + 2, 1); a.counts[r] = 0; break; }
+        q.load(a.packed, r, len);
+        ts = len < msl ? S_FINISH : S_NEXT;                  // src/bwa_wrapper.cpp:150
+        break;
+      }
+      case S_NEXT: {                                         // the call loops of mem_collect_intv_new (:214-226)
+        bool call = false;
+        if (pass == 1) {
+          while (x < q.len && q.isN(x)) ++x;
+          if (x < q.len) { sx = x; mi = 1; call = true; }
+          else { pass = 2; old_n = n_mem < a.cap ? n_mem : a.cap; k2 = 0; }
+        }
+        if (pass == 2 && !call) {
+          while (k2 < old_n) {
+            const bwaflow_intv_t p = mem[k2++];
+            const int s = (int)(p.info >> 32), e = (int)(uint32_t)p.info;
+            if (e - s < a.split_len || p.x[2] > (uint64_t)a.split_width) continue;
+            if (q.isN((s + e) >> 1)) continue;               // bwt_smem1a_new :338
+            sx = (s + e) >> 1; mi = (int)p.x[2] + 1; call = true;
+            break;
+          }
+          if (!call) pass = 3;
+        }
+        if (call) {                                          // forward sweep from sx (:338-363)
+          fwd_n = 0; fwd_ns = 0; ik = set_intv(ix, q.base(sx)); pb = sx; pe = sx + 1; mode = SM_F;
+          nb = q.prev_n(sx) + 1;
+          if (pe < q.len && !q.isN(pe)) set_kind();
+          else { push_fwd(ik, pe); fi = 0; lb = nb; ts = S_ENTRY; }
+          break;
+        }
+        ts = S_FINISH;                                       // pass 3 has its own kernel
+        break;
+      }
+      case S_ENTRY: {                                        // forward match fi = q[sx, f_end): how far does it reach to the left?
+        if (fi >= fwd_n) { ts = S_CALL_DONE; break; }
+        f_end = get_end(fi); pe = f_end;
+        if (f_end - sx > K) {                                // from its own interval
+          int d;
+          ik = unpack_entry(fwd_l[fi - fwd_ns], &d); pb = sx; mode = SM_B;
+          if (pb > lb) set_kind(); else ts = S_ENTRY_DONE;
+        } else {                                             // from the table entry of the (at most K) bases ending at f_end
+          sL = min(K, f_end - lb); mode = SM_W; kind = SK_T; ts = S_NONE;
+        }
+        break;
+      }
+      case S_ENTRY_DONE: {                                   // candidate logic (:392-400, :418-427) and the skip rule (:431-443)
+        if (fi > 0 && pb > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+        cand = ik; cand_beg = pb; cand_end = f_end; lb = pb;
+        ++fi;
+        if (fi < fwd_n) {
+          int stop = 0, max_len = cand_beg + get_end(fi);
+          while (max_len < msl && fi < fwd_n) {
+            ++fi;
+            if (fi < fwd_n) stop = get_end(fi);
+            max_len = cand_beg + stop;
+          }
+        }
+        if (fi >= fwd_n && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+        ts = S_ENTRY;
+        break;
+      }
+      case S_CALL_DONE:
+        if (pass == 1) x = get_end(fwd_n - 1);
+        ts = S_NEXT;
+        break;
+      case S_FINISH:
+        a.counts[r] = n_mem;
+        if (n_mem > a.cap) atomicExch(a.ctl + 1, 1);
+        ts = S_FETCH;
+        break;
+      }
+    }
+    if (__ballot_sync(full, ts == S_NONE) == 0) break;
+    Intv o = {0, 0, 0}; bool have = false;
+    // ---- T: one table read
+    if (ts == S_NONE && kind == SK_T) {
+      if (mode == SM_F) o = tab(pb, pe - pb + 1);
+      else if (mode == SM_B) o = tab(pb - 1, pe - pb + 1);
+      else o = tab(pe - sL, sL);                             // window / level walk: the sL bases ending at pe
+      have = true;
+    }
+    // ---- X: bwt_extend on the index once enough lanes want one
+    const unsigned wx = __ballot_sync(full, ts == S_NONE && kind == SK_X);
+    const unsigned wo = __ballot_sync(full, ts == S_NONE && kind != SK_X);
+    if (wx && (__popc(wx) >= a.x_min || !wo)) {
+      if (ts == S_NONE && kind == SK_X) {
+        unsigned long long nbk = 0;
+        const int c = mode == SM_B ? q.base(pb - 1) : 3 - q.base(pe);
+        o = extend1(ix, ik, mode == SM_B, c, &nbk);
+        have = true;
+      }
+    }
+    if (have) {
+      const bool small = o.x2 < (uint64_t)mi;
+      if (TEXT && mi == 1 && o.x2 == 1) o = text_intv(ix.sa[o.x0]);       // unique from here on: anchor it in the text
+      if (mode == SM_F) {                                    // :350-363
+        const bool changed = o.x2 != ik.x2;
+        if (changed) push_fwd(ik, pe);
+        if (changed && small) { fi = 0; lb = nb; ts = S_ENTRY; }
+        else {
+          ik = o; ++pe;
+          if (pe < q.len && !q.isN(pe)) set_kind(); else { push_fwd(ik, pe); fi = 0; lb = nb; ts = S_ENTRY; }
+        }
+      } else if (mode == SM_B) {                             // one more base on the left (:374-386)
+        if (small) ts = S_ENTRY_DONE;
+        else {
+          ik = o; --pb;
+          if (pb > lb) set_kind(); else ts = S_ENTRY_DONE;
+        }
+      } else {                                               // SM_W / SM_S: is the window q[pe - sL, pe) frequent enough?
+        if (!small || sL == pe - sx) {                       // (the forward match itself is taken as it is, :371)
+          ik = o; pb = pe - sL;
+          if (mode == SM_W && pb > lb) { mode = SM_B; set_kind(); } else ts = S_ENTRY_DONE;
+        } else { --sL; mode = SM_S; }                        // walk the levels down: everything longer is too rare
+      }
+    }
+    // ---- A: anchored interval: compare up to 32 bases of the read with the text
+    if (TEXT && ts == S_NONE && kind == SK_A) {
+      if (mode == SM_B) {
+        int cap = pb - lb;                                   // read bases available on the left (>= 1)
+        if ((uint64_t)cap > ik.x0) cap = (int)ik.x0;         // ... and text symbols
+        const int want = min(cap, 32);
+        int n = 0;
+        if (want > 0) {
+          const uint64_t diff = q.win_end(pb) ^ text_win_end(ix.text, ik.x0);
+          n = min(diff ? (__ffsll((long long)diff) - 1) >> 1 : 32, want);
+        }
+        pb -= n; ik.x0 -= (uint64_t)n;
+        if (!(n == 32 && cap > 32)) ts = S_ENTRY_DONE;
+      } else {                                               // forward sweep on a unique interval: runs to the first mismatch
+        const int lim = q.next_n(pe);
+        const int want = lim - pe;
+        const uint64_t tp = ik.x0 + (uint64_t)(pe - pb);
+        const int64_t tcap = (int64_t)ix.seq_len - (int64_t)tp;
+        const int w = (int)min((int64_t)min(want, 32), max(tcap, (int64_t)0));
+        int n = 0;
+        if (w > 0) {
+          const uint64_t diff = q.win(pe) ^ text_win(ix.text, tp);
+          n = min(diff ? __clzll((long long)diff) >> 1 : 32, w);
+        }
+        pe += n;
+        if (!(n == 32 && want > 32 && tcap > 32)) { push_fwd(ik, pe); fi = 0; lb = nb; ts = S_ENTRY; }
+      }
+    }
+  }
+}
+
+template <int MAXL>
+static int sweep_launch_t(const SmemArgs &a, int grid, bool text, cudaStream_t st)
+{
+  const size_t sh = 128 * (size_t)Row<MAXL>::ROW_BYTES;
+  if (text) smem_sweep_kernel<MAXL, true><<<grid, 128, sh, st>>>(a);
+  else smem_sweep_kernel<MAXL, false><<<grid, 128, sh, st>>>(a);
+  BF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// passes 1-2 for a batch of packed reads shorter than 256 bases (pack and pass 3 are launched by smem_fast_launch)
+int smem_sweep_launch(bwaflow_smem_batch *b, const SmemArgs &a, bool text)
+{
+  const int64_t want = (b->n_reads + 127) / 128;
+  const int64_t cap = (int64_t)b->ctx->n_sm * b->sweep_blocks_per_sm;
+  const int grid = (int)(want < cap ? want : cap);
+  return b->max_len < 160 ? sweep_launch_t<160>(a, grid, text, b->stream) : sweep_launch_t<256>(a, grid, text, b->stream);
+}
+
+int smem_sweep_setup(bwaflow_smem_batch *b)
+{
+  int per_sm = 0;
+  BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smem_sweep_kernel<160, true>, 128, 128 * Row<160>::ROW_BYTES));
+  if (per_sm < 1) per_sm = 1;
+  if (const char *s = getenv("BWAFLOW_SWEEP_BLOCKS_PER_SM")) per_sm = atoi(s) > 0 ? atoi(s) : per_sm;
+  b->sweep_blocks_per_sm = per_sm;
+  return 0;
+}
+
+} // namespace bwaflow

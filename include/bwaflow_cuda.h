@@ -154,6 +154,15 @@ int bwaflow_smem_submit(bwaflow_smem_batch_t *b, int64_t n_reads, const uint8_t 
 int bwaflow_smem_collect(bwaflow_smem_batch_t *b, const bwaflow_intv_t **intv, const int64_t **intv_off,
                          int64_t *n_intv, bwaflow_timing_t *timing);
 int bwaflow_smem_rerun(bwaflow_smem_batch_t *b);
+/* on != 0: an interval that is unique (x[2] == 1) may be returned "anchored" as x[0] = its position in the forward +
+ * reverse-complement text (what bwt_sa(x[0]) would give), x[1] = BWAFLOW_ANCHORED, x[2] = 1 -- the form the fused hot
+ * path uses internally: such intervals are extended by comparing bases against the 2-bit text and their seed
+ * position needs no suffix-array read.  bwaflow_smem_seed_positions understands both forms.  Default off (BWT rows). */
+#define BWAFLOW_ANCHORED ((1ull << 39) - 1)
+int bwaflow_smem_set_anchored(bwaflow_smem_batch_t *b, int on);
+/* same on the kernel instances that also count the 64-byte occ-block touches the reference makes for these reads (bwt_2occ4,
+ * bwa/bwt.c:189-220: one block if both interval ends share it, else two); reported as timing.work_units.  Same intervals. */
+int bwaflow_smem_rerun_counted(bwaflow_smem_batch_t *b);
 
 /* Seed positions for chaining (replaces the bwt_sa loop of mem_chain_postprocess, src/bwa_wrapper.cpp:281-291):
  * for the intervals of the last collect, pos[] holds bwt_sa(x[0]+k) for k = 0, step, 2*step.. (count < max_occ)
@@ -200,7 +209,7 @@ void bwaflow_hot_batch_destroy(bwaflow_hot_batch_t *b);
 int bwaflow_hot_submit(bwaflow_hot_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off);
 int bwaflow_hot_rerun(bwaflow_hot_batch_t *b);        /* reads of the last submit, already resident */
 int bwaflow_hot_exact_reads(bwaflow_hot_batch_t *b, int64_t *n_exact);   /* as bwaflow_c2a_exact_reads, after bwaflow_hot_collect */
-int bwaflow_hot_rerun_counted(bwaflow_hot_batch_t *b); /* same, stage 4 as in bwaflow_c2a_rerun_counted (fills timing.cells) */
+int bwaflow_hot_rerun_counted(bwaflow_hot_batch_t *b); /* same on the counting instances of stage 2 (timing.smem_blocks) and stage 4 (timing.cells, as bwaflow_c2a_rerun_counted) */
 int bwaflow_hot_collect(bwaflow_hot_batch_t *b, const bwaflow_alnreg_t **regs, const int64_t **reg_off, int64_t *n_regs,
                         bwaflow_hot_timing_t *timing);
 

@@ -111,6 +111,7 @@ def orc_lib():
         L.orc_bwt_sa.argtypes = [C.POINTER(IndexView), C.c_uint64]
         L.orc_bwt_extend.argtypes = [C.POINTER(IndexView), C.c_void_p, C.c_int, C.c_void_p]
         L.orc_collect_intv.argtypes = [C.POINTER(IndexView), C.POINTER(OrcOpt), C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_collect_intv_leftmost.argtypes = L.orc_collect_intv.argtypes
         L.orc_ksw_extend2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]
         L.orc_chains2aln.argtypes = [C.POINTER(IndexView), C.POINTER(OrcOpt), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -347,6 +348,14 @@ class Oracle:
         nt4 = np.ascontiguousarray(nt4, dtype=np.uint8)
         out = np.zeros(4096, dtype=INTV)
         n = self.L.orc_collect_intv(C.byref(self.view), C.byref(self.opt), _p(nt4), len(nt4), _p(out), len(out))
+        assert n <= len(out)
+        return out[:n].copy()
+
+    def collect_intv_leftmost(self, nt4):
+        """passes 1-2 stated as "leftmost begin per forward match" (the formulation of smem_sweep.cu)"""
+        nt4 = np.ascontiguousarray(nt4, dtype=np.uint8)
+        out = np.zeros(4096, dtype=INTV)
+        n = self.L.orc_collect_intv_leftmost(C.byref(self.view), C.byref(self.opt), _p(nt4), len(nt4), _p(out), len(out))
         assert n <= len(out)
         return out[:n].copy()
 

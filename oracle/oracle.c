@@ -278,6 +278,94 @@ int orc_collect_intv(const orc_index_t *ix, const orc_opt_t *opt, const uint8_t 
   return n;
 }
 
+/* The same search stated as a function (what bwa-flow_b200/csrc/smem_sweep.cu computes; kept here so that the equivalence
+ * is pinned on the CPU, tests/test_oracle_golden.py): both routes of the backward loop above ("back-enlarge" and
+ * "forward-enlarge") return, for the forward match q[x, e), the leftmost begin b whose interval still has min_intv rows
+ * (not crossing an N or the read start), because interval sizes only shrink as a pattern grows.  So the backward loop is:
+ * for every visited forward match, extend it leftwards as far as it goes, then run the candidate / skip rules. */
+static int smem_leftmost(const orc_index_t *ix, int len, const uint8_t *q, int x, int min_intv, int min_seed_len, ivec_t *mem)
+{
+  if (q[x] > 3) return x + 1;
+  if (min_intv < 1) min_intv = 1;
+  ivec_t fwd = {0, 0, 0};
+  orc_intv_t ik, ok[4], cand;
+  int i, ret, lb = 0;
+  memset(&cand, 0, sizeof(cand));
+  set_intv(ix, q[x], &ik); ik.info = (uint64_t)(x + 1);
+  for (i = x + 1; i < len; ++i) {
+    if (q[i] > 3) { ipush(&fwd, &ik); break; }
+    int c = 3 - q[i];
+    extend(ix, &ik, ok, 0);
+    if (ok[c].x[2] != ik.x[2]) {
+      ipush(&fwd, &ik);
+      if (ok[c].x[2] < (uint64_t)min_intv) break;
+    }
+    ik = ok[c]; ik.info = (uint64_t)(i + 1);
+  }
+  if (i == len) ipush(&fwd, &ik);
+  ret = INFO_END(fwd.a[fwd.n - 1]);
+  for (lb = x; lb > 0 && q[lb - 1] < 4; --lb) {}              /* leftmost begin any match through x can have */
+  i = 0;
+  while (i < fwd.n) {
+    int beg = x;
+    ik = fwd.a[i];
+    while (beg > lb) {                                       /* begins never move left from one forward match to the next */
+      extend(ix, &ik, ok, 1);
+      if (ok[q[beg - 1]].x[2] < (uint64_t)min_intv) break;
+      ik = ok[q[beg - 1]]; --beg;
+    }
+    ik.info = (uint64_t)beg << 32 | (uint32_t)INFO_END(fwd.a[i]);
+    if (i > 0 && beg > INFO_BEG(cand) && INFO_END(cand) - INFO_BEG(cand) >= min_seed_len) ipush(mem, &cand);
+    cand = ik; lb = beg;
+    ++i;
+    if (i < fwd.n) {
+      int stop = 0, max_len = INFO_BEG(cand) + INFO_END(fwd.a[i]);
+      while (max_len < min_seed_len && i < fwd.n) {
+        ++i;
+        if (i < fwd.n) stop = INFO_END(fwd.a[i]);
+        max_len = INFO_BEG(cand) + stop;
+      }
+    }
+    if (i >= fwd.n && INFO_END(cand) - INFO_BEG(cand) >= min_seed_len) ipush(mem, &cand);
+  }
+  free(fwd.a);
+  return ret;
+}
+
+/* passes 1 and 2 of mem_collect_intv_new through smem_leftmost, pass 3 and the sort as in orc_collect_intv */
+static int seed_strategy1(const orc_index_t *ix, int len, const uint8_t *q, int x, int min_len, int max_intv, orc_intv_t *out);
+static int intv_cmp(const void *a, const void *b);
+int orc_collect_intv_leftmost(const orc_index_t *ix, const orc_opt_t *opt, const uint8_t *seq, int len, orc_intv_t *out, int cap)
+{
+  ivec_t mem = {0, 0, 0};
+  if (len < opt->min_seed_len) return 0;
+  int split_len = (int)(opt->min_seed_len * opt->split_factor + .499);
+  int x = 0;
+  while (x < len) x = seq[x] < 4 ? smem_leftmost(ix, len, seq, x, 1, opt->min_seed_len, &mem) : x + 1;
+  int old_n = mem.n;
+  for (int k = 0; k < old_n; ++k) {
+    int s = INFO_BEG(mem.a[k]), e = INFO_END(mem.a[k]);
+    uint64_t occ = mem.a[k].x[2];
+    if (e - s < split_len || occ > (uint64_t)opt->split_width) continue;
+    smem_leftmost(ix, len, seq, (s + e) >> 1, (int)occ + 1, opt->min_seed_len, &mem);
+  }
+  if (opt->max_mem_intv > 0) {
+    x = 0;
+    while (x < len) {
+      if (seq[x] < 4) {
+        orc_intv_t m;
+        x = seed_strategy1(ix, len, seq, x, opt->min_seed_len, opt->max_mem_intv, &m);
+        if (m.x[2] > 0) ipush(&mem, &m);
+      } else ++x;
+    }
+  }
+  qsort(mem.a, mem.n, sizeof(orc_intv_t), intv_cmp);
+  int n = mem.n;
+  for (int i = 0; i < n && i < cap; ++i) out[i] = mem.a[i];
+  free(mem.a);
+  return n;
+}
+
 /* --------------------------------------------------------- banded extension */
 
 /* bwa/ksw.c:380-479.  out = {score, qle, tle, gtle, gscore, max_off}.  Adds executed cells to the counter. */

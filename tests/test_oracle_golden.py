@@ -91,3 +91,44 @@ def test_extend_and_edge_cases(index_c1):
             t[:n] = np.where(q[:n] < 4, q[:n], 0)
         args = (6, 1, 6, 1, int(rng.choice([1, 5, 100, 200])), int(rng.choice([0, 5])), int(rng.choice([0, 10, 100])), int(rng.integers(1, 120)))
         assert list(api.orc_ksw_extend2(q, t, mat, *args)) == list(api.ref_ksw_extend2(q, t, mat, *args))
+
+
+@pytest.mark.parametrize("case", ["index_c1", "index_c5"])
+def test_leftmost_begin_formulation(case, request):
+    """The seeding kernel (smem_sweep.cu) does not replay the reference's back-enlarge / forward-enlarge routes: it computes,
+    per forward match, the leftmost begin whose interval keeps min_intv rows.  The CPU twin of that formulation gives the
+    golden intervals on the golden reads and agrees with the route-by-route restatement on adversarial reads (N runs,
+    homopolymers, tandem repeats, exact reference substrings of both strands, mutated copies of the repeat family)."""
+    ix = request.getfixturevalue(case)
+    g = request.getfixturevalue(case.replace("index", "golden"))
+    O = api.Oracle.from_ref(ix.ref)
+    nt4 = ix.reads.nt4()
+    off = ix.reads.offsets
+    for i in range(ix.reads.n):
+        exp = g["intv"][g["intv_off"][i]:g["intv_off"][i + 1]]
+        assert O.collect_intv_leftmost(nt4[off[i]:off[i + 1]]).tobytes() == exp.tobytes(), i
+    rng = np.random.default_rng(17)
+    codes = g["ref_codes"]
+    L = len(codes)
+    for t in range(300):
+        n = int(rng.integers(19, 250))
+        p = int(rng.integers(0, L - n))
+        s = codes[p:p + n].copy()
+        s[s > 3] = 4
+        if rng.random() < 0.5:
+            s = np.where(s < 4, 3 - s, 4)[::-1].astype(np.uint8)
+        k = t % 6
+        if k == 1:
+            s[rng.random(n) < 0.08] = 4
+        elif k == 2:
+            m = rng.random(n) < 0.04
+            s[m] = (s[m] + 1) % 4
+        elif k == 3:
+            s[n // 3:n // 3 + 30] = int(rng.integers(0, 4))
+        elif k == 4:
+            unit = rng.integers(0, 4, int(rng.integers(2, 7)), dtype=np.uint8)
+            s[n // 2:] = np.resize(unit, n - n // 2)
+        elif k == 5:
+            s[:n // 2] = s[n - n // 2:][::-1]
+        s = np.ascontiguousarray(s, dtype=np.uint8)
+        assert O.collect_intv_leftmost(s).tobytes() == O.collect_intv(s).tobytes(), (t, k)

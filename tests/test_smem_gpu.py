@@ -15,11 +15,38 @@ def _ctx(ix, **opt_over):
     return capi.Context(0, index, opt, keepalive=keep)
 
 
-@pytest.fixture(params=["14", "12", "5", "0"])
+@pytest.fixture(params=["13", "default", "5", "0"])
 def kmer_k(request, monkeypatch):
-    """Pass 3 starts every seed from a K-mer table entry (default K = 12); 0 = step by step as bwt_seed_strategy1 does."""
-    monkeypatch.setenv("BWAFLOW_KMER_K", request.param)
+    """Depth K of the level tables (intervals of all 1..K-mers, smem_fast.cu): deeper than the index warrants (most
+    K-mers absent or unique), the default for the index size, shallow, and 0 = every step on the index."""
+    if request.param != "default":
+        monkeypatch.setenv("BWAFLOW_KMER_K", request.param)
     return request.param
+
+
+def _oracle_blocks(ix, nt4, off, n):
+    """occ-block touches of mem_collect_intv_new for reads [0, n) as the oracle restatement counts them."""
+    from oracle import api
+    O = api.Oracle.from_ref(ix.ref)
+    O.reset()
+    for i in range(n):
+        O.collect_intv(nt4[off[i]:off[i + 1]])
+    return O.blocks()
+
+
+def _same_modulo_anchoring(ix, got, exp):
+    """Anchored form: same info and size; a unique interval may carry bwt_sa(x0) and the ANCHORED marker instead of rows."""
+    from bwaflow_b200 import capi
+    assert len(got) == len(exp)
+    assert (got["info"] == exp["info"]).all() and (got["x2"] == exp["x2"]).all()
+    anch = got["x1"] == capi.ANCHORED
+    assert (got["x2"][anch] == 1).all()
+    plain = ~anch
+    assert (got["x0"][plain] == exp["x0"][plain]).all() and (got["x1"][plain] == exp["x1"][plain]).all()
+    idx = np.nonzero(anch)[0]
+    for i in idx[:: max(1, len(idx) // 400)]:
+        assert int(got["x0"][i]) == ix.ref.bwt_sa(int(exp["x0"][i])), i
+    return int(anch.sum())
 
 
 @pytest.mark.parametrize("case", ["c1", "c5"])
@@ -34,7 +61,6 @@ def test_smem_matches_golden(case, request, kmer_k):
     intv, off, t = b.collect()
     assert (off == g["intv_off"]).all(), np.nonzero(off != g["intv_off"])[0][:5]
     assert intv.tobytes() == g["intv"].tobytes()
-    assert t.work_units > 0
     # seed positions = bwt_sa over each interval exactly as mem_chain_postprocess samples them
     pos, poff, _ = b.seed_positions()
     max_occ = ctx.opt.max_occ
@@ -48,6 +74,21 @@ def test_smem_matches_golden(case, request, kmer_k):
     b.rerun()
     intv2, off2, _ = b.collect()
     assert intv2.tobytes() == g["intv"].tobytes() and (off2 == off).all()
+    # the counting instances: same intervals, and the algorithmic work unit of the seeding roofline (64-byte occ-block
+    # touches of the reference) equal to the oracle's count
+    b.rerun(counted=True)
+    intv3, off3, t3 = b.collect()
+    assert intv3.tobytes() == g["intv"].tobytes() and (off3 == off).all()
+    assert int(t3.work_units) == _oracle_blocks(ix, nt4, ix.reads.offsets, ix.reads.n)
+    # the hot path's internal form: unique intervals anchored in the text (positions instead of rows)
+    b.set_anchored(True)
+    b.rerun()
+    intv4, off4, _ = b.collect()
+    assert (off4 == off).all()
+    n_anch = _same_modulo_anchoring(ix, intv4, g["intv"])
+    assert n_anch > 0
+    pos4, poff4, _ = b.seed_positions()
+    assert (poff4 == poff).all() and (pos4 == pos).all()
     b.close()
     ctx.close()
 
@@ -97,10 +138,23 @@ def test_smem_edge_reads(index_c1, kmer_k):
     b = capi.SmemBatch(ctx, len(reads), len(bases))
     b.submit(bases, off)
     intv, ioff, _ = b.collect()
+    O.reset()
+    exp_all = []
     for i, r in enumerate(reads):
         exp = O.collect_intv(r)
+        exp_all.append(exp)
         got = intv[ioff[i]:ioff[i + 1]]
         assert got.tobytes() == exp.tobytes(), (i, len(r), got, exp)
+    exp_blocks = O.blocks()
+    b.rerun(counted=True)
+    intv2, ioff2, t2 = b.collect()
+    assert intv2.tobytes() == intv.tobytes() and (ioff2 == ioff).all()
+    assert int(t2.work_units) == exp_blocks
+    b.set_anchored(True)
+    b.rerun()
+    intv3, ioff3, _ = b.collect()
+    assert (ioff3 == ioff).all()
+    _same_modulo_anchoring(ix, intv3, np.concatenate(exp_all))
     b.close()
     ctx.close()
 
