@@ -33,7 +33,7 @@
 namespace bwaflow {
 
 enum { SK_T = 0, SK_X = 1, SK_A = 2 };
-enum { SM_F = 0, SM_W = 1, SM_S = 2, SM_B = 3 };          // forward sweep | window lookup | level walk | leftward extension
+enum { SM_F = 0, SM_W = 1, SM_S = 2, SM_B = 3, SM_C = 4, SM_CF = 5 };   // forward sweep | window lookup | level walk | leftward extension | continue the previous anchored match | (that failed)
 enum { S_NONE = 0, S_FETCH, S_NEXT, S_ENTRY, S_ENTRY_DONE, S_CALL_DONE, S_FINISH, S_EXIT };
 
 #ifndef SWEEP_MIN_BLOCKS
@@ -78,7 +78,42 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
   auto set_kind = [&]() { kind = (TEXT && is_text(ik)) ? SK_A : (pe - pb + 1 <= K ? SK_T : SK_X); ts = S_NONE; };
 
   for (;;) {
-    while (ts != S_NONE && ts != S_EXIT) {
+    // ---- the entry boundary (every ~4 steps of a lane): one straight-line block so that the lanes at a boundary run it together
+    while (ts == S_ENTRY || ts == S_ENTRY_DONE) {
+      if (ts == S_ENTRY_DONE) {                              // candidate logic (:392-400, :418-427) and the skip rule (:431-443)
+        if (fi > 0 && pb > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+        cand = ik; cand_beg = pb; cand_end = f_end; lb = pb;
+        ++fi;
+        if (fi < fwd_n) {
+          int stop = 0, max_len = cand_beg + get_end(fi);
+          while (max_len < msl && fi < fwd_n) {
+            ++fi;
+            if (fi < fwd_n) stop = get_end(fi);
+            max_len = cand_beg + stop;
+          }
+        }
+        if (fi >= fwd_n && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+      }
+      // forward match fi = q[sx, f_end): how far does it reach to the left?
+      if (fi >= fwd_n) { ts = S_CALL_DONE; break; }
+      f_end = get_end(fi);
+      if (TEXT && fi > 0 && mode != SM_CF && is_text(cand) && f_end - cand_end <= 32) {
+        // the previous match is one occurrence in the text and begins can only move right: if the read keeps matching the
+        // text up to f_end, this match is the same occurrence with the same begin
+        ik = cand; pb = cand_beg; pe = cand_end; mode = SM_C; kind = SK_A; ts = S_NONE;
+        break;
+      }
+      pe = f_end;
+      if (f_end - sx > K) {                                  // from its own interval
+        int d;
+        ik = unpack_entry(fwd_l[fi - fwd_ns], &d); pb = sx; mode = SM_B;
+        if (pb > lb) set_kind(); else ts = S_ENTRY_DONE;
+      } else {                                               // from the table entry of the (at most K) bases ending at f_end
+        sL = min(K, f_end - lb); mode = SM_W; kind = SK_T; ts = S_NONE;
+      }
+    }
+    // ---- everything else (once per call / per read)
+    while (ts != S_NONE && ts != S_EXIT && ts != S_ENTRY) {
       switch (ts) {
       case S_FETCH: {
         r = (int64_t)atomicAdd(a.ctl, 1);
@@ -118,34 +153,6 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
         ts = S_FINISH;                                       // pass 3 has its own kernel
         break;
       }
-      case S_ENTRY: {                                        // forward match fi = q[sx, f_end): how far does it reach to the left?
-        if (fi >= fwd_n) { ts = S_CALL_DONE; break; }
-        f_end = get_end(fi); pe = f_end;
-        if (f_end - sx > K) {                                // from its own interval
-          int d;
-          ik = unpack_entry(fwd_l[fi - fwd_ns], &d); pb = sx; mode = SM_B;
-          if (pb > lb) set_kind(); else ts = S_ENTRY_DONE;
-        } else {                                             // from the table entry of the (at most K) bases ending at f_end
-          sL = min(K, f_end - lb); mode = SM_W; kind = SK_T; ts = S_NONE;
-        }
-        break;
-      }
-      case S_ENTRY_DONE: {                                   // candidate logic (:392-400, :418-427) and the skip rule (:431-443)
-        if (fi > 0 && pb > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
-        cand = ik; cand_beg = pb; cand_end = f_end; lb = pb;
-        ++fi;
-        if (fi < fwd_n) {
-          int stop = 0, max_len = cand_beg + get_end(fi);
-          while (max_len < msl && fi < fwd_n) {
-            ++fi;
-            if (fi < fwd_n) stop = get_end(fi);
-            max_len = cand_beg + stop;
-          }
-        }
-        if (fi >= fwd_n && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
-        ts = S_ENTRY;
-        break;
-      }
       case S_CALL_DONE:
         if (pass == 1) x = get_end(fwd_n - 1);
         ts = S_NEXT;
@@ -157,7 +164,8 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
         break;
       }
     }
-    if (__ballot_sync(full, ts == S_NONE) == 0) break;
+    __syncwarp();                                            // lanes leave the transition loop at different times: rejoin them here
+    if (__ballot_sync(full, ts != S_EXIT) == 0) break;
     Intv o = {0, 0, 0}; bool have = false;
     // ---- T: one table read
     if (ts == S_NONE && kind == SK_T) {
@@ -214,6 +222,13 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
         }
         pb -= n; ik.x0 -= (uint64_t)n;
         if (!(n == 32 && cap > 32)) ts = S_ENTRY_DONE;
+      } else if (mode == SM_C) {                             // does the previous occurrence also cover [cand_end, f_end)?
+        const int want = f_end - pe;
+        const uint64_t tp = ik.x0 + (uint64_t)(pe - pb);
+        const uint64_t diff = q.win(pe) ^ text_win(ix.text, tp);
+        const int n = diff ? __clzll((long long)diff) >> 1 : 32;
+        if (n >= want && tp + (uint64_t)want <= ix.seq_len) { pe = f_end; ts = S_ENTRY_DONE; }
+        else { mode = SM_CF; ts = S_ENTRY; }
       } else {                                               // forward sweep on a unique interval: runs to the first mismatch
         const int lim = q.next_n(pe);
         const int want = lim - pe;
