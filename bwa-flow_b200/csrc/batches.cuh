@@ -15,7 +15,8 @@ struct bwaflow_smem_batch {
   bwaflow_intv_t *d_slots; int cap; int64_t slots_cap;
   int *d_counts; int64_t *d_cnt64, *d_off, *h_off;
   bwaflow_intv_t *d_out, *h_out; int64_t out_cap;
-  int *d_ctl, *h_ctl;               // head | overflow | too-long | pad | blocks(u64)
+  int *d_ctl, *h_ctl;               // head | slot overflow | too-long | pass-3 head | blocks(u64) | capacity flags | pad
+  int64_t *h_stat;                  // {n_intv, n_pos} of the last device-driven run (hot path)
   void *d_tmp; size_t tmp_bytes;
   int64_t n_intv;
   // seed positions
@@ -77,6 +78,9 @@ int smem_sweep_setup(bwaflow_smem_batch *b);
 int build_level_tables(bwaflow_ctx *c, int K, void **d_tab);
 // smem.cu: device-side halves of submit/collect (no interval D2H); used by the fused hot path
 int smem_launch(bwaflow_smem_batch *b);
+int smem_tail_device(bwaflow_smem_batch *b);                   // hot path: compact + seed positions, no host read-back
+int smem_status_d2h(bwaflow_smem_batch *b);
+int smem_check_capacity(bwaflow_smem_batch *b, bool *redo, int64_t *n_pos);
 int smem_finish_device(bwaflow_smem_batch *b);                 // waits, regrows slots on overflow, compacts into d_out/d_off; sets n_intv
 int smem_seedpos_device(bwaflow_smem_batch *b, int64_t *total); // d_pos/d_poff for the current intervals
 // chain2aln.cu

@@ -19,6 +19,7 @@ using namespace chain;
 struct ChainArgs {
   int64_t n_reads; const int64_t *read_off;
   const bwaflow_intv_t *intv; const int64_t *intv_off; const int64_t *pos; const int64_t *pos_off;
+  int64_t out_cap, pos_cap;          // capacities of intv / pos: a read beyond them is left to the redo (smem.cu, device-driven tail)
   // per-read scratch, carved by the read's first position index
   SeedNode *seeds; Chain *chains; Chain *sorted; int *order; int *kept; Node *nodes;
   int64_t *n_chains, *n_seeds; float *frac_rep; int *err;
@@ -41,8 +42,9 @@ __global__ void __launch_bounds__(128) chain_kernel(const ChainArgs a)
   if (r >= a.n_reads) return;
   const int len = (int)(a.read_off[r + 1] - a.read_off[r]);
   if (len >= a.opt.min_seed_len && needs_seed_rescoring(a.opt, len)) { atomicExch(a.err, 1); a.n_chains[r] = 0; a.n_seeds[r] = 0; return; }
-  Scratch S = read_scratch(a, r);
   const int64_t i0 = a.intv_off[r], i1 = a.intv_off[r + 1];
+  if (i1 > a.out_cap || a.pos_off[i1] > a.pos_cap) { a.n_chains[r] = 0; a.n_seeds[r] = 0; return; }
+  Scratch S = read_scratch(a, r);
   float fr;
   const int n = chain_read(S, a.opt, a.ctg, len, a.intv + i0, i1 - i0, a.pos, a.pos_off + i0, &fr);
   int ns = 0;
@@ -80,7 +82,7 @@ struct bwaflow_hot_batch {
   bwaflow_smem_batch *s;
   bwaflow_c2a_batch *c;
   cudaStream_t stream;
-  cudaEvent_t ev[6];
+  cudaEvent_t ev[7];
   int64_t max_reads, max_bases;
   // chaining scratch
   int64_t scr_entries, scr_nodes;
@@ -91,7 +93,8 @@ struct bwaflow_hot_batch {
   bwaflow_chain_opt_t copt;
   int64_t n_intv, n_pos, n_chains, n_seeds;
   float ms_smem, ms_seedpos, ms_chain, ms_c2a, ms_h2d;
-  bool count_cells, new_input;
+  bool count_cells, new_input, front_queued;
+  bwaflow::ChainArgs cargs;
   double blocks_smem, blocks_pos;
   bool pending;
 };
@@ -133,34 +136,28 @@ static int hot_make_c2a(bwaflow_hot_batch *b, int64_t max_chains, int64_t max_se
   return 0;
 }
 
-static int hot_run(bwaflow_hot_batch *b)
+// Front half, nothing but enqueues: stage 2 (seeding, compaction, seed positions) and chaining on the batch's stream, every
+// kernel bounded by the batch's capacities and sized from device-side counts, then the read-back of the batch's status words.
+static int hot_enqueue_front(bwaflow_hot_batch *b)
 {
   bwaflow_smem_batch *s = b->s;
   cudaStream_t st = b->stream;
   const int64_t nr = s->n_reads;
   int r;
-  // ---- stage 2
   BF_CUDA(cudaEventRecord(b->ev[1], st));
   s->want_rows = false; s->count_blocks = b->count_cells;   // rows are not needed downstream: text-anchored seeds carry positions
   if ((r = smem_launch(s))) return r;
-  BF_CUDA(cudaMemcpyAsync(s->h_off, s->d_off, (nr + 1) * 8, cudaMemcpyDeviceToHost, st));
-  BF_CUDA(cudaMemcpyAsync(s->h_ctl, s->d_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  s->pending = true;
-  if ((r = smem_finish_device(s))) return r;
-  b->blocks_smem = (double)*(unsigned long long *)(s->h_ctl + 4);
   BF_CUDA(cudaEventRecord(b->ev[2], st));
-  int64_t n_pos = 0;
-  if ((r = smem_seedpos_device(s, &n_pos))) return r;
-  b->n_intv = s->n_intv; b->n_pos = n_pos;
-  BF_CUDA(cudaMemcpyAsync(b->h_tot + 2, s->d_ctl + 4, 8, cudaMemcpyDeviceToHost, st));   // occ blocks touched by the SA walks
+  if ((r = smem_tail_device(s))) return r;
   BF_CUDA(cudaEventRecord(b->ev[3], st));
   // ---- chaining
-  if ((r = hot_grow_scratch(b, n_pos + nr + 8, n_pos / 4 + 4 * nr + 8))) return r;
   ChainArgs a;
   a.n_reads = nr; a.read_off = s->d_read_off; a.intv = s->d_out; a.intv_off = s->d_off; a.pos = s->d_pos; a.pos_off = s->d_poff;
+  a.out_cap = s->out_cap; a.pos_cap = s->pos_cap;
   a.seeds = b->d_seeds; a.chains = b->d_chains; a.sorted = b->d_sorted; a.order = b->d_order; a.kept = b->d_kept; a.nodes = b->d_nodes;
   a.n_chains = b->d_nch; a.n_seeds = b->d_nsd; a.frac_rep = b->d_frac; a.err = b->d_err; a.opt = b->copt;
   a.ctg = chain::Ctg{b->ctx->ix.n_seqs, b->ctx->ix.ctg_offset, b->ctx->ix.ctg_len, b->d_ctg_alt, b->ctx->ix.l_pac};
+  b->cargs = a;
   BF_CUDA(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
   BF_CUDA(cudaMemsetAsync(b->d_choff, 0, (nr + 1) * 8, st));
   BF_CUDA(cudaMemsetAsync(b->d_sdoff, 0, (nr + 1) * 8, st));
@@ -174,22 +171,49 @@ static int hot_run(bwaflow_hot_batch *b)
     tmp = b->tmp_bytes;
     BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_nsd, b->d_sdoff, (int)(nr + 1), st));
   }
+  BF_CUDA(cudaEventRecord(b->ev[4], st));
   BF_CUDA(cudaMemcpyAsync(b->h_tot, b->d_choff + nr, 8, cudaMemcpyDeviceToHost, st));
   BF_CUDA(cudaMemcpyAsync(b->h_tot + 1, b->d_sdoff + nr, 8, cudaMemcpyDeviceToHost, st));
   BF_CUDA(cudaMemcpyAsync(b->h_err, b->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-  BF_CUDA(cudaStreamSynchronize(st));
+  if ((r = smem_status_d2h(s))) return r;
+  b->front_queued = true;
+  return 0;
+}
+
+// Back half: the one host wait of a batch (status words of the front half), a redo of the front half if a capacity was overrun
+// (first batches only: capacities keep their high-water marks), then stage 4 on the resident chains.
+static int hot_finish(bwaflow_hot_batch *b)
+{
+  bwaflow_smem_batch *s = b->s;
+  cudaStream_t st = b->stream;
+  const int64_t nr = s->n_reads;
+  int r;
+  for (int round = 0;; ++round) {
+    BF_CUDA(cudaStreamSynchronize(st));
+    bool redo = false; int64_t n_pos = 0;
+    if ((r = smem_check_capacity(s, &redo, &n_pos))) return r;
+    if (!redo) {
+      b->n_intv = s->n_intv; b->n_pos = n_pos;
+      if (n_pos + nr + 8 > b->scr_entries) { if ((r = hot_grow_scratch(b, n_pos + nr + 8, n_pos / 4 + 4 * nr + 8))) return r; redo = true; }
+    } else if ((r = hot_grow_scratch(b, s->pos_cap + nr + 8, s->pos_cap / 4 + 4 * nr + 8))) return r;
+    if (!redo) break;
+    BF_REQUIRE(round < 8, -5, "hot path: capacities did not settle");
+    if ((r = hot_enqueue_front(b))) return r;
+  }
+  b->front_queued = false;
+  b->blocks_smem = (double)*(unsigned long long *)(s->h_ctl + 4);
   BF_REQUIRE(!*b->h_err, -34, "read too long for chaining: mem_flt_chained_seeds (bwa/bwamem.c:607) would rescore its seeds");
   const int64_t n_chains = b->h_tot[0], n_seeds = b->h_tot[1];
   b->n_chains = n_chains; b->n_seeds = n_seeds;
   if (!b->c || n_chains > b->c->max_chains || n_seeds > b->c->max_seeds)
     if ((r = hot_make_c2a(b, n_chains + n_chains / 4 + 1024, n_seeds + n_seeds / 4 + 1024))) return r;
   bwaflow_c2a_batch *c = b->c;
+  BF_CUDA(cudaEventRecord(b->ev[6], st));
   if (nr) {
     const unsigned grid = (unsigned)((nr + 127) / 128);
-    chain_emit_kernel<<<grid, 128, 0, st>>>(a, b->d_choff, b->d_sdoff, c->d_chains, c->d_seeds);
+    chain_emit_kernel<<<grid, 128, 0, st>>>(b->cargs, b->d_choff, b->d_sdoff, c->d_chains, c->d_seeds);
     BF_CUDA(cudaMemcpyAsync(c->d_chain_off, b->d_choff, (nr + 1) * 8, cudaMemcpyDeviceToDevice, st));
   }
-  BF_CUDA(cudaEventRecord(b->ev[4], st));
   // ---- stage 4 on the resident chains
   c->n_reads = nr; c->n_chains = n_chains; c->n_seeds = n_seeds;
   BF_CUDA(cudaEventRecord(c->tm.ev[0], st));
@@ -199,7 +223,6 @@ static int hot_run(bwaflow_hot_batch *b)
   if ((r = c2a_launch(c))) return r;
   if ((r = c2a_finish_queue(c))) return r;
   BF_CUDA(cudaEventRecord(b->ev[5], st));
-  b->pending = true;
   return 0;
 }
 
@@ -213,10 +236,12 @@ int bwaflow_hot_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_
   bwaflow_hot_batch *b = (bwaflow_hot_batch *)calloc(1, sizeof(*b));
   b->ctx = ctx; b->max_reads = max_reads; b->max_bases = max_bases;
   if (copt) b->copt = *copt; else bwaflow_chain_opt_default(&b->copt);
+  // the fields mem_opt_t holds once (bwa/bwamem.h:26-58) come from the context, so the two option structs cannot disagree
+  b->copt.min_seed_len = ctx->par.opt.min_seed_len; b->copt.max_occ = ctx->par.opt.max_occ; b->copt.w = ctx->par.opt.w;
   int r = bwaflow_smem_batch_create(ctx, max_reads, max_bases, &b->s);
   if (r) return r;
   b->stream = b->s->stream;
-  for (int i = 0; i < 6; ++i) BF_CUDA(cudaEventCreate(&b->ev[i]));
+  for (int i = 0; i < 7; ++i) BF_CUDA(cudaEventCreate(&b->ev[i]));
   BF_CUDA(cudaMalloc(&b->d_nch, (max_reads + 2) * 8));
   BF_CUDA(cudaMalloc(&b->d_nsd, (max_reads + 2) * 8));
   BF_CUDA(cudaMalloc(&b->d_choff, (max_reads + 2) * 8));
@@ -232,6 +257,7 @@ int bwaflow_hot_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_
     BF_CUDA(cudaMalloc(&b->d_ctg_alt, ctx->ix.n_seqs * 4));
     BF_CUDA(cudaMemcpy(b->d_ctg_alt, ctg_is_alt, ctx->ix.n_seqs * 4, cudaMemcpyHostToDevice));
   }
+  if ((r = hot_grow_scratch(b, b->s->pos_cap + max_reads + 8, b->s->pos_cap / 4 + 4 * max_reads + 8))) return r;
   if ((r = hot_make_c2a(b, 4 * max_reads + 1024, 12 * max_reads + 1024))) return r;
   *out = b;
   return 0;
@@ -247,7 +273,7 @@ void bwaflow_hot_batch_destroy(bwaflow_hot_batch_t *b)
   cudaFree(b->d_seeds); cudaFree(b->d_chains); cudaFree(b->d_sorted); cudaFree(b->d_order); cudaFree(b->d_kept); cudaFree(b->d_nodes);
   cudaFree(b->d_nch); cudaFree(b->d_nsd); cudaFree(b->d_choff); cudaFree(b->d_sdoff); cudaFree(b->d_frac); cudaFree(b->d_err);
   cudaFreeHost(b->h_tot); cudaFreeHost(b->h_err); cudaFree(b->d_tmp); cudaFree(b->d_ctg_alt);
-  for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
+  for (int i = 0; i < 7; ++i) cudaEventDestroy(b->ev[i]);
   free(b);
 }
 
@@ -269,7 +295,8 @@ int bwaflow_hot_submit(bwaflow_hot_batch_t *b, int64_t n_reads, const uint8_t *b
     BF_CUDA(cudaMemcpyAsync(s->d_read_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, b->stream));
   }
   b->count_cells = false; b->new_input = true;
-  return hot_run(b);
+  b->pending = true;
+  return hot_enqueue_front(b);
 }
 
 static int hot_rerun(bwaflow_hot_batch_t *b, bool counted)
@@ -278,7 +305,8 @@ static int hot_rerun(bwaflow_hot_batch_t *b, bool counted)
   BF_CUDA(cudaSetDevice(b->ctx->device));
   BF_CUDA(cudaEventRecord(b->ev[0], b->stream));
   b->count_cells = counted;
-  return hot_run(b);
+  b->pending = true;
+  return hot_enqueue_front(b);
 }
 
 int bwaflow_hot_exact_reads(bwaflow_hot_batch_t *b, int64_t *n_exact)
@@ -295,7 +323,10 @@ int bwaflow_hot_collect(bwaflow_hot_batch_t *b, const bwaflow_alnreg_t **regs, c
 {
   BF_REQUIRE(b && b->pending, -22, "bwaflow_hot_collect: nothing submitted");
   bwaflow_timing_t ct;
-  int r = bwaflow_c2a_collect(b->c, regs, reg_off, n_regs, &ct);
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  int r = hot_finish(b);
+  if (r) { b->pending = false; return r; }
+  r = bwaflow_c2a_collect(b->c, regs, reg_off, n_regs, &ct);
   b->pending = false;
   if (r) return r;
   if (t) {
@@ -304,7 +335,7 @@ int bwaflow_hot_collect(bwaflow_hot_batch_t *b, const bwaflow_alnreg_t **regs, c
     cudaEventElapsedTime(&t->smem_ms, b->ev[1], b->ev[2]);
     cudaEventElapsedTime(&t->seedpos_ms, b->ev[2], b->ev[3]);
     cudaEventElapsedTime(&t->chain_ms, b->ev[3], b->ev[4]);
-    cudaEventElapsedTime(&t->c2a_ms, b->ev[4], b->ev[5]);
+    cudaEventElapsedTime(&t->c2a_ms, b->ev[6], b->ev[5]);     // from the host's go-ahead (the batch's one wait) to the last stage-4 kernel
     t->d2h_ms = ct.d2h_ms;
     cudaEventElapsedTime(&t->total_ms, b->ev[0], b->c->tm.ev[3]);
     t->smem_blocks = b->blocks_smem;

@@ -359,6 +359,46 @@ __global__ void seedpos_kernel(DevIndex ix, const bwaflow_intv_t *intv, int64_t 
   if (nb) atomicAdd(blocks, nb);
 }
 
+// ---- device-driven tail for the fused hot path: nothing is read back between the stages.  Every kernel is bounded by the batch's
+// capacities, takes its item count from device memory, and reports an overrun in ctl[6] (bit 0: intervals, bit 1: positions);
+// the host looks at the flags once per batch (hotpath.cu) and only then grows the buffers and redoes the batch.
+__global__ void smem_compact_dev(const bwaflow_intv_t *slots, int cap, const int64_t *off, int64_t n_reads, bwaflow_intv_t *out,
+                                 int64_t out_cap, int *flags)
+{
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_reads) return;
+  const int64_t lo = off[r], n = off[r + 1] - lo;
+  if (lo + n > out_cap) { if (lane == 0 && n) atomicOr(flags, 1); return; }
+  const uint4 *src = (const uint4 *)(slots + r * cap);
+  uint4 *dst = (uint4 *)(out + lo);
+  for (int64_t t = lane; t < 2 * n; t += 32) dst[t] = src[t];
+}
+
+__global__ void seedpos_counts_dev(const bwaflow_intv_t *intv, const int64_t *n_ptr, int64_t out_cap, int max_occ, int64_t *out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > out_cap) return;
+  const int64_t n = *n_ptr < out_cap ? *n_ptr : out_cap;
+  out[i] = i < n ? (intv[i].x[2] < (uint64_t)max_occ ? (int64_t)intv[i].x[2] : max_occ) : 0;
+}
+
+__global__ void seedpos_dev_kernel(DevIndex ix, const bwaflow_intv_t *intv, const int64_t *n_ptr, int64_t out_cap, const int64_t *off,
+                                   int64_t pos_cap, int max_occ, int64_t *pos, int *flags)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_intv = *n_ptr < out_cap ? *n_ptr : out_cap;
+  int64_t total = off[n_intv];
+  if (total > pos_cap) { if (t == 0) atomicOr(flags, 2); total = pos_cap; }
+  if (t >= total) return;
+  int64_t lo = 0, hi = n_intv;                         // last interval with off[iv] <= t
+  while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
+  const bwaflow_intv_t p = intv[lo];
+  const uint64_t step = p.x[2] > (uint64_t)max_occ ? p.x[2] / max_occ : 1;
+  unsigned long long nb = 0;
+  pos[t] = p.x[1] == TEXT_MARK ? (int64_t)p.x[0] : (int64_t)sa_lookup(ix, p.x[0] + (uint64_t)(t - off[lo]) * step, &nb);
+}
+
 } // namespace bwaflow
 
 using namespace bwaflow;
@@ -369,6 +409,21 @@ static int smem_alloc_slots(bwaflow_smem_batch *b, int cap)
   if (b->d_slots) cudaFree(b->d_slots);
   b->cap = cap; b->slots_cap = b->max_reads * cap;
   BF_CUDA(cudaMalloc(&b->d_slots, b->slots_cap * sizeof(bwaflow_intv_t)));
+  return 0;
+}
+
+static int smem_grow_out(bwaflow_smem_batch *b, int64_t total)
+{
+  cudaFree(b->d_out); cudaFreeHost(b->h_out); cudaFree(b->d_pcnt); cudaFree(b->d_poff); cudaFreeHost(b->h_poff); cudaFree(b->d_tmp);
+  b->out_cap = total + total / 4;
+  BF_CUDA(cudaMalloc(&b->d_out, b->out_cap * sizeof(bwaflow_intv_t)));
+  BF_CUDA(cudaMallocHost(&b->h_out, b->out_cap * sizeof(bwaflow_intv_t)));
+  BF_CUDA(cudaMalloc(&b->d_pcnt, (b->out_cap + 2) * 8));
+  BF_CUDA(cudaMalloc(&b->d_poff, (b->out_cap + 2) * 8));
+  BF_CUDA(cudaMallocHost(&b->h_poff, (b->out_cap + 2) * 8));
+  BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b->tmp_bytes, b->d_cnt64, b->d_off, (int)(b->out_cap + 1), b->stream));
+  b->tmp_bytes += 256;
+  BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
   return 0;
 }
 
@@ -443,22 +498,67 @@ int bwaflow::smem_finish_device(bwaflow_smem_batch *b)
   b->pending = false;
   BF_REQUIRE(!b->h_ctl[2], -34, "a read is too long for the seeding kernel instance chosen for this batch");
   const int64_t total = b->n_reads ? b->h_off[b->n_reads] : 0;
-  if (total > b->out_cap) {
-    cudaFree(b->d_out); cudaFreeHost(b->h_out); cudaFree(b->d_pcnt); cudaFree(b->d_poff); cudaFreeHost(b->h_poff); cudaFree(b->d_tmp);
-    b->out_cap = total + total / 4;
-    BF_CUDA(cudaMalloc(&b->d_out, b->out_cap * sizeof(bwaflow_intv_t)));
-    BF_CUDA(cudaMallocHost(&b->h_out, b->out_cap * sizeof(bwaflow_intv_t)));
-    BF_CUDA(cudaMalloc(&b->d_pcnt, (b->out_cap + 2) * 8));
-    BF_CUDA(cudaMalloc(&b->d_poff, (b->out_cap + 2) * 8));
-    BF_CUDA(cudaMallocHost(&b->h_poff, (b->out_cap + 2) * 8));
-    BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b->tmp_bytes, b->d_cnt64, b->d_off, (int)(b->out_cap + 1), b->stream));
-    b->tmp_bytes += 256;
-    BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
-  }
+  if (total > b->out_cap) { int r = smem_grow_out(b, total); if (r) return r; }
   if (total)
     smem_compact<<<(unsigned)((b->n_reads * 32 + 255) / 256), 256, 0, b->stream>>>(b->d_slots, b->cap, b->d_off, b->n_reads, b->d_out);
   BF_CUDA(cudaGetLastError());
   b->n_intv = total;
+  return 0;
+}
+
+// Hot path, all asynchronous: compacted intervals, seed-position offsets and positions for the batch on its stream.
+int bwaflow::smem_tail_device(bwaflow_smem_batch *b)
+{
+  cudaStream_t st = b->stream;
+  const int64_t nr = b->n_reads;
+  const int max_occ = b->ctx->par.opt.max_occ;
+  if (nr == 0) { BF_CUDA(cudaMemsetAsync(b->d_poff, 0, 16, st)); return 0; }
+  smem_compact_dev<<<(unsigned)((nr * 32 + 255) / 256), 256, 0, st>>>(b->d_slots, b->cap, b->d_off, nr, b->d_out, b->out_cap, b->d_ctl + 6);
+  seedpos_counts_dev<<<(unsigned)((b->out_cap + 1 + 255) / 256), 256, 0, st>>>(b->d_out, b->d_off + nr, b->out_cap, max_occ, b->d_pcnt);
+  size_t tmp = b->tmp_bytes;
+  BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_pcnt, b->d_poff, (int)(b->out_cap + 1), st));
+  seedpos_dev_kernel<<<(unsigned)((b->pos_cap + 127) / 128), 128, 0, st>>>(b->ctx->ix, b->d_out, b->d_off + nr, b->out_cap, b->d_poff, b->pos_cap,
+                                                                         max_occ, b->d_pos, b->d_ctl + 6);
+  BF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// queues the read-back of the batch's status words: h_stat = {n_intv, n_pos}, h_ctl = the control block
+int bwaflow::smem_status_d2h(bwaflow_smem_batch *b)
+{
+  cudaStream_t st = b->stream;
+  BF_CUDA(cudaMemcpyAsync(b->h_stat, b->d_off + b->n_reads, 8, cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaMemcpyAsync(b->h_stat + 1, b->d_poff + b->out_cap, 8, cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaMemcpyAsync(b->h_ctl, b->d_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+// After the stream has been synchronised: did the batch fit?  Grows what overflowed (slots x4, interval / position arrays to 1.25x
+// the true counts) and sets *redo when the batch has to be run again; otherwise leaves n_intv set and *n_pos.
+int bwaflow::smem_check_capacity(bwaflow_smem_batch *b, bool *redo, int64_t *n_pos)
+{
+  *redo = false;
+  BF_REQUIRE(!b->h_ctl[2], -34, "a read is too long for the seeding kernel instance chosen for this batch");
+  if (b->n_reads == 0) { b->n_intv = 0; *n_pos = 0; return 0; }
+  if (b->h_ctl[1]) {                         // some read filled its slot
+    BF_REQUIRE(b->cap < 4096, -34, "a read produced more than 4096 intervals");
+    int r = smem_alloc_slots(b, b->cap * 4);
+    if (r) return r;
+    *redo = true;
+  }
+  const int64_t total = b->h_stat[0];
+  if (total > b->out_cap) {
+    int r = smem_grow_out(b, total);
+    if (r) return r;
+    *redo = true;
+  }
+  if (!*redo && ((b->h_ctl[6] & 2) || b->h_stat[1] > b->pos_cap)) {
+    cudaFree(b->d_pos);
+    b->pos_cap = b->h_stat[1] + b->h_stat[1] / 4 + 1024;
+    BF_CUDA(cudaMalloc(&b->d_pos, b->pos_cap * 8));
+    *redo = true;
+  }
+  b->n_intv = total; *n_pos = b->h_stat[1];
   return 0;
 }
 
@@ -525,7 +625,9 @@ int bwaflow_smem_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max
   BF_CUDA(cudaMalloc(&b->d_pcnt, (b->out_cap + 2) * 8));
   BF_CUDA(cudaMalloc(&b->d_poff, (b->out_cap + 2) * 8));
   BF_CUDA(cudaMallocHost(&b->h_poff, (b->out_cap + 2) * 8));
-  b->pos_cap = 0; b->d_pos = 0; b->h_pos = 0;
+  b->pos_cap = max_reads * 12 + 1024; b->h_pos = 0;     // grown to 1.25x the need when a batch overruns it
+  BF_CUDA(cudaMalloc(&b->d_pos, b->pos_cap * 8));
+  BF_CUDA(cudaMallocHost(&b->h_stat, 4 * 8));
   int per_sm = 0;
   BF_CUDA(cudaFuncSetAttribute(smem_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (164 + SMEM_FEND)));
   BF_CUDA(cudaFuncSetAttribute(smem_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (260 + SMEM_FEND)));
@@ -547,7 +649,7 @@ void bwaflow_smem_batch_destroy(bwaflow_smem_batch_t *b)
   cudaFree(b->d_bases); cudaFree(b->d_read_off); cudaFree(b->d_counts); cudaFree(b->d_cnt64); cudaFree(b->d_off);
   cudaFreeHost(b->h_off); cudaFree(b->d_ctl); cudaFreeHost(b->h_ctl); cudaFree(b->d_slots); cudaFree(b->d_out);
   cudaFreeHost(b->h_out); cudaFree(b->d_tmp); cudaFree(b->d_pcnt); cudaFree(b->d_poff); cudaFreeHost(b->h_poff);
-  cudaFree(b->d_pos); cudaFreeHost(b->h_pos); cudaFree(b->d_packed);
+  cudaFree(b->d_pos); cudaFreeHost(b->h_pos); cudaFree(b->d_packed); cudaFreeHost(b->h_stat);
   b->tm.destroy();
   cudaStreamDestroy(b->stream);
   free(b);
