@@ -118,3 +118,83 @@ def test_fused_hot_path_repeat_rich(tmp_path):
     B.close()
     rb.free()
     R.close()
+
+
+def _against_compiled_reference(tmp_path, ref, reads, n_threads=8):
+    """Fused hot path vs the compiled reference (oracle/_ref: mem_seq2chain_wrapper + mem_chain2aln) on a workload built
+    here; returns (timing, reads redone on the exact stage-4 kernel, ksw_extend2 job table of the reference)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from bwaflow_b200 import capi, stages
+    from oracle import api
+    fa = str(tmp_path / "r.fa")
+    ref.write_fasta(fa)
+    api.build_index(fa, str(tmp_path / "r"))
+    R = api.Ref(str(tmp_path / "r"))
+    cuts = np.linspace(0, reads.n, n_threads + 1).astype(np.int64) & ~1
+
+    def part(i):
+        R.hook_begin()
+        rb = R.batch(reads.slice(int(cuts[i]), int(cuts[i + 1])), int(cuts[i]))
+        rb.seq2chains()
+        rb.chains2regions()
+        jobs = R.hook_end()[0]
+        out = rb.regions()
+        rb.free()
+        return out, jobs
+    with ThreadPoolExecutor(n_threads) as ex:
+        parts = list(ex.map(part, range(n_threads)))
+    regs = np.concatenate([p[0][0] for p in parts])
+    n_per = np.concatenate([np.diff(p[0][1]) for p in parts])
+    jobs = np.concatenate([p[1] for p in parts])
+    B = capi.BuiltIndex(ref.concat(), ref.lengths)
+    ctx = capi.Context(0, B.index(), keepalive=B)
+    nt4 = reads.nt4()
+    fp = stages.FusedHotPath(ctx, reads.n, len(nt4))
+    out = fp.run(stages.seqs_record(0, nt4, reads.offsets))
+    assert (np.diff(out["alnreg_off"]) == n_per).all()
+    assert out["alnreg"].tobytes() == regs.tobytes()
+    t, n_exact = fp.last, fp.batch.exact_reads()
+    fp.close()
+    ctx.close()
+    B.close()
+    R.close()
+    return t, n_exact, jobs
+
+
+def test_fused_hot_path_c5_shape_6k_reads(tmp_path):
+    """BASELINE config[4] shape at a size where the hard paths are populated: 3 000 indel-heavy 2x250 bp pairs (chimeric reads,
+    long indels) plus 400 reads crafted so that a flank extension crosses an 80-95 bp deletion (max_off >= 75: mem_chain2aln's
+    second band try with w = 200, bwa/bwamem.c:742,770) -- reads that leave the speculative stage-4 path."""
+    from bwaflow_b200 import synth
+    ref = synth.make_reference(3_000_000, n_contigs=3, seed=55, repeat_copies=60, repeat_len=600)
+    reads = synth.simulate_pairs_indel(ref, 3000, 250, 0.05, seed=5)
+    extra = synth.simulate_pairs(ref, 200, 250, 0.0, seed=6, first_id=3000)
+    rng = np.random.default_rng(8)
+    whole = ref.concat()
+    asc = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for i in range(extra.n):
+        k, a = int(rng.integers(80, 96)), int(rng.integers(105, 125))
+        p = int(rng.integers(0, len(whole) // 3 - 600))
+        seq = np.concatenate([whole[p:p + a], whole[p + a + k:p + a + k + 250 - a]])
+        if i & 1:
+            seq = (3 - seq)[::-1]
+        extra.bases[extra.offsets[i]:extra.offsets[i + 1]] = asc[seq & 3]
+    both = synth.ReadBatch(reads.names + extra.names, np.concatenate([reads.bases, extra.bases]),
+                           np.concatenate([reads.quals, extra.quals]),
+                           np.concatenate([reads.offsets, extra.offsets[1:] + reads.offsets[-1]]))
+    t, n_exact, jobs = _against_compiled_reference(tmp_path, ref, both)
+    second_try = int((jobs["w"] > 100).sum())
+    print("c5 shape: %d reads, %d chains; %d ksw_extend2 calls, %d second band tries (max_off up to %d); %d reads on the exact kernel"
+          % (both.n, t.n_chains, len(jobs), second_try, int(jobs["max_off"].max()), n_exact))
+    assert second_try > 100 and n_exact > 100
+
+
+def test_fused_hot_path_repeat_rich_c1_shape(tmp_path):
+    """BASELINE config[0] shape on a reference with a diverged repeat family and N runs (the i.i.d. reference alone
+    leaves max_occ sampling, pass-2 re-seeding and the containment skip between chains idle): 20 000 2x150 bp reads."""
+    from bwaflow_b200 import synth
+    ref = synth.make_reference(5_000_000, n_contigs=4, seed=5, n_run_frac=0.001, repeat_copies=800, repeat_len=500, repeat_div=0.03)
+    reads = synth.simulate_pairs(ref, 10000, 150, 0.01, seed=1, n_rate=0.0005)
+    t, n_exact, jobs = _against_compiled_reference(tmp_path, ref, reads)
+    print("repeat-rich c1 shape: %d reads, %d chains, %d seeds; %d reads on the exact kernel" % (reads.n, t.n_chains, t.n_seeds, n_exact))
+    assert t.n_chains > reads.n

@@ -79,7 +79,7 @@ def test_smem_matches_golden(case, request, kmer_k):
     b.rerun(counted=True)
     intv3, off3, t3 = b.collect()
     assert intv3.tobytes() == g["intv"].tobytes() and (off3 == off).all()
-    assert int(t3.work_units) == _oracle_blocks(ix, nt4, ix.reads.offsets, ix.reads.n)
+    assert int(t3.work_units) == _oracle_blocks(ix, nt4, ix.reads.offsets, ix.reads.n) == int(g["blocks_total"])
     # the hot path's internal form: unique intervals anchored in the text (positions instead of rows)
     b.set_anchored(True)
     b.rerun()
