@@ -42,8 +42,18 @@ struct C2AArgs {
   int *n_regs;                       // [n_reads]
   const uint32_t *order; int *queue; int *err; unsigned long long *cells;
   int cls, qmax, refill;
+  // results of the speculative first-seed waves (null when they did not run): chain c's first seed, left / right flank, first band
+  // try; cflag[c] != 0 = not run ahead.  The exact kernel takes them instead of recomputing, so a read that was handed to it because
+  // ONE of its chains needs more (a repeat read has hundreds of chains) only runs the extensions that are actually missing.
+  const uint8_t *cflag; const bwaflow_ext_result_t *resL, *resR;
   DevIndex ix; DevScore sc; C2AOpt o;
 };
+
+__device__ __forceinline__ void lane_take_result(KswLane &k, const bwaflow_ext_result_t &x)
+{
+  k.best = x.score; k.best_j = x.qle - 1; k.best_i = x.tle - 1; k.end_i = x.gtle - 1; k.gscore = x.gscore; k.max_off = x.max_off;
+  k.cells = 0;
+}
 
 // cal_max_gap, bwa/bwamem.c:630-637 (integer-exact form of the double arithmetic, see gap_limit)
 __device__ __forceinline__ int max_gap(const C2AOpt &o, int qlen)
@@ -242,6 +252,11 @@ __global__ void __launch_bounds__(THREADS) c2a_kernel(const C2AArgs a)
           if (phase == PH_RIGHT_START) {
             if (s_qbeg + s_len != lq) {                              // :755-771
               sc0 = a_score; prev = a_score; tri = 0; aw1 = o.w;
+              if (p == 0 && a.resR && !a.cflag[ci] && (s_qbeg == 0 || a.resL[ci].score == sc0)) {   // run ahead from this very h0
+                lane_take_result(k, a.resR[ci]);
+                phase = PH_RIGHT;
+                continue;
+              }
               const int qlen = lq - (s_qbeg + s_len), tlen = (int)(whi - (s_rbeg + s_len));
               tpos = s_rbeg + s_len; tstep = 1;
               const uint8_t *qp = rd + s_qbeg + s_len;
@@ -309,6 +324,11 @@ __global__ void __launch_bounds__(THREADS) c2a_kernel(const C2AArgs a)
             aw0 = aw1 = o.w; a_score = a_truesc = -1;                // :717-721
             if (s_qbeg) {                                            // :724-743
               prev = -1; tri = 0;
+              if (p == 0 && a.resL && !a.cflag[ci]) {                // this call was run ahead
+                lane_take_result(k, a.resL[ci]);
+                phase = PH_LEFT;
+                continue;
+              }
               const int tlen = (int)(s_rbeg - wlo);
               tpos = s_rbeg - 1; tstep = -1;
               const uint8_t *qp = rd + s_qbeg - 1;
@@ -544,6 +564,7 @@ int bwaflow::c2a_launch(bwaflow_c2a_batch *b)
   a.cells = (unsigned long long *)(b->d_ctl + 3 * C2A_NCLASS + 2);
   a.refill = b->refill; a.ix = b->ctx->ix; a.sc = b->ctx->par.sc; a.o = o;
   a.cls = 0; a.qmax = 0;
+  a.cflag = nullptr; a.resL = a.resR = nullptr;
   // speculative waves + replay; what is left goes to the exact kernel below
   const uint8_t *only = nullptr;
   if (b->spec && !b->count_cells && nc > 0 && ns > 0) {
@@ -566,6 +587,7 @@ int bwaflow::c2a_launch(bwaflow_c2a_batch *b)
     BF_CUDA(cudaMemsetAsync(b->d_skipped2, 0, ns, st));
     c2a_replay_kernel<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(a, nr, b->d_cflag, b->d_resL, x.out, b->d_skipped2, b->d_strag);
     only = b->d_strag;
+    a.cflag = b->d_cflag; a.resL = b->d_resL; a.resR = x.out;
   }
   // read queue
   c2a_read_prep<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(b->d_read_off, b->d_chain_off, b->d_sbase, b->d_sseeds, nr, only, b->d_rkeys[0], b->d_rvals[0], hist, err);

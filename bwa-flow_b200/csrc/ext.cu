@@ -14,6 +14,7 @@
 #include "internal.cuh"
 #include "ksw_lane.cuh"
 #include "ksw_pair.cuh"
+#include "ksw_cols.cuh"
 #include "batches.cuh"
 
 namespace bwaflow {
@@ -236,6 +237,75 @@ __global__ void __launch_bounds__(32) ext_pair_kernel(const ExtArgs a)
   }
 }
 
+// Two-columns-per-word engine (ksw_cols.cuh): every lane owns ONE job and walks its own window; one warp per block, the row
+// state of its 32 jobs interleaved in shared memory.  Jobs the packed form cannot represent go to the deferred queue.
+__global__ void __launch_bounds__(32) ext_cols_kernel(const ExtArgs a)
+{
+  extern __shared__ uint2 s_cols[];
+  const int lane = threadIdx.x;
+  const int npmax = (a.qmax >> 1) + 1;
+  uint2 *st = s_cols + lane;
+  uint8_t *qb = (uint8_t *)(s_cols + (size_t)npmax * 32) + lane;
+  const unsigned full = 0xffffffffu;
+  int *head = a.queue + a.cls;
+  const int q_end = a.queue[EXT_NQ + a.cls];
+
+  __shared__ uint32_t s_stage[16];
+  ColsK ck;
+  ck.load(a.pc, s_stage);
+  ColJob k;
+  bool active = false, drained = false;
+  int job = -1, tcur = 0;
+  const uint8_t *tp = nullptr;
+
+  for (;;) {
+    const unsigned idle = __ballot_sync(full, !active);
+    if (idle == full || (!drained && __popc(idle) >= a.refill)) {
+      const int n_idle = __popc(idle);
+      int base = q_end;
+      if (!drained) {
+        if (lane == 0) base = atomicAdd(head, n_idle);
+        base = __shfl_sync(full, base, 0);
+        if (base + n_idle >= q_end) drained = true;
+      }
+      if (!active) {
+        const int slot = base + __popc(idle & ((1u << lane) - 1));
+        if (slot < q_end) {
+          job = (int)a.order[slot];
+          const bwaflow_ext_job_t jb = a.jobs[job];
+          const uint8_t *qp = a.qpool + jb.q_off;
+          tp = a.tpool + jb.t_off;
+          int r = PAIR_BAD;
+          if (jb.qlen >= 0 && jb.qlen <= a.qmax)
+            r = cols_begin(k, st, qb, a.sc, a.pc, jb.qlen, jb.tlen, jb.w, jb.h0, jb.end_bonus, [&](int j) { return (uint32_t)qp[j]; });
+          if (r == PAIR_BAD) {
+            atomicExch(a.err, 2);
+            a.out[job] = bwaflow_ext_result_t{0, 0, 0, 0, 0, 0};
+          } else if (jb.tlen <= 0) {
+            a.out[job] = bwaflow_ext_result_t{k.best, 0, 0, 0, -1, 0};
+          } else if (r == PAIR_SLOW) {
+            a.slow[atomicAdd(a.queue + EXT_NQ + EXT_NCLASS, 1)] = (uint32_t)job;
+          } else {
+            active = true;
+            tcur = tp[0];
+          }
+        }
+      }
+      if (__ballot_sync(full, active) == 0) break;
+    }
+    if (active && tcur > 3) {                              // an ambiguous target base sends the job to the int32 engine
+      a.slow[atomicAdd(a.queue + EXT_NQ + EXT_NCLASS, 1)] = (uint32_t)job;
+      active = false;
+    }
+    const int t = active ? tcur : 0;
+    if (active && k.i + 1 < k.tlen) tcur = tp[k.i + 1];    // fetched before the row so that the load overlaps it
+    if (cols_row(k, st, qb, a.sc, ck, active, t)) {
+      a.out[job] = bwaflow_ext_result_t{k.best, k.best_j + 1, k.best_i + 1, k.end_i + 1, k.gscore, k.max_off};
+      active = false;
+    }
+  }
+}
+
 } // namespace bwaflow
 
 using namespace bwaflow;
@@ -252,7 +322,9 @@ struct bwaflow_ext_batch {
   int *d_ctl;                       // hist[8] | queue[16] | err | pad | cells (u64)
   bwaflow_ext_result_t *d_out, *h_out;
   int *h_err;                       // err | pad | cells (u64)
-  int blocks[EXT_NCLASS], blocks_pair[EXT_NCLASS];
+  int blocks[EXT_NCLASS], blocks_pair[EXT_NCLASS], blocks_cols[EXT_NCLASS];
+  bool use_cols;               // packed classes run on the two-columns-per-word engine (the two-jobs-per-lane engine keeps the counting variant)
+  int refill_cols;
   int refill, refill_pair, pair_sync, pair_classes, order_rows;
   bool use_pair, multi_stream;
   double cells_known;
@@ -292,6 +364,7 @@ static int ext_launch(bwaflow_ext_batch *b)
     if (b->use_pair && c < b->pair_classes) {
       a.refill = b->refill_pair; a.pair_sync = b->pair_sync;
       if (b->count_cells) ext_pair_kernel<true><<<b->blocks_pair[c], 32, pair_smem(h_ext_qmax[c]), cs>>>(a);
+      else if (b->use_cols) { a.refill = b->refill_cols; ext_cols_kernel<<<b->blocks_cols[c], 32, cols_smem(h_ext_qmax[c]), cs>>>(a); }
       else ext_pair_kernel<false><<<b->blocks_pair[c], 32, pair_smem(h_ext_qmax[c]), cs>>>(a);
     } else {
       a.refill = b->refill;
@@ -364,7 +437,9 @@ int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_q
   if (const char *s = getenv("BWAFLOW_EXT_STREAMS")) b->multi_stream = atoi(s) != 1;
   fill_pair_consts(ctx->par.opt, ctx->par.sc, b->pc);
   b->use_pair = b->pc.ok != 0;
-  if (const char *s = getenv("BWAFLOW_EXT_ENGINE")) if (!strcmp(s, "int32")) b->use_pair = false;
+  b->use_cols = true; b->refill_cols = 8;
+  if (const char *s = getenv("BWAFLOW_EXT_ENGINE")) { if (!strcmp(s, "int32")) b->use_pair = false; if (!strcmp(s, "pair")) b->use_cols = false; }
+  if (const char *s = getenv("BWAFLOW_EXT_REFILL_COLS")) b->refill_cols = atoi(s) > 0 ? atoi(s) : 8;
   BF_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   if (b->tm.init()) return -5;
   BF_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
@@ -409,6 +484,10 @@ int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_q
       if (per_sm2 < per_sm) per_sm = per_sm2;
       BF_REQUIRE(per_sm > 0, -12, "packed extension kernel class %d does not fit on an SM", c);
       b->blocks_pair[c] = per_sm * ctx->n_sm;
+      BF_CUDA(cudaFuncSetAttribute(ext_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ext_cols_kernel, 32, cols_smem(h_ext_qmax[c])));
+      BF_REQUIRE(per_sm > 0, -12, "two-column extension kernel class %d does not fit on an SM", c);
+      b->blocks_cols[c] = per_sm * ctx->n_sm;
     }
   }
   *out = b;

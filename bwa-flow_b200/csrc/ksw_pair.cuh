@@ -34,6 +34,7 @@ struct PairConsts {
   int ok;                      // scoring matrix has the packed form
   int a, b, bias;
   uint32_t B2, A2, NAB, K, HKC, OED2, ED2, OEI2, EI2, NEI2;
+  uint32_t one, neg1, sh16, kmul;   // 1, -1, 65536 and the key multiplier as run-time values: multiply-adds by them stay IMADs (FMA pipe)
 };
 
 inline void fill_pair_consts(const bwaflow_opt_t &o, const DevScore &sc, PairConsts &c)
@@ -58,6 +59,7 @@ inline void fill_pair_consts(const bwaflow_opt_t &o, const DevScore &sc, PairCon
   c.OED2 = (uint32_t)(sc.o_del + sc.e_del) * one; c.ED2 = (uint32_t)sc.e_del * one;
   c.OEI2 = (uint32_t)(sc.o_ins + sc.e_ins) * one; c.EI2 = (uint32_t)sc.e_ins * one;
   c.NEI2 = (uint32_t)(uint16_t)(-sc.e_ins) * one;      // per-half -e_ins, added inside the DPX instruction
+  c.one = 1u; c.neg1 = 0xFFFFFFFFu; c.sh16 = 65536u; c.kmul = 128u;
 }
 
 __device__ __forceinline__ uint32_t mad_fma(uint32_t a, uint32_t b, uint32_t c)
