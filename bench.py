@@ -505,6 +505,7 @@ def main():
         out = h.run(rec)                   # first touch: allocations, local-memory setup, capacity growth
     n_regs = len(out["alnreg"])
     n_exact_reads = hps[-1].batch.exact_reads()
+    second_round = hps[-1].batch.second_round()
     n_chk = min(reads.n, args.parity_reads) & ~1   # kept for the parity check against the reference in the CPU-baseline leg
     chk_off = np.array(out["alnreg_off"][:n_chk + 1], dtype=np.int64)
     chk_regs = np.array(out["alnreg"][:chk_off[-1]])
@@ -594,7 +595,8 @@ def main():
                              "step": ms_step, "e2e_step": ms_e2e / args.steps},
             "index_build_s": t_index, "dpx_peak_lane_ops_per_s": {"s16x2": dpx16, "s32": dpx32},
             "counts": {"n_intv": parts[-1].n_intv, "n_pos": parts[-1].n_pos, "n_chains": parts[-1].n_chains,
-                       "n_seeds": parts[-1].n_seeds, "n_regs": n_regs, "stage4_reads_on_exact_kernel": n_exact_reads}}
+                       "n_seeds": parts[-1].n_seeds, "n_regs": n_regs, "stage4_reads_left_by_first_replay": second_round[0], "stage4_second_round_jobs": second_round[1],
+                       "stage4_reads_on_exact_kernel": n_exact_reads}}
     if not args.no_ext_microbench:
         line["ext_microbench"] = ext_microbench(ctx, peak_gcups, args.ext_jobs)
     if world == 1 and not args.no_cpu_baseline:

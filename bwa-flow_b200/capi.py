@@ -96,6 +96,8 @@ def lib():
             L.bwaflow_c2a_rerun.argtypes = [C.c_void_p]
             L.bwaflow_c2a_rerun_counted.argtypes = [C.c_void_p]
             L.bwaflow_c2a_exact_reads.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+            L.bwaflow_c2a_second_round.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+            L.bwaflow_hot_second_round.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         if hasattr(L, "bwaflow_smem_batch_create"):
             L.bwaflow_smem_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
             L.bwaflow_smem_batch_destroy.argtypes = [C.c_void_p]
@@ -289,6 +291,11 @@ class C2ABatch:
         check(self.L.bwaflow_c2a_exact_reads(self.h, C.byref(n)))
         return n.value
 
+    def second_round(self):
+        r, j = C.c_int64(), C.c_int64()
+        check(self.L.bwaflow_c2a_second_round(self.h, C.byref(r), C.byref(j)))
+        return r.value, j.value
+
     def rerun(self, counted=False):
         check(self.L.bwaflow_c2a_rerun_counted(self.h) if counted else self.L.bwaflow_c2a_rerun(self.h))
 
@@ -464,6 +471,12 @@ class HotBatch:
         n = C.c_int64()
         check(self.L.bwaflow_hot_exact_reads(self.h, C.byref(n)))
         return n.value
+
+    def second_round(self):
+        """(reads the first replay of stage 4 left, extension jobs the second round of waves ran ahead for them)"""
+        r, j = C.c_int64(), C.c_int64()
+        check(self.L.bwaflow_hot_second_round(self.h, C.byref(r), C.byref(j)))
+        return r.value, j.value
 
     def rerun(self, counted=False):
         check(self.L.bwaflow_hot_rerun_counted(self.h) if counted else self.L.bwaflow_hot_rerun(self.h))

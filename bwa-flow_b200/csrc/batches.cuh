@@ -59,6 +59,15 @@ struct bwaflow_c2a_batch {
   uint8_t *d_cflag;                 // per chain: 1 = no speculative result (pool overflow, unrepresentable job)
   uint8_t *d_strag;                 // per read: 1 = must be redone by the exact kernel
   uint8_t *d_skipped2;              // the replay's own copy of the per-seed "skipped" flags
+  // second round of waves: every later seed of the reads the first replay could not finish (chain2aln.cu, "wave B")
+  bwaflow_ext_batch_t *xb2;
+  bwaflow_ext_result_t *d_resL2;    // per wave-B job
+  int32_t *d_slot_chain;            // per seed slot (processing order): its chain
+  int32_t *d_jslot, *d_slot_job;    // wave-B job -> seed slot and back (-1 = none)
+  uint8_t *d_cand, *d_cflag2;       // per slot: candidate for wave B; per wave-B job: 1 = no result
+  int64_t *d_jsz2, *d_joff2; void *d_jdesc2;
+  int32_t *d_nsel; int *h_sel;      // {wave-B jobs, reads left by the first replay}
+  int64_t waveb_jobs, waveb_reads;  // of the last launch
 };
 
 namespace bwaflow {

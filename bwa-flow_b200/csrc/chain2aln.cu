@@ -17,6 +17,8 @@
 //   scan + gather    compact the per-read region lists
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <string.h>
 #include <stdlib.h>
 #include "internal.cuh"
@@ -46,6 +48,8 @@ struct C2AArgs {
   // try; cflag[c] != 0 = not run ahead.  The exact kernel takes them instead of recomputing, so a read that was handed to it because
   // ONE of its chains needs more (a repeat read has hundreds of chains) only runs the extensions that are actually missing.
   const uint8_t *cflag; const bwaflow_ext_result_t *resL, *resR;
+  // wave B: the same for every later seed of the reads the first replay left (slot_job[slot] = job or -1; null when it did not run)
+  const int32_t *slot_job; const uint8_t *cflag2; const bwaflow_ext_result_t *resL2, *resR2;
   DevIndex ix; DevScore sc; C2AOpt o;
 };
 
@@ -75,7 +79,7 @@ __device__ __forceinline__ int ref_base(const DevIndex &ix, int64_t p)
 
 __global__ void c2a_chain_prep(const bwaflow_chain_t *chains, int64_t n_chains, const int64_t *chain_read,
                                const int64_t *read_off, const bwaflow_seed_t *seeds, const int64_t *sbase,
-                               DevIndex ix, C2AOpt o, int64_t *win, uint64_t *keys, uint32_t *vals, int *err)
+                               DevIndex ix, C2AOpt o, int64_t *win, uint64_t *keys, uint32_t *vals, int32_t *slot_chain, int *err)
 {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_chains) return;
@@ -98,6 +102,7 @@ __global__ void c2a_chain_prep(const bwaflow_chain_t *chains, int64_t n_chains, 
     const uint64_t inner = ((uint64_t)(uint32_t)s.score << 20 | (uint32_t)i) ^ 0xFFFFFFFFFFull;
     keys[sbase[c] + i] = (uint64_t)c << 40 | inner;
     vals[sbase[c] + i] = (uint32_t)(ch.seed_off + i);
+    slot_chain[sbase[c] + i] = (int32_t)c;
   }
   if (ch.n_seeds > 0) {
     lo = lo > 0 ? lo : 0;
@@ -164,6 +169,23 @@ __global__ void c2a_ranges_kernel(const int *hist, int *queue)
 {
   int pos = 0;
   for (int c = C2A_NCLASS - 1; c >= 0; --c) { queue[c] = pos; pos += hist[c]; queue[C2A_NCLASS + c] = pos; }
+}
+
+// Run-ahead results of the seed at processing position p of chain ci (slot = its index in processing order): the first seed of a
+// chain comes from the first-seed waves, later seeds from wave B.  Returns false when there is none.
+__device__ __forceinline__ bool spec_lookup(const C2AArgs &a, int64_t ci, int p, int64_t slot, const bwaflow_ext_result_t **L,
+                                            const bwaflow_ext_result_t **R)
+{
+  if (p == 0) {
+    if (!a.resL || a.cflag[ci]) return false;
+    *L = a.resL + ci; *R = a.resR + ci;
+    return true;
+  }
+  if (!a.slot_job) return false;
+  const int j = a.slot_job[slot];
+  if (j < 0 || a.cflag2[j]) return false;
+  *L = a.resL2 + j; *R = a.resR2 + j;
+  return true;
 }
 
 enum { PH_NEXT_SEED = 0, PH_LEFT = 1, PH_RIGHT_START = 2, PH_RIGHT = 3 };
@@ -252,10 +274,13 @@ __global__ void __launch_bounds__(THREADS) c2a_kernel(const C2AArgs a)
           if (phase == PH_RIGHT_START) {
             if (s_qbeg + s_len != lq) {                              // :755-771
               sc0 = a_score; prev = a_score; tri = 0; aw1 = o.w;
-              if (p == 0 && a.resR && !a.cflag[ci] && (s_qbeg == 0 || a.resL[ci].score == sc0)) {   // run ahead from this very h0
-                lane_take_result(k, a.resR[ci]);
-                phase = PH_RIGHT;
-                continue;
+              {
+                const bwaflow_ext_result_t *xl, *xr;
+                if (spec_lookup(a, ci, p, s_base + p, &xl, &xr) && (s_qbeg == 0 || xl->score == sc0)) {   // run ahead from this very h0
+                  lane_take_result(k, *xr);
+                  phase = PH_RIGHT;
+                  continue;
+                }
               }
               const int qlen = lq - (s_qbeg + s_len), tlen = (int)(whi - (s_rbeg + s_len));
               tpos = s_rbeg + s_len; tstep = 1;
@@ -324,10 +349,13 @@ __global__ void __launch_bounds__(THREADS) c2a_kernel(const C2AArgs a)
             aw0 = aw1 = o.w; a_score = a_truesc = -1;                // :717-721
             if (s_qbeg) {                                            // :724-743
               prev = -1; tri = 0;
-              if (p == 0 && a.resL && !a.cflag[ci]) {                // this call was run ahead
-                lane_take_result(k, a.resL[ci]);
-                phase = PH_LEFT;
-                continue;
+              {
+                const bwaflow_ext_result_t *xl, *xr;
+                if (spec_lookup(a, ci, p, s_base + p, &xl, &xr)) {    // this call was run ahead
+                  lane_take_result(k, *xl);
+                  phase = PH_LEFT;
+                  continue;
+                }
               }
               const int tlen = (int)(s_rbeg - wlo);
               tpos = s_rbeg - 1; tstep = -1;
@@ -374,31 +402,36 @@ __device__ __forceinline__ void spec_flank(int side, const bwaflow_seed_t &s, in
 struct SpecDesc { int64_t q_src, tpos; int32_t qlen, tlen, h0; int8_t qstep, tstep, nospec, end_bonus; };
 static_assert(sizeof(SpecDesc) == 32, "SpecDesc is allocated as 32 bytes per chain");
 
-__global__ void c2a_spec_size(int side, const bwaflow_chain_t *chains, int64_t n_chains, const int64_t *chain_read, const int64_t *read_off,
+// Job j of a wave: the first seed of chain j (jslot == null: the first-seed waves) or the seed at slot jslot[j] (wave B).
+__global__ void c2a_spec_size(int side, const bwaflow_chain_t *chains, int64_t n_jobs, const int32_t *jslot, const int32_t *slot_chain,
+                              const int64_t *chain_read, const int64_t *read_off,
                               const int64_t *sbase, const bwaflow_seed_t *sseeds, const int64_t *win, DevScore sc, C2AOpt o,
                               const bwaflow_ext_result_t *resL, const uint8_t *cflag, SpecDesc *desc, int64_t *jsz)
 {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > n_chains) return;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > n_jobs) return;
   SpecDesc d;
   memset(&d, 0, sizeof(d));
   d.nospec = 1; d.h0 = 1; d.qstep = d.tstep = 1;
-  if (c < n_chains && chains[c].n_seeds > 0 && !(side == 1 && cflag[c])) {
-    const int64_t r = chain_read[c];
-    const int64_t ro = read_off[r];
-    const int lq = (int)(read_off[r + 1] - ro);
-    const bwaflow_seed_t s = sseeds[sbase[c]];
-    int qlen, tlen;
-    spec_flank(side, s, lq, win[2 * c], win[2 * c + 1], &qlen, &tlen);
-    if (qlen == 0) tlen = 0;                                  // no call at all (bwa/bwamem.c:753, 780)
-    d.qlen = qlen; d.tlen = tlen;
-    if (side == 0) { d.h0 = s.len * o.a; d.end_bonus = (int8_t)o.pen_clip5; d.q_src = ro + s.qbeg - 1; d.qstep = -1; d.tpos = s.rbeg - 1; d.tstep = -1; }
-    else { d.h0 = s.qbeg ? resL[c].score : s.len * o.a; d.end_bonus = (int8_t)o.pen_clip3; d.q_src = ro + s.qbeg + s.len; d.tpos = s.rbeg + s.len; }
-    d.nospec = d.h0 <= 0 || d.h0 + qlen * sc.smax > KSW_MAX_SCORE || o.pen_clip5 > 127 || o.pen_clip3 > 127;
+  if (j < n_jobs) {
+    const int64_t c = jslot ? slot_chain[jslot[j]] : j;
+    if (chains[c].n_seeds > 0 && !(side == 1 && cflag[j])) {
+      const int64_t r = chain_read[c];
+      const int64_t ro = read_off[r];
+      const int lq = (int)(read_off[r + 1] - ro);
+      const bwaflow_seed_t s = sseeds[jslot ? (int64_t)jslot[j] : sbase[c]];
+      int qlen, tlen;
+      spec_flank(side, s, lq, win[2 * c], win[2 * c + 1], &qlen, &tlen);
+      if (qlen == 0) tlen = 0;                                  // no call at all (bwa/bwamem.c:753, 780)
+      d.qlen = qlen; d.tlen = tlen;
+      if (side == 0) { d.h0 = s.len * o.a; d.end_bonus = (int8_t)o.pen_clip5; d.q_src = ro + s.qbeg - 1; d.qstep = -1; d.tpos = s.rbeg - 1; d.tstep = -1; }
+      else { d.h0 = s.qbeg ? resL[j].score : s.len * o.a; d.end_bonus = (int8_t)o.pen_clip3; d.q_src = ro + s.qbeg + s.len; d.tpos = s.rbeg + s.len; }
+      d.nospec = d.h0 <= 0 || d.h0 + qlen * sc.smax > KSW_MAX_SCORE || o.pen_clip5 > 127 || o.pen_clip3 > 127;
+    }
   }
   if (d.nospec) { d.qlen = 0; d.tlen = 0; d.h0 = 1; }
-  if (c < n_chains) desc[c] = d;
-  jsz[c] = d.qlen; jsz[n_chains + 1 + c] = d.tlen;
+  if (j < n_jobs) desc[j] = d;
+  jsz[j] = d.qlen; jsz[n_jobs + 1 + j] = d.tlen;
 }
 
 // one warp per chain: job record and its query / target bytes
@@ -426,11 +459,12 @@ __global__ void c2a_spec_fill(int side, int64_t n_chains, const SpecDesc *desc, 
 
 // One thread per read: mem_chain2aln's seed loop (bwa/bwamem.c:676-792) in the reference's order, with the two extensions of
 // a chain's first seed taken from the speculative waves.  Sets strag[r] (and leaves no regions) when the read needs more.
-__global__ void c2a_replay_kernel(C2AArgs a, int64_t n_reads, const uint8_t *cflag, const bwaflow_ext_result_t *resL,
-                                  const bwaflow_ext_result_t *resR, uint8_t *skipped, uint8_t *strag)
+// `again`: second replay, only for the reads the first one left (strag[r] != 0), now with the wave-B results in `a`.
+__global__ void c2a_replay_kernel(C2AArgs a, int64_t n_reads, uint8_t *skipped, uint8_t *strag, int again)
 {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
+  if (again && !strag[r]) return;
   const C2AOpt o = a.o;
   const int lq = (int)(a.read_off[r + 1] - a.read_off[r]);
   bwaflow_alnreg_t *av = a.regs + a.sbase[a.chain_off[r]];
@@ -469,18 +503,19 @@ __global__ void c2a_replay_kernel(C2AArgs a, int64_t n_reads, const uint8_t *cfl
         }
         if (e < 0) { skipped[s_base + p] = 1; continue; }
       }
-      if (p != 0 || cflag[ci]) { bail = true; break; }         // only first seeds were run ahead
+      const bwaflow_ext_result_t *xl, *xr;
+      if (!spec_lookup(a, ci, p, s_base + p, &xl, &xr)) { bail = true; break; }   // not run ahead
       const int wtest = (o.w >> 1) + (o.w >> 2);
       int a_score, a_truesc, a_qb, a_qe; int64_t a_rb, a_re;
       if (s.qbeg) {                                            // :724-751
-        const bwaflow_ext_result_t x = resL[ci];
+        const bwaflow_ext_result_t x = *xl;
         if (!(x.max_off < wtest)) { bail = true; break; }      // would take the second band try
         a_score = x.score;
         if (x.gscore <= 0 || x.gscore <= a_score - o.pen_clip5) { a_qb = s.qbeg - x.qle; a_rb = s.rbeg - x.tle; a_truesc = a_score; }
         else { a_qb = 0; a_rb = s.rbeg - x.gtle; a_truesc = x.gscore; }
       } else { a_score = a_truesc = s.len * o.a; a_qb = 0; a_rb = s.rbeg; }
       if (s.qbeg + s.len != lq) {                              // :755-779
-        const bwaflow_ext_result_t x = resR[ci];
+        const bwaflow_ext_result_t x = *xr;
         const int sc0 = a_score;
         if (!(x.score == sc0 || x.max_off < wtest)) { bail = true; break; }
         a_score = x.score;
@@ -501,8 +536,32 @@ __global__ void c2a_replay_kernel(C2AArgs a, int64_t n_reads, const uint8_t *cfl
     }
   }
   strag[r] = bail ? 1 : 0;
-  if (bail) atomicAdd(a.err + 1, 1);                       // reads left to the exact kernel (reported, not an error)
+  if (bail) atomicAdd(a.err + 1, 1);                       // reads left to the exact kernel (reported, not an error; reset before a second replay)
   a.n_regs[r] = bail ? 0 : n_av;
+}
+
+// wave B candidates: every later seed of the chains of the reads the first replay left
+__global__ void c2a_cand_kernel(int64_t n_slots, const int32_t *slot_chain, const int64_t *chain_read, const int64_t *sbase, const uint8_t *strag,
+                                uint8_t *cand, int32_t *slot_job)
+{
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  const int64_t c = slot_chain[s];
+  cand[s] = strag[chain_read[c]] && s != sbase[c];
+  slot_job[s] = -1;
+}
+
+__global__ void c2a_slot_job_kernel(const int32_t *n_jobs, int64_t cap, const int32_t *jslot, int32_t *slot_job)
+{
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < *n_jobs && j < cap) slot_job[jslot[j]] = (int32_t)j;
+}
+
+__global__ void c2a_count_strag(const uint8_t *strag, int64_t n_reads, int32_t *out)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned m = __ballot_sync(0xffffffffu, r < n_reads && strag[r]);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, __popc(m));
 }
 
 __global__ void c2a_compact(const int64_t *chain_off, const int64_t *sbase, const int *n_regs, const int64_t *reg_off,
@@ -529,6 +588,28 @@ using namespace bwaflow;
 
 static size_t max3(size_t a, size_t b, size_t c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 
+// The left and the right flank of n jobs (job j = first seed of chain j, or the seed at slot jslot[j]) as two waves on an extension
+// batch: sizes -> offsets -> job records and byte pools -> kernels.  Left results end in resL, right results stay in xb's output.
+static int c2a_waves(bwaflow_c2a_batch *b, const C2AOpt &o, cudaStream_t st, bwaflow_ext_batch_t *xb, int64_t n, const int32_t *jslot,
+                     uint8_t *cflag, bwaflow_ext_result_t *resL, void *jdesc, int64_t *jsz, int64_t *joff)
+{
+  const ExtDeviceView x = ext_device_view(xb);
+  for (int side = 0; side < 2; ++side) {
+    if (side == 0) BF_CUDA(cudaMemsetAsync(cflag, 0, n, st));
+    c2a_spec_size<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(side, b->d_chains, n, jslot, b->d_slot_chain, b->d_chain_read, b->d_read_off, b->d_sbase,
+                                                               b->d_sseeds, b->d_win, b->ctx->par.sc, o, resL, cflag, (SpecDesc *)jdesc, jsz);
+    for (int k = 0; k < 2; ++k) {
+      size_t tmp = b->tmp_bytes;
+      BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, jsz + k * (n + 1), joff + k * (n + 1), (int)(n + 1), st));
+    }
+    c2a_spec_fill<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(side, n, (const SpecDesc *)jdesc, b->d_bases, joff, b->ctx->ix, b->ctx->par.sc, o, x, cflag);
+    int r = ext_launch_device(xb, n, st);
+    if (r) return r;
+    if (side == 0) BF_CUDA(cudaMemcpyAsync(resL, x.out, n * sizeof(bwaflow_ext_result_t), cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
 int bwaflow::c2a_launch(bwaflow_c2a_batch *b)
 {
   const int64_t nr = b->n_reads, nc = b->n_chains, ns = b->n_seeds;
@@ -549,7 +630,7 @@ int bwaflow::c2a_launch(bwaflow_c2a_batch *b)
   cub::DoubleBuffer<uint32_t> sv(b->d_svals[0], b->d_svals[1]);
   if (nc) {
     c2a_chain_prep<<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(b->d_chains, nc, b->d_chain_read, b->d_read_off, b->d_seeds, b->d_sbase,
-                                                               b->ctx->ix, o, b->d_win, b->d_skeys[0], b->d_svals[0], err);
+                                                               b->ctx->ix, o, b->d_win, b->d_skeys[0], b->d_svals[0], b->d_slot_chain, err);
     if (ns) {
       tmp = b->tmp_bytes;
       BF_CUDA(cub::DeviceRadixSort::SortPairs(b->d_tmp, tmp, sk, sv, (int)ns, 0, 64, st));
@@ -565,29 +646,45 @@ int bwaflow::c2a_launch(bwaflow_c2a_batch *b)
   a.refill = b->refill; a.ix = b->ctx->ix; a.sc = b->ctx->par.sc; a.o = o;
   a.cls = 0; a.qmax = 0;
   a.cflag = nullptr; a.resL = a.resR = nullptr;
+  a.slot_job = nullptr; a.cflag2 = nullptr; a.resL2 = a.resR2 = nullptr;
   // speculative waves + replay; what is left goes to the exact kernel below
   const uint8_t *only = nullptr;
+  b->waveb_jobs = b->waveb_reads = 0;
   if (b->spec && !b->count_cells && nc > 0 && ns > 0) {
     const ExtDeviceView x = ext_device_view(b->xb);
-    for (int side = 0; side < 2; ++side) {
-      if (side == 0) BF_CUDA(cudaMemsetAsync(b->d_cflag, 0, nc, st));
-      c2a_spec_size<<<(unsigned)((nc + 1 + 255) / 256), 256, 0, st>>>(side, b->d_chains, nc, b->d_chain_read, b->d_read_off, b->d_sbase,
-                                                                  b->d_sseeds, b->d_win, b->ctx->par.sc, o, b->d_resL, b->d_cflag,
-                                                                  (SpecDesc *)b->d_jdesc, b->d_jsz);
-      for (int k = 0; k < 2; ++k) {
-        tmp = b->tmp_bytes;
-        BF_CUDA(cub::DeviceScan::ExclusiveSum(b->d_tmp, tmp, b->d_jsz + k * (nc + 1), b->d_joff + k * (nc + 1), (int)(nc + 1), st));
-      }
-      c2a_spec_fill<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(side, nc, (const SpecDesc *)b->d_jdesc, b->d_bases, b->d_joff, b->ctx->ix,
-                                                                   b->ctx->par.sc, o, x, b->d_cflag);
-      int r = ext_launch_device(b->xb, nc, st);
-      if (r) return r;
-      if (side == 0) BF_CUDA(cudaMemcpyAsync(b->d_resL, x.out, nc * sizeof(bwaflow_ext_result_t), cudaMemcpyDeviceToDevice, st));
-    }
-    BF_CUDA(cudaMemsetAsync(b->d_skipped2, 0, ns, st));
-    c2a_replay_kernel<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(a, nr, b->d_cflag, b->d_resL, x.out, b->d_skipped2, b->d_strag);
-    only = b->d_strag;
+    int r = c2a_waves(b, o, st, b->xb, nc, nullptr, b->d_cflag, b->d_resL, b->d_jdesc, b->d_jsz, b->d_joff);
+    if (r) return r;
     a.cflag = b->d_cflag; a.resL = b->d_resL; a.resR = x.out;
+    BF_CUDA(cudaMemsetAsync(b->d_skipped2, 0, ns, st));
+    c2a_replay_kernel<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(a, nr, b->d_skipped2, b->d_strag, 0);
+    only = b->d_strag;
+    // Wave B.  A read the replay left (a later seed of a chain is not contained, typically one chain out of the hundreds of a
+    // repeat read) would otherwise run ALL its missing extensions one after the other on one lane of the exact kernel.  Every
+    // later seed of such reads is run ahead as well -- two more waves on the batch engine -- and the reads are replayed once
+    // more; only second band tries and jobs the engine cannot hold are then left.  One small read-back decides whether there
+    // is anything to do (nothing on the i.i.d. workloads).
+    if (b->xb2) {
+      BF_CUDA(cudaMemsetAsync(b->d_nsel, 0, 2 * sizeof(int32_t), st));
+      c2a_count_strag<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(b->d_strag, nr, b->d_nsel + 1);
+      c2a_cand_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(ns, b->d_slot_chain, b->d_chain_read, b->d_sbase, b->d_strag, b->d_cand, b->d_slot_job);
+      tmp = b->tmp_bytes;
+      BF_CUDA(cub::DeviceSelect::Flagged(b->d_tmp, tmp, cub::CountingInputIterator<int32_t>(0), b->d_cand, b->d_jslot, b->d_nsel, (int)ns, st));
+      BF_CUDA(cudaMemcpyAsync(b->h_sel, b->d_nsel, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      BF_CUDA(cudaStreamSynchronize(st));
+      const ExtDeviceView x2 = ext_device_view(b->xb2);
+      int64_t nb = b->h_sel[0];
+      b->waveb_reads = b->h_sel[1];
+      if (nb > x2.max_jobs) nb = x2.max_jobs;
+      if (b->waveb_reads > 0 && nb > 0) {
+        b->waveb_jobs = nb;
+        c2a_slot_job_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(b->d_nsel, nb, b->d_jslot, b->d_slot_job);
+        r = c2a_waves(b, o, st, b->xb2, nb, b->d_jslot, b->d_cflag2, b->d_resL2, b->d_jdesc2, b->d_jsz2, b->d_joff2);
+        if (r) return r;
+        a.slot_job = b->d_slot_job; a.cflag2 = b->d_cflag2; a.resL2 = b->d_resL2; a.resR2 = x2.out;
+        BF_CUDA(cudaMemsetAsync(err + 1, 0, sizeof(int), st));
+        c2a_replay_kernel<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(a, nr, b->d_skipped2, b->d_strag, 1);
+      }
+    }
   }
   // read queue
   c2a_read_prep<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(b->d_read_off, b->d_chain_off, b->d_sbase, b->d_sseeds, nr, only, b->d_rkeys[0], b->d_rvals[0], hist, err);
@@ -661,6 +758,10 @@ int bwaflow_c2a_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_
     BF_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, t2, rk, rv, (int)mr, 0, 28, b->stream));
     BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t3, b->d_nseeds, b->d_sbase, (int)(mc + 1), b->stream));
     BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t4, b->d_nseeds, b->d_sbase, (int)(mr + 1), b->stream));
+    size_t t5 = 0, t6 = 0;
+    BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t5, b->d_nseeds, b->d_sbase, (int)(ms + 1), b->stream));
+    BF_CUDA(cub::DeviceSelect::Flagged(nullptr, t6, cub::CountingInputIterator<int32_t>(0), (uint8_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, (int)ms, b->stream));
+    t4 = max3(t4, t5, t6);
   }
   b->tmp_bytes = max3(t1, t2, t3 > t4 ? t3 : t4) + 256;
   BF_CUDA(cudaMalloc(&b->d_tmp, b->tmp_bytes));
@@ -682,6 +783,24 @@ int bwaflow_c2a_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_
     // first-seed flanks of weak chains are long and die early: with that mix the packed engine only pays up to qlen 95 (measured)
     ext_set_pair_classes(b->xb, 3);
     ext_set_order_rows(b->xb, 1);
+  }
+  BF_CUDA(cudaMalloc(&b->d_slot_chain, ms * 4));
+  if (b->spec && !(getenv("BWAFLOW_C2A_WAVEB") && atoi(getenv("BWAFLOW_C2A_WAVEB")) == 0)) {
+    // wave B: up to one job per seed slot, pools as above
+    int r = bwaflow_ext_batch_create(ctx, ms, 96 * ms + 4096, 288 * ms + 4096, &b->xb2);
+    if (r) return r;
+    ext_set_pair_classes(b->xb2, 5);
+    ext_set_order_rows(b->xb2, 1);
+    BF_CUDA(cudaMalloc(&b->d_resL2, ms * sizeof(bwaflow_ext_result_t)));
+    BF_CUDA(cudaMalloc(&b->d_jslot, ms * 4));
+    BF_CUDA(cudaMalloc(&b->d_slot_job, ms * 4));
+    BF_CUDA(cudaMalloc(&b->d_cand, ms));
+    BF_CUDA(cudaMalloc(&b->d_cflag2, ms));
+    BF_CUDA(cudaMalloc(&b->d_jsz2, 2 * (ms + 1) * 8));
+    BF_CUDA(cudaMalloc(&b->d_joff2, 2 * (ms + 1) * 8));
+    BF_CUDA(cudaMalloc(&b->d_jdesc2, ms * 32));
+    BF_CUDA(cudaMalloc(&b->d_nsel, 2 * sizeof(int32_t)));
+    BF_CUDA(cudaMallocHost(&b->h_sel, 2 * sizeof(int)));
   }
   BF_CUDA(cudaMalloc(&b->d_regs, ms * sizeof(bwaflow_alnreg_t)));
   BF_CUDA(cudaMalloc(&b->d_regs_out, ms * sizeof(bwaflow_alnreg_t)));
@@ -718,6 +837,9 @@ void bwaflow_c2a_batch_destroy(bwaflow_c2a_batch_t *b)
   cudaFree(b->d_sseeds); cudaFree(b->d_nseeds); cudaFree(b->d_sbase); cudaFree(b->d_chain_read); cudaFree(b->d_win);
   for (int i = 0; i < 2; ++i) { cudaFree(b->d_skeys[i]); cudaFree(b->d_svals[i]); cudaFree(b->d_rkeys[i]); cudaFree(b->d_rvals[i]); }
   if (b->xb) bwaflow_ext_batch_destroy(b->xb);
+  if (b->xb2) bwaflow_ext_batch_destroy(b->xb2);
+  cudaFree(b->d_slot_chain); cudaFree(b->d_resL2); cudaFree(b->d_jslot); cudaFree(b->d_slot_job); cudaFree(b->d_cand); cudaFree(b->d_cflag2);
+  cudaFree(b->d_jsz2); cudaFree(b->d_joff2); cudaFree(b->d_jdesc2); cudaFree(b->d_nsel); if (b->h_sel) cudaFreeHost(b->h_sel);
   cudaFree(b->d_skipped2); cudaFree(b->d_strag); cudaFree(b->d_cflag); cudaFree(b->d_jsz); cudaFree(b->d_joff); cudaFree(b->d_resL); cudaFree(b->d_jdesc);
   cudaFree(b->d_tmp); cudaFree(b->d_skipped); cudaFree(b->d_regs); cudaFree(b->d_regs_out); cudaFreeHost(b->h_regs);
   cudaFree(b->d_nregs); cudaFree(b->d_nregs64); cudaFree(b->d_reg_off); cudaFreeHost(b->h_reg_off);
@@ -775,6 +897,14 @@ static int c2a_rerun(bwaflow_c2a_batch_t *b, bool counted)
   int r = c2a_launch(b);
   if (r) return r;
   return c2a_finish_queue(b);
+}
+
+int bwaflow_c2a_second_round(bwaflow_c2a_batch_t *b, int64_t *n_reads, int64_t *n_jobs)
+{
+  BF_REQUIRE(b && !b->pending, -22, "bwaflow_c2a_second_round: call after collect");
+  if (n_reads) *n_reads = b->waveb_reads;
+  if (n_jobs) *n_jobs = b->waveb_jobs;
+  return 0;
 }
 
 int bwaflow_c2a_exact_reads(bwaflow_c2a_batch_t *b, int64_t *n_exact)

@@ -309,6 +309,12 @@ static int hot_rerun(bwaflow_hot_batch_t *b, bool counted)
   return hot_enqueue_front(b);
 }
 
+int bwaflow_hot_second_round(bwaflow_hot_batch_t *b, int64_t *n_reads, int64_t *n_jobs)
+{
+  BF_REQUIRE(b && b->c, -22, "bwaflow_hot_second_round: call after collect");
+  return bwaflow_c2a_second_round(b->c, n_reads, n_jobs);
+}
+
 int bwaflow_hot_exact_reads(bwaflow_hot_batch_t *b, int64_t *n_exact)
 {
   BF_REQUIRE(b && b->c && n_exact, -22, "bwaflow_hot_exact_reads: call after collect");

@@ -143,6 +143,9 @@ int bwaflow_c2a_rerun_counted(bwaflow_c2a_batch_t *b);
 /* after a collect: how many reads of the last launch were (re)done by the exact lane-per-read kernel rather than served by the
  * speculative first-seed waves + replay (all of them when speculation is off or for a counted pass) */
 int bwaflow_c2a_exact_reads(bwaflow_c2a_batch_t *b, int64_t *n_exact);
+/* after a collect: how many reads the first replay left and how many extension jobs (their later seeds) the second round of
+ * waves ran ahead for them before the second replay; both 0 when every read was served by the first-seed waves */
+int bwaflow_c2a_second_round(bwaflow_c2a_batch_t *b, int64_t *n_reads, int64_t *n_jobs);
 
 /* ---- stage 2: reads -> SMEM intervals (replaces SeqsToChainsFPGA::compute, src/fpga/FPGAPipeline.cpp:582;
  *      arithmetic = mem_collect_intv_new src/bwa_wrapper.cpp:207-246).  Output per read: bwtintv_t list sorted
@@ -209,6 +212,7 @@ void bwaflow_hot_batch_destroy(bwaflow_hot_batch_t *b);
 int bwaflow_hot_submit(bwaflow_hot_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off);
 int bwaflow_hot_rerun(bwaflow_hot_batch_t *b);        /* reads of the last submit, already resident */
 int bwaflow_hot_exact_reads(bwaflow_hot_batch_t *b, int64_t *n_exact);   /* as bwaflow_c2a_exact_reads, after bwaflow_hot_collect */
+int bwaflow_hot_second_round(bwaflow_hot_batch_t *b, int64_t *n_reads, int64_t *n_jobs);   /* as bwaflow_c2a_second_round */
 int bwaflow_hot_rerun_counted(bwaflow_hot_batch_t *b); /* same on the counting instances of stage 2 (timing.smem_blocks) and stage 4 (timing.cells, as bwaflow_c2a_rerun_counted) */
 int bwaflow_hot_collect(bwaflow_hot_batch_t *b, const bwaflow_alnreg_t **regs, const int64_t **reg_off, int64_t *n_regs,
                         bwaflow_hot_timing_t *timing);
