@@ -26,9 +26,10 @@ struct Chain {
   int64_t pos;
   int n, rid, head, tail;                                       // seeds: singly linked list in the read's pool
   int w, kept, first, is_alt;
-};                                                              // 40 B
+  int beg, end;                                                 // query span, filled by chain_flt (chn_beg / chn_end, bwa/bwamem.c:40-41)
+};                                                              // 48 B
 constexpr int BT_T = 5, BT_MAXK = 2 * BT_T - 1;                 // kb_init(chn, 512): t = ((512-4-8)/(8+40)+1)>>1
-struct Node { int internal, n; int key[BT_MAXK]; int ptr[BT_MAXK + 1]; };   // 84 B
+struct Node { int internal, n; int key[BT_MAXK]; int ptr[BT_MAXK + 1]; int64_t kpos[BT_MAXK]; };   // kpos[i] = chains[key[i]].pos, kept beside the key: one load per probe instead of two dependent ones
 
 struct Scratch {
   SeedNode *seeds; Chain *chains; Node *nodes; int *order; Chain *sorted; int *kept;
@@ -72,10 +73,10 @@ BF_HD int bt_find(const Scratch &S, const Node &x, int64_t k, int *r)
   int begin = 0, end = x.n;
   while (begin < end) {
     const int mid = (begin + end) >> 1;
-    if (S.chains[x.key[mid]].pos < k) begin = mid + 1; else end = mid;
+    if (x.kpos[mid] < k) begin = mid + 1; else end = mid;
   }
   if (begin == x.n) { *r = 1; return x.n - 1; }
-  const int64_t kp = S.chains[x.key[begin]].pos;
+  const int64_t kp = x.kpos[begin];
   *r = (kp < k) - (k < kp);
   if (*r < 0) --begin;
   return begin;
@@ -108,13 +109,13 @@ BF_HD void bt_split(Scratch &S, int xi, int i, int yi)
   const int zi = bt_new_node(S, S.nodes[yi].internal);
   Node &x = S.nodes[xi], &y = S.nodes[yi], &z = S.nodes[zi];
   z.n = BT_T - 1;
-  for (int j = 0; j < BT_T - 1; ++j) z.key[j] = y.key[BT_T + j];
+  for (int j = 0; j < BT_T - 1; ++j) { z.key[j] = y.key[BT_T + j]; z.kpos[j] = y.kpos[BT_T + j]; }
   if (y.internal) for (int j = 0; j < BT_T; ++j) z.ptr[j] = y.ptr[BT_T + j];
   y.n = BT_T - 1;
   for (int j = x.n; j > i; --j) x.ptr[j + 1] = x.ptr[j];
   x.ptr[i + 1] = zi;
-  for (int j = x.n - 1; j >= i; --j) x.key[j + 1] = x.key[j];
-  x.key[i] = y.key[BT_T - 1];
+  for (int j = x.n - 1; j >= i; --j) { x.key[j + 1] = x.key[j]; x.kpos[j + 1] = x.kpos[j]; }
+  x.key[i] = y.key[BT_T - 1]; x.kpos[i] = y.kpos[BT_T - 1];
   ++x.n;
 }
 // kb_putp
@@ -134,15 +135,15 @@ BF_HD void bt_put(Scratch &S, int c)
     Node &x = S.nodes[xi];
     if (!x.internal) {
       const int i = bt_find(S, x, k, &r);
-      for (int j = x.n - 1; j > i; --j) x.key[j + 1] = x.key[j];
-      x.key[i + 1] = c;
+      for (int j = x.n - 1; j > i; --j) { x.key[j + 1] = x.key[j]; x.kpos[j + 1] = x.kpos[j]; }
+      x.key[i + 1] = c; x.kpos[i + 1] = k;
       ++x.n;
       return;
     }
     int i = bt_find(S, x, k, &r) + 1;
     if (S.nodes[x.ptr[i]].n == BT_MAXK) {
       bt_split(S, xi, i, x.ptr[i]);
-      if (k > S.chains[S.nodes[xi].key[i]].pos) ++i;
+      if (k > S.nodes[xi].kpos[i]) ++i;
     }
     xi = S.nodes[xi].ptr[i];
   }
@@ -279,6 +280,7 @@ BF_HD int chain_flt(Scratch &S, const bwaflow_chain_opt_t &o, int n_chn)
     Chain &c = a[i];
     c.first = -1; c.kept = 0;
     c.w = chain_weight(S, c);
+    c.beg = chn_beg(S, c); c.end = chn_end(S, c);
     if (c.w >= o.min_chain_weight) a[k++] = c;
   }
   n_chn = k;
@@ -288,16 +290,17 @@ BF_HD int chain_flt(Scratch &S, const bwaflow_chain_opt_t &o, int n_chn)
   a[0].kept = 3; S.kept[n_kept++] = 0;
   for (i = 1; i < n_chn; ++i) {
     int large_ovlp = 0, kk;
+    const int bi = a[i].beg, ei = a[i].end, wi = a[i].w, alt_i = a[i].is_alt;
     for (kk = 0; kk < n_kept; ++kk) {
       const int j = S.kept[kk];
-      const int bi = chn_beg(S, a[i]), bj = chn_beg(S, a[j]), ei = chn_end(S, a[i]), ej = chn_end(S, a[j]);
+      const int bj = a[j].beg, ej = a[j].end;
       const int b_max = bj > bi ? bj : bi, e_min = ej < ei ? ej : ei;
-      if (e_min > b_max && (!a[j].is_alt || a[i].is_alt)) {
+      if (e_min > b_max && (!a[j].is_alt || alt_i)) {
         const int li = ei - bi, lj = ej - bj, min_l = li < lj ? li : lj;
         if (e_min - b_max >= min_l * o.mask_level && min_l < o.max_chain_gap) {
           large_ovlp = 1;
           if (a[j].first < 0) a[j].first = i;
-          if (a[i].w < a[j].w * o.drop_ratio && a[j].w - a[i].w >= o.min_seed_len << 1) break;
+          if (wi < a[j].w * o.drop_ratio && a[j].w - wi >= o.min_seed_len << 1) break;
         }
       }
     }
