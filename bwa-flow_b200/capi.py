@@ -22,7 +22,12 @@ EXT_JOB = np.dtype([("qlen", "<i4"), ("tlen", "<i4"), ("w", "<i4"), ("h0", "<i4"
                     ("zdrop", "<i4"), ("q_off", "<i8"), ("t_off", "<i8")])
 EXT_RES = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"), ("gscore", "<i4"),
                     ("max_off", "<i4")])
+SW_JOB = np.dtype([("qlen", "<i4"), ("tlen", "<i4"), ("xtra", "<i4"), ("pad", "<i4"), ("q_off", "<i8"), ("t_off", "<i8")])
+SW_RES = np.dtype([("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"), ("tb", "<i4"), ("qb", "<i4")])
+PESTAT = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("pad", "<i4"), ("avg", "<f8"), ("std", "<f8")])
+KSW_XBYTE, KSW_XSTOP, KSW_XSUBO, KSW_XSTART = 0x10000, 0x20000, 0x40000, 0x80000
 assert EXT_JOB.itemsize == 40 and EXT_RES.itemsize == 24 and ALNREG.itemsize == 88
+assert SW_JOB.itemsize == 32 and SW_RES.itemsize == 28 and PESTAT.itemsize == 32
 
 
 class Index(C.Structure):
@@ -41,6 +46,11 @@ class Opt(C.Structure):
 class ChainOpt(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("w", "max_chain_gap", "min_chain_weight", "max_chain_extend", "min_seed_len", "max_occ")] + \
                [("mask_level", C.c_float), ("drop_ratio", C.c_float)]
+
+
+class PeOpt(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("pen_unpaired", "max_matesw", "max_ins", "max_chain_gap")] + \
+               [("mask_level", C.c_float), ("mask_level_redun", C.c_float), ("no_rescue", C.c_int32), ("_pad", C.c_int32)]
 
 
 class Timing(C.Structure):
@@ -263,6 +273,95 @@ class ExtBatch:
     def close(self):
         if self.h:
             self.L.bwaflow_ext_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class SwBatch:
+    """Batch of raw ksw_align2 jobs (local SW with second-best score and start, bwa/ksw.c:343-365)."""
+
+    def __init__(self, ctx: Context, max_jobs, max_qbytes, max_tbytes):
+        self.L = ctx.L
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        self.L.bwaflow_sw_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
+        self.L.bwaflow_sw_submit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        self.L.bwaflow_sw_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(Timing)]
+        self.L.bwaflow_sw_batch_destroy.argtypes = [C.c_void_p]
+        check(self.L.bwaflow_sw_batch_create(ctx.h, max_jobs, max_qbytes, max_tbytes, C.byref(self.h)))
+        self.n = 0
+
+    def submit(self, jobs, qpool, tpool):
+        assert jobs.dtype == SW_JOB
+        self._keep = (jobs, qpool, tpool)
+        self.n = len(jobs)
+        check(self.L.bwaflow_sw_submit(self.h, len(jobs), _p(jobs), _p(qpool), len(qpool), _p(tpool), len(tpool)))
+
+    def collect(self):
+        out = C.c_void_p()
+        t = Timing()
+        check(self.L.bwaflow_sw_collect(self.h, C.byref(out), C.byref(t)))
+        return _view(out.value, self.n, SW_RES), t
+
+    def close(self):
+        if self.h:
+            self.L.bwaflow_sw_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def default_pe_opt():
+    po = PeOpt()
+    lib().bwaflow_pe_opt_default(C.byref(po))
+    return po
+
+
+def pestat(opt, po, l_pac, regs, reg_off):
+    """mem_pestat over one batch (host code of the library): returns PESTAT[4]."""
+    L = lib()
+    L.bwaflow_pestat.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    regs = np.ascontiguousarray(regs, dtype=ALNREG)
+    reg_off = np.ascontiguousarray(reg_off, dtype=np.int64)
+    pes = np.zeros(4, dtype=PESTAT)
+    check(L.bwaflow_pestat(C.byref(opt), C.byref(po), l_pac, len(reg_off) - 1, _p(regs), _p(reg_off), _p(pes)))
+    return pes
+
+
+class MateswBatch:
+    """The mate-rescue block of mem_sam_pe for a batch of pairs (bwaflow_matesw_*)."""
+
+    def __init__(self, ctx: Context, max_reads, max_bases, po=None):
+        self.L = ctx.L
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        L = self.L
+        L.bwaflow_matesw_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.bwaflow_matesw_submit.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5
+        L.bwaflow_matesw_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                             C.POINTER(C.c_int64), C.POINTER(Timing)]
+        L.bwaflow_matesw_batch_destroy.argtypes = [C.c_void_p]
+        check(L.bwaflow_matesw_batch_create(ctx.h, max_reads, max_bases, C.byref(po) if po is not None else None, C.byref(self.h)))
+        self.n = 0
+
+    def submit(self, bases, read_off, regs, reg_off, pes):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        regs = np.ascontiguousarray(regs, dtype=ALNREG)
+        reg_off = np.ascontiguousarray(reg_off, dtype=np.int64)
+        pes = np.ascontiguousarray(pes, dtype=PESTAT)
+        self._keep = (bases, read_off, regs, reg_off, pes)
+        self.n = len(read_off) - 1
+        check(self.L.bwaflow_matesw_submit(self.h, self.n, _p(bases), _p(read_off), _p(regs), _p(reg_off), _p(pes)))
+
+    def collect(self):
+        regs, off = C.c_void_p(), C.c_void_p()
+        n, nsw, nj = C.c_int64(), C.c_int64(), C.c_int64()
+        t = Timing()
+        check(self.L.bwaflow_matesw_collect(self.h, C.byref(regs), C.byref(off), C.byref(n), C.byref(nsw), C.byref(nj), C.byref(t)))
+        return {"alnreg": np.array(_view(regs.value, n.value, ALNREG)), "alnreg_off": np.array(_view(off.value, self.n + 1, np.dtype("<i8"))),
+                "n_sw": nsw.value, "n_jobs": nj.value, "timing": t}
+
+    def close(self):
+        if self.h:
+            self.L.bwaflow_matesw_batch_destroy(self.h)
             self.h = C.c_void_p()
 
 

@@ -77,6 +77,10 @@ ExtDeviceView ext_device_view(bwaflow_ext_batch_t *b);
 int ext_launch_device(bwaflow_ext_batch_t *b, int64_t n_jobs, cudaStream_t st);
 void ext_set_pair_classes(bwaflow_ext_batch_t *b, int n);   // qlen classes below n run on the packed engine
 void ext_set_order_rows(bwaflow_ext_batch_t *b, int on);    // queue order by estimated lifetime first (see ext_key_kernel)
+// sw.cu: a ksw_align2 batch driven from the device side of another stage (matesw.cu)
+struct SwDeviceView { bwaflow_sw_job_t *jobs; uint8_t *q, *t; bwaflow_sw_result_t *out; int *d_ctl, *h_ctl; };
+SwDeviceView sw_device_view(bwaflow_sw_batch_t *b);
+int sw_launch_device(bwaflow_sw_batch_t *b, int64_t n_jobs, int max_qlen, int max_tlen, cudaStream_t st);
 // smem_fast.cu
 struct SmemArgs;
 int smem_fast_launch(bwaflow_smem_batch *b, const SmemArgs &a, bool text, bool count);

@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "../../include/bwaflow_cuda.h"
+#include "klib_sort.h"
 
 #ifdef __CUDACC__
 #define BF_HD __host__ __device__ __forceinline__
@@ -209,63 +210,7 @@ BF_HD int chain_weight(const Scratch &S, const Chain &c)
 }
 
 // ---- bwa/ksort.h:140-232 for KSORT_INIT(mem_flt, mem_chain_t, flt_lt), flt_lt(a,b) = a.w > b.w ---------------------
-#define BF_FLT_LT(a, b) ((a).w > (b).w)
-BF_HD void flt_insertsort(Chain *s, Chain *t)
-{
-  for (Chain *i = s + 1; i < t; ++i)
-    for (Chain *j = i; j > s && BF_FLT_LT(*j, *(j - 1)); --j) { const Chain tmp = *j; *j = *(j - 1); *(j - 1) = tmp; }
-}
-BF_HD void flt_combsort(int64_t n, Chain *a)
-{
-  const double shrink = 1.2473309501039786540366528676643;
-  int do_swap; int64_t gap = n;
-  do {
-    if (gap > 2) { gap = (int64_t)(gap / shrink); if (gap == 9 || gap == 10) gap = 11; }
-    do_swap = 0;
-    for (Chain *i = a; i < a + n - gap; ++i) {
-      Chain *j = i + gap;
-      if (BF_FLT_LT(*j, *i)) { const Chain tmp = *i; *i = *j; *j = tmp; do_swap = 1; }
-    }
-  } while (do_swap || gap > 2);
-  if (gap != 1) flt_insertsort(a, a + n);
-}
-BF_HD void flt_introsort(int64_t n, Chain *a)
-{
-  if (n < 1) return;
-  if (n == 2) { if (BF_FLT_LT(a[1], a[0])) { const Chain t = a[0]; a[0] = a[1]; a[1] = t; } return; }
-  int d;
-  for (d = 2; (1ll << d) < n; ++d) {}
-  Chain *sl[64], *sr[64]; int sd[64]; int top = 0;   // the larger half is pushed, the smaller iterated: depth <= log2 n
-  Chain *s = a, *t = a + (n - 1), *i, *j, *k;
-  d <<= 1;
-  for (;;) {
-    if (s < t) {
-      if (--d == 0) { flt_combsort(t - s + 1, s); t = s; continue; }
-      i = s; j = t; k = i + ((j - i) >> 1) + 1;
-      if (BF_FLT_LT(*k, *i)) { if (BF_FLT_LT(*k, *j)) k = j; }
-      else k = BF_FLT_LT(*j, *i) ? i : j;
-      const Chain rp = *k;
-      if (k != t) { const Chain tmp = *k; *k = *t; *t = tmp; }
-      for (;;) {
-        do ++i; while (BF_FLT_LT(*i, rp));
-        do --j; while (i <= j && BF_FLT_LT(rp, *j));
-        if (j <= i) break;
-        const Chain tmp = *i; *i = *j; *j = tmp;
-      }
-      { const Chain tmp = *i; *i = *t; *t = tmp; }
-      if (i - s > t - i) {
-        if (i - s > 16) { sl[top] = s; sr[top] = i - 1; sd[top] = d; ++top; }
-        s = t - i > 16 ? i + 1 : t;
-      } else {
-        if (t - i > 16) { sl[top] = i + 1; sr[top] = t; sd[top] = d; ++top; }
-        t = i - s > 16 ? i - 1 : s;
-      }
-    } else {
-      if (top == 0) { flt_insertsort(a, a + n); return; }
-      --top; s = sl[top]; t = sr[top]; d = sd[top];
-    }
-  }
-}
+struct FltLt { BF_HD bool operator()(const Chain &a, const Chain &b) const { return a.w > b.w; } };   // flt_lt, bwa/bwamem.c:334
 
 BF_HD int chn_beg(const Scratch &S, const Chain &c) { return S.seeds[c.head].s.qbeg; }
 BF_HD int chn_end(const Scratch &S, const Chain &c) { return S.seeds[c.tail].s.qbeg + S.seeds[c.tail].s.len; }
@@ -285,7 +230,7 @@ BF_HD int chain_flt(Scratch &S, const bwaflow_chain_opt_t &o, int n_chn)
   }
   n_chn = k;
   if (n_chn == 0) return 0;
-  flt_introsort(n_chn, a);
+  klib_introsort(n_chn, a, FltLt());
   int n_kept = 0;
   a[0].kept = 3; S.kept[n_kept++] = 0;
   for (i = 1; i < n_chn; ++i) {

@@ -207,6 +207,8 @@ static int ctx_init(bwaflow_ctx_t *c, int device, const cudaDeviceProp &prop, co
     if ((r = upload(&c->d_sa, idx->sa, (size_t)idx->n_sa * 8))) return r;
     if ((r = upload(&c->d_pac, idx->pac, (size_t)(idx->l_pac / 4 + 1)))) return r;
     if ((r = upload(&c->d_ctg_off, idx->ctg_offset, (size_t)idx->n_seqs * 8))) return r;
+    c->h_ctg_off = (int64_t *)malloc((size_t)idx->n_seqs * 8); c->h_ctg_len = (int32_t *)malloc((size_t)idx->n_seqs * 4);
+    memcpy(c->h_ctg_off, idx->ctg_offset, (size_t)idx->n_seqs * 8); memcpy(c->h_ctg_len, idx->ctg_len, (size_t)idx->n_seqs * 4);
     if ((r = upload(&c->d_ctg_len, idx->ctg_len, (size_t)idx->n_seqs * 4))) return r;
     {
       // re-lay the occurrence array out for the device (occ32), then drop the upload of bwa's layout
@@ -347,6 +349,7 @@ void bwaflow_ctx_destroy(bwaflow_ctx_t *c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
+  free(c->h_ctg_off); free(c->h_ctg_len);
   cudaFree(c->d_bwt); cudaFree(c->d_sa); cudaFree(c->d_text); cudaFree(c->d_ktab); cudaFree(c->d_pac); cudaFree(c->d_ctg_off); cudaFree(c->d_ctg_len);
   free(c);
 }

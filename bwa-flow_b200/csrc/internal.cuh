@@ -78,6 +78,8 @@ struct bwaflow_ctx {
   bwaflow::Params par;
   // owned device allocations
   void *d_bwt, *d_sa, *d_pac, *d_ctg_off, *d_ctg_len, *d_text, *d_ktab;
+  // host copies of the contig table (bns->anns[].offset / .len) for the host halves of the pairing stages
+  int64_t *h_ctg_off; int32_t *h_ctg_len;
 };
 
 namespace bwaflow {

@@ -217,6 +217,43 @@ int bwaflow_hot_rerun_counted(bwaflow_hot_batch_t *b); /* same on the counting i
 int bwaflow_hot_collect(bwaflow_hot_batch_t *b, const bwaflow_alnreg_t **regs, const int64_t **reg_off, int64_t *n_regs,
                         bwaflow_hot_timing_t *timing);
 
+/* ---- mate rescue (stage 5) ------------------------------------------------------------------------
+ *      ksw_align2 (bwa/ksw.c:343-365 over ksw_u8 / ksw_i16 :110-339): local Smith-Waterman of a whole query against a target
+ *      window, second-best score, start by the reversed pass.  xtra as in bwa/ksw.h:6-9: KSW_XBYTE 0x10000, KSW_XSTOP 0x20000,
+ *      KSW_XSUBO 0x40000, KSW_XSTART 0x80000, low 16 bits = the threshold.  Scoring matrix and gap costs are the context's. */
+typedef struct { int32_t qlen, tlen, xtra, _pad; int64_t q_off, t_off; } bwaflow_sw_job_t;
+typedef struct { int32_t score, te, qe, score2, te2, tb, qb; } bwaflow_sw_result_t;       /* kswr_t, bwa/ksw.h:14-20 */
+typedef struct bwaflow_sw_batch bwaflow_sw_batch_t;
+int bwaflow_sw_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_qbytes, int64_t max_tbytes, bwaflow_sw_batch_t **out);
+void bwaflow_sw_batch_destroy(bwaflow_sw_batch_t *b);
+int bwaflow_sw_submit(bwaflow_sw_batch_t *b, int64_t n_jobs, const bwaflow_sw_job_t *jobs, const uint8_t *qpool, int64_t qbytes,
+                      const uint8_t *tpool, int64_t tbytes);
+int bwaflow_sw_collect(bwaflow_sw_batch_t *b, const bwaflow_sw_result_t **out, bwaflow_timing_t *timing);
+
+/* mem_pestat_t, bwa/bwamem.h:80-86 (32 B, identical layout) */
+typedef struct { int32_t low, high, failed, _pad; double avg, std; } bwaflow_pestat_t;
+/* the mem_opt_t fields the pairing steps read besides bwaflow_opt_t (defaults bwa/bwamem.c:59-78) */
+typedef struct { int32_t pen_unpaired, max_matesw, max_ins, max_chain_gap; float mask_level, mask_level_redun; int32_t no_rescue, _pad; } bwaflow_pe_opt_t;
+void bwaflow_pe_opt_default(bwaflow_pe_opt_t *po);
+/* mem_pestat (bwa/bwamem_pair.c:49-112) over the regions of one whole batch (src/Pipeline.cpp:578-579): reads 2k and 2k+1 are
+ * mates, regions of read r = regs[reg_off[r] .. reg_off[r+1]) after mem_sort_dedup_patch.  Host code. */
+int bwaflow_pestat(const bwaflow_opt_t *opt, const bwaflow_pe_opt_t *po, int64_t l_pac, int64_t n_reads, const bwaflow_alnreg_t *regs,
+                   const int64_t *reg_off, bwaflow_pestat_t pes[4]);
+/* The rescue block of mem_sam_pe (src/bwa_wrapper.cpp:657-668) for every pair of a batch: mem_matesw (bwa/bwamem_pair.c:114-183)
+ * for the up-to-max_matesw best regions of either end against the mate.  Every window any of those calls can ask for is aligned on
+ * the device ahead of time (ksw_align2 kernel); collect then replays the calls in the reference's order on the host -- which
+ * windows are skipped depends on the hits rescued so far -- inserting hits and re-running mem_sort_dedup_patch (no patching, as
+ * mem_matesw calls it) exactly as the reference does.  Input regions: after mem_sort_dedup_patch + ALT marking
+ * (src/Pipeline.cpp:560-575).  Output: the regions mem_mark_primary_se / mem_pair see.  *n_sw = sum of mem_matesw's return values. */
+typedef struct bwaflow_matesw_batch bwaflow_matesw_batch_t;
+int bwaflow_matesw_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_bases, const bwaflow_pe_opt_t *po,
+                                bwaflow_matesw_batch_t **out);
+void bwaflow_matesw_batch_destroy(bwaflow_matesw_batch_t *b);
+int bwaflow_matesw_submit(bwaflow_matesw_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off,
+                          const bwaflow_alnreg_t *regs, const int64_t *reg_off, const bwaflow_pestat_t pes[4]);
+int bwaflow_matesw_collect(bwaflow_matesw_batch_t *b, const bwaflow_alnreg_t **regs, const int64_t **reg_off, int64_t *n_regs,
+                           int64_t *n_sw, int64_t *n_jobs, bwaflow_timing_t *timing);
+
 /* ---- index construction for synthetic references (workload preparation; the arrays equal what `bwa index`
  *      + bwa_idx_load leave in memory, bwa/bwtindex.c:256-324).  codes: 0..3 = ACGT, >=4 = N, contigs concatenated. */
 typedef struct bwaflow_built_index bwaflow_built_index_t;

@@ -94,6 +94,12 @@ def ref_lib():
         L.bwaref_batch_seq2chains.argtypes = [C.c_void_p]
         L.bwaref_batch_chainspipe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bwaref_batch_chains2regions.argtypes = [C.c_void_p]
+        L.bwaref_batch_dedup_pestat.argtypes = [C.c_void_p, C.c_void_p]
+        L.bwaref_batch_matesw.argtypes = [C.c_void_p]
+        L.bwaref_batch_matesw.restype = C.c_int64
+        L.bwaref_swhook_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bwaref_swhook_count.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.bwaref_swhook_count.restype = C.c_int64
         L.bwaref_batch_set_regions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _ref = L
     return _ref
@@ -232,8 +238,40 @@ class Ref:
         self.L.bwaref_hook_fetch(_p(jobs), _p(q), _p(t))
         return jobs, q[:qb.value], t[:tb.value]
 
+    def swhook_begin(self):
+        self.L.bwaref_swhook_begin()
+
+    def swhook_end(self):
+        """-> (jobs[SWJOB] with their kswr_t, query pool, target pool): the ksw_align2 calls of mem_matesw since swhook_begin."""
+        self.L.bwaref_swhook_end()
+        qb, tb = C.c_int64(), C.c_int64()
+        self.L.bwaref_swhook_count.restype = C.c_int64
+        n = self.L.bwaref_swhook_count(C.byref(qb), C.byref(tb))
+        jobs = np.zeros(n, dtype=SWJOB)
+        q = np.zeros(max(qb.value, 1), dtype=np.uint8)
+        t = np.zeros(max(tb.value, 1), dtype=np.uint8)
+        self.L.bwaref_swhook_fetch(_p(jobs), _p(q), _p(t))
+        return jobs, q[:qb.value], t[:tb.value]
+
     def batch(self, reads, start_idx=0):
         return RefBatch(self, reads, start_idx)
+
+
+SWJOB = np.dtype([("qlen", "<i4"), ("tlen", "<i4"), ("xtra", "<i4"), ("pad", "<i4"), ("q_off", "<i8"), ("t_off", "<i8"),
+                  ("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"), ("tb", "<i4"), ("qb", "<i4"), ("pad2", "<i4")])
+PES = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("pad", "<i4"), ("avg", "<f8"), ("std", "<f8")])
+
+
+def ref_ksw_align2(query, target, mat, o_del, e_del, o_ins, e_ins, xtra):
+    """the reference's ksw_align2 (bwa/ksw.c:343-365) -> [score, te, qe, score2, te2, tb, qb]"""
+    q = np.array(query, dtype=np.uint8)
+    t = np.array(target, dtype=np.uint8)
+    m = np.ascontiguousarray(mat, dtype=np.int8)
+    out = np.zeros(7, dtype=np.int32)
+    L = ref_lib()
+    L.bwaref_ksw_align2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+    L.bwaref_ksw_align2(len(q), _p(q), len(t), _p(t), _p(m), o_del, e_del, o_ins, e_ins, xtra, _p(out))
+    return out
 
 
 def ref_ksw_extend2(query, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0):
@@ -301,6 +339,20 @@ class RefBatch:
 
     def regions(self):
         return self._two(self.L.bwaref_batch_regions, ALNREG)
+
+    def dedup_pestat(self):
+        """stage 5, first part: mem_sort_dedup_patch + ALT marking of every read, then mem_pestat over the batch -> PES[4]"""
+        out = np.zeros(20, dtype=np.float64)
+        self.L.bwaref_batch_dedup_pestat(self.h, _p(out))
+        pes = np.zeros(4, dtype=PES)
+        for d in range(4):
+            pes[d] = (int(out[d * 5]), int(out[d * 5 + 1]), int(out[d * 5 + 2]), 0, out[d * 5 + 3], out[d * 5 + 4])
+        return pes
+
+    def matesw(self):
+        """stage 5, second part: the rescue block of mem_sam_pe for every pair -> sum of mem_matesw's return values"""
+        self.L.bwaref_batch_matesw.restype = C.c_int64
+        return self.L.bwaref_batch_matesw(self.h)
 
     def regions2sam(self):
         a, b = C.c_void_p(), C.c_void_p()

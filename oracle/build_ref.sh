@@ -29,6 +29,7 @@ for f in utils kthread kstring ksw bwt bntseq bwa bwamem bwamem_pair bwamem_extr
          QSufSort bwt_gen rope rle is bwtindex kopen; do
   extra=""
   [ "$f" = bwamem ] && extra="-Dksw_extend2=bwaref_ksw_hook"
+  [ "$f" = bwamem_pair ] && extra="-Dksw_align2=bwaref_sw_hook"
   gcc -c $CFLAGS $extra "$REF/bwa/$f.c" -o "$OBJ/$f.o" &
   pids+=($!)
 done

@@ -88,6 +88,34 @@ extern "C" int bwaref_ksw_hook(int qlen, const uint8_t *query, int tlen, const u
   return sc;
 }
 
+// ---- ksw_align2 observation hook (mem_matesw's calls; bwamem_pair.c is compiled with -Dksw_align2=bwaref_sw_hook) -------------
+struct flat_swjob_t {                     // one observed ksw_align2 call and its kswr_t
+  int32_t qlen, tlen, xtra, pad;
+  int64_t q_off, t_off;
+  int32_t score, te, qe, score2, te2, tb, qb, pad2;
+};
+struct swhook_state_t { bool on = false; std::vector<flat_swjob_t> jobs; std::vector<uint8_t> qpool, tpool; };
+static thread_local swhook_state_t g_swhook;
+extern "C" kswr_t ksw_align2(int qlen, uint8_t *query, int tlen, uint8_t *target, int m, const int8_t *mat, int o_del, int e_del, int o_ins,
+                             int e_ins, int xtra, kswq_t **qry);
+extern "C" kswr_t bwaref_sw_hook(int qlen, uint8_t *query, int tlen, uint8_t *target, int m, const int8_t *mat, int o_del, int e_del,
+                                 int o_ins, int e_ins, int xtra, kswq_t **qry)
+{
+  flat_swjob_t j;
+  if (g_swhook.on) {
+    j.qlen = qlen; j.tlen = tlen; j.xtra = xtra; j.pad = j.pad2 = 0;
+    j.q_off = (int64_t)g_swhook.qpool.size(); j.t_off = (int64_t)g_swhook.tpool.size();
+    g_swhook.qpool.insert(g_swhook.qpool.end(), query, query + qlen);
+    g_swhook.tpool.insert(g_swhook.tpool.end(), target, target + tlen);
+  }
+  kswr_t r = ksw_align2(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, xtra, qry);
+  if (g_swhook.on) {
+    j.score = r.score; j.te = r.te; j.qe = r.qe; j.score2 = r.score2; j.te2 = r.te2; j.tb = r.tb; j.qb = r.qb;
+    g_swhook.jobs.push_back(j);
+  }
+  return r;
+}
+
 // ---- handle ------------------------------------------------------------------
 struct ref_t {
   bwaidx_t *idx;
@@ -103,6 +131,7 @@ struct batch_t {
   mem_chain_v *chains;     // stage-2 output (owned until consumed by stage 4)
   mem_alnreg_v *alnreg;    // stage-4 output
   bool nt4;
+  mem_pestat_t pes[4]; bool have_pes;
   // flat export scratch
   std::vector<bwtintv_t> intv; std::vector<int64_t> intv_off;
   std::vector<flat_chain_t> fchains; std::vector<flat_seed_t> fseeds; std::vector<int64_t> chain_off;
@@ -446,6 +475,74 @@ int64_t bwaref_batch_regions2sam(void *hb, const char **sam, const int64_t **off
   }
   *sam = b->sam.data(); *off = b->sam_off.data();
   return (int64_t)b->sam.size();
+}
+
+// ---- pieces of stage 5 taken one at a time (RegionsToSam::compute, src/Pipeline.cpp:560-604) -------------------------------------
+// (1) mem_sort_dedup_patch + ALT marking of every read (:560-575), then mem_pestat over the whole batch (:578-579).
+//     pes_out: 4 x {low, high, failed, avg, std} as doubles.
+void bwaref_batch_dedup_pestat(void *hb, double *pes_out)
+{
+  batch_t *b = (batch_t *)hb;
+  const mem_opt_t *opt = b->ref->opt; const bwaidx_t *idx = b->ref->idx;
+  batch_nt4(b);
+  for (int i = 0; i < b->n; ++i) {
+    b->alnreg[i].n = mem_sort_dedup_patch(opt, idx->bns, idx->pac, (uint8_t *)b->seqs[i].seq, (int)b->alnreg[i].n, b->alnreg[i].a);
+    for (size_t j = 0; j < b->alnreg[i].n; ++j) {
+      mem_alnreg_t *p = &b->alnreg[i].a[j];
+      if (p->rid >= 0 && idx->bns->anns[p->rid].is_alt) p->is_alt = 1;
+    }
+  }
+  mem_pestat(opt, idx->bns->l_pac, b->n, b->alnreg, b->pes);
+  b->have_pes = true;
+  for (int d = 0; d < 4; ++d) {
+    pes_out[d * 5 + 0] = b->pes[d].low; pes_out[d * 5 + 1] = b->pes[d].high; pes_out[d * 5 + 2] = b->pes[d].failed;
+    pes_out[d * 5 + 3] = b->pes[d].avg; pes_out[d * 5 + 4] = b->pes[d].std;
+  }
+}
+
+// (2) the mate-rescue block of mem_sam_pe (src/bwa_wrapper.cpp:657-668) for every pair, calling the reference's own mem_matesw.
+//     Returns the sum of its return values; the regions afterwards are read with bwaref_batch_regions.
+extern "C" int mem_matesw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4], const mem_alnreg_t *a,
+                          int l_ms, const uint8_t *ms, mem_alnreg_v *ma);
+int64_t bwaref_batch_matesw(void *hb)
+{
+  batch_t *b = (batch_t *)hb;
+  const mem_opt_t *opt = b->ref->opt; const bwaidx_t *idx = b->ref->idx;
+  int64_t n = 0;
+  if (!b->have_pes) return -1;
+  for (int pr = 0; pr < b->n / 2; ++pr) {
+    bseq1_t *s = &b->seqs[pr << 1]; mem_alnreg_v *a = &b->alnreg[pr << 1];
+    if (opt->flag & MEM_F_NO_RESCUE) continue;
+    mem_alnreg_v bb[2];
+    kv_init(bb[0]); kv_init(bb[1]);
+    for (int i = 0; i < 2; ++i)
+      for (size_t j = 0; j < a[i].n; ++j)
+        if (a[i].a[j].score >= a[i].a[0].score - opt->pen_unpaired) kv_push(mem_alnreg_t, bb[i], a[i].a[j]);
+    for (int i = 0; i < 2; ++i)
+      for (size_t j = 0; j < bb[i].n && (int)j < opt->max_matesw; ++j)
+        n += mem_matesw(opt, idx->bns, idx->pac, b->pes, &bb[i].a[j], s[!i].l_seq, (uint8_t *)s[!i].seq, &a[!i]);
+    free(bb[0].a); free(bb[1].a);
+  }
+  return n;
+}
+
+// ksw_align2 as the library exports it (query / target are restored by the function itself)
+void bwaref_ksw_align2(int qlen, uint8_t *query, int tlen, uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
+                       int xtra, int out[7])
+{
+  kswr_t r = ksw_align2(qlen, query, tlen, target, 5, mat, o_del, e_del, o_ins, e_ins, xtra, 0);
+  out[0] = r.score; out[1] = r.te; out[2] = r.qe; out[3] = r.score2; out[4] = r.te2; out[5] = r.tb; out[6] = r.qb;
+}
+
+void bwaref_swhook_begin(void) { g_swhook.on = true; g_swhook.jobs.clear(); g_swhook.qpool.clear(); g_swhook.tpool.clear(); }
+void bwaref_swhook_end(void) { g_swhook.on = false; }
+int64_t bwaref_swhook_count(int64_t *qbytes, int64_t *tbytes)
+{ *qbytes = (int64_t)g_swhook.qpool.size(); *tbytes = (int64_t)g_swhook.tpool.size(); return (int64_t)g_swhook.jobs.size(); }
+void bwaref_swhook_fetch(flat_swjob_t *jobs, uint8_t *q, uint8_t *t)
+{
+  if (!g_swhook.jobs.empty()) memcpy(jobs, g_swhook.jobs.data(), g_swhook.jobs.size() * sizeof(flat_swjob_t));
+  if (!g_swhook.qpool.empty()) memcpy(q, g_swhook.qpool.data(), g_swhook.qpool.size());
+  if (!g_swhook.tpool.empty()) memcpy(t, g_swhook.tpool.data(), g_swhook.tpool.size());
 }
 
 } // extern "C"
