@@ -25,6 +25,10 @@ EXT_RES = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "
 SW_JOB = np.dtype([("qlen", "<i4"), ("tlen", "<i4"), ("xtra", "<i4"), ("pad", "<i4"), ("q_off", "<i8"), ("t_off", "<i8")])
 SW_RES = np.dtype([("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"), ("tb", "<i4"), ("qb", "<i4")])
 PESTAT = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("pad", "<i4"), ("avg", "<f8"), ("std", "<f8")])
+ALN = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("flag", "<i4"), ("is_rev", "<i4"), ("is_alt", "<i4"), ("mapq", "<i4"), ("NM", "<i4"),
+                ("n_cigar", "<i4"), ("score", "<i4"), ("sub", "<i4"), ("alt_sc", "<i4"), ("global_score", "<i4"), ("pad", "<i4"),
+                ("cigar_off", "<i8"), ("md_off", "<i8")])
+assert ALN.itemsize == 72
 KSW_XBYTE, KSW_XSTOP, KSW_XSUBO, KSW_XSTART = 0x10000, 0x20000, 0x40000, 0x80000
 assert EXT_JOB.itemsize == 40 and EXT_RES.itemsize == 24 and ALNREG.itemsize == 88
 assert SW_JOB.itemsize == 32 and SW_RES.itemsize == 28 and PESTAT.itemsize == 32
@@ -50,7 +54,8 @@ class ChainOpt(C.Structure):
 
 class PeOpt(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("pen_unpaired", "max_matesw", "max_ins", "max_chain_gap")] + \
-               [("mask_level", C.c_float), ("mask_level_redun", C.c_float), ("no_rescue", C.c_int32), ("_pad", C.c_int32)]
+               [("mask_level", C.c_float), ("mask_level_redun", C.c_float), ("no_rescue", C.c_int32), ("mapq_coef_len", C.c_float),
+                ("mapq_coef_fac", C.c_int32), ("_pad", C.c_int32)]
 
 
 class Timing(C.Structure):
@@ -362,6 +367,48 @@ class MateswBatch:
     def close(self):
         if self.h:
             self.L.bwaflow_matesw_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class CigarBatch:
+    """mem_reg2aln for a batch of (read, region) jobs (bwaflow_cigar_*)."""
+
+    def __init__(self, ctx: Context, max_reads, max_bases, max_jobs, po=None):
+        self.L = ctx.L
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        L = self.L
+        L.bwaflow_cigar_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.bwaflow_cigar_submit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.bwaflow_cigar_collect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(Timing)]
+        L.bwaflow_cigar_batch_destroy.argtypes = [C.c_void_p]
+        check(L.bwaflow_cigar_batch_create(ctx.h, max_reads, max_bases, max_jobs, C.byref(po) if po is not None else None, C.byref(self.h)))
+        self.n = 0
+
+    def submit(self, bases, read_off, job_read, job_reg):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        job_read = np.ascontiguousarray(job_read, dtype=np.int32)
+        job_reg = np.ascontiguousarray(job_reg, dtype=ALNREG)
+        self._keep = (bases, read_off, job_read, job_reg)
+        self.n = len(job_read)
+        check(self.L.bwaflow_cigar_submit(self.h, len(read_off) - 1, _p(bases), _p(read_off), self.n, _p(job_read), _p(job_reg)))
+
+    def collect(self):
+        """-> (ALN[n], list of CIGAR arrays, list of MD strings, timing)"""
+        aln, cp, mp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        t = Timing()
+        check(self.L.bwaflow_cigar_collect(self.h, C.byref(aln), C.byref(cp), C.byref(mp), C.byref(t)))
+        a = np.array(_view(aln.value, self.n, ALN))
+        n_cig = int(a["cigar_off"][-1] + a["n_cigar"][-1]) if self.n else 0
+        cig = np.array(_view(cp.value, n_cig, np.dtype("<u4")))
+        cigars = [cig[a["cigar_off"][j]:a["cigar_off"][j] + a["n_cigar"][j]] for j in range(self.n)]
+        mds = [C.string_at(mp.value + int(a["md_off"][j])) for j in range(self.n)]
+        return a, cigars, mds, t
+
+    def close(self):
+        if self.h:
+            self.L.bwaflow_cigar_batch_destroy(self.h)
             self.h = C.c_void_p()
 
 

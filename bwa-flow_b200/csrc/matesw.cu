@@ -174,6 +174,7 @@ void bwaflow_pe_opt_default(bwaflow_pe_opt_t *po)
   memset(po, 0, sizeof(*po));
   po->pen_unpaired = 17; po->max_matesw = 50; po->max_ins = 10000; po->max_chain_gap = 10000;
   po->mask_level = 0.50f; po->mask_level_redun = 0.95f; po->no_rescue = 0;
+  po->mapq_coef_len = 50.f; po->mapq_coef_fac = (int)log(50.);
 }
 
 int bwaflow_pestat(const bwaflow_opt_t *opt, const bwaflow_pe_opt_t *po, int64_t l_pac, int64_t n_reads, const bwaflow_alnreg_t *regs,

@@ -233,7 +233,10 @@ int bwaflow_sw_collect(bwaflow_sw_batch_t *b, const bwaflow_sw_result_t **out, b
 /* mem_pestat_t, bwa/bwamem.h:80-86 (32 B, identical layout) */
 typedef struct { int32_t low, high, failed, _pad; double avg, std; } bwaflow_pestat_t;
 /* the mem_opt_t fields the pairing steps read besides bwaflow_opt_t (defaults bwa/bwamem.c:59-78) */
-typedef struct { int32_t pen_unpaired, max_matesw, max_ins, max_chain_gap; float mask_level, mask_level_redun; int32_t no_rescue, _pad; } bwaflow_pe_opt_t;
+typedef struct {
+  int32_t pen_unpaired, max_matesw, max_ins, max_chain_gap; float mask_level, mask_level_redun; int32_t no_rescue;
+  float mapq_coef_len; int32_t mapq_coef_fac, _pad;     /* mapQ_coef_len (float) and mapQ_coef_fac (int: log(50) truncated), bwa/bwamem.h:52-53 */
+} bwaflow_pe_opt_t;
 void bwaflow_pe_opt_default(bwaflow_pe_opt_t *po);
 /* mem_pestat (bwa/bwamem_pair.c:49-112) over the regions of one whole batch (src/Pipeline.cpp:578-579): reads 2k and 2k+1 are
  * mates, regions of read r = regs[reg_off[r] .. reg_off[r+1]) after mem_sort_dedup_patch.  Host code. */
@@ -253,6 +256,25 @@ int bwaflow_matesw_submit(bwaflow_matesw_batch_t *b, int64_t n_reads, const uint
                           const bwaflow_alnreg_t *regs, const int64_t *reg_off, const bwaflow_pestat_t pes[4]);
 int bwaflow_matesw_collect(bwaflow_matesw_batch_t *b, const bwaflow_alnreg_t **regs, const int64_t **reg_off, int64_t *n_regs,
                            int64_t *n_sw, int64_t *n_jobs, bwaflow_timing_t *timing);
+
+/* ---- CIGAR generation (stage 5): mem_reg2aln (bwa/bwamem.c:1104-1174) for a batch of (read, region) jobs --
+ *      band inference and up to three band tries, bwa_gen_cigar2 (bwa/bwa.c:121-207) with ksw_global2 (bwa/ksw.c:504-606) and its
+ *      traceback, NM and MD, the squeeze of a leading / trailing deletion, clipping, position.  One job = one call of mem_reg2aln on a
+ *      mapped region (the caller decides which regions are reported: primary, supplementary, the XA candidates of mem_gen_alt). */
+typedef struct {                                  /* mem_aln_t, bwa/bwamem.h:88-99, with the CIGAR and MD as offsets into the pools */
+  int64_t pos; int32_t rid, flag, is_rev, is_alt, mapq, NM, n_cigar, score, sub, alt_sc;
+  int32_t global_score;                           /* score of the last ksw_global2 / ungapped pass (mem_reg2aln's local `score`) */
+  int64_t cigar_off, md_off;                      /* cigar = cigar_pool + cigar_off (n_cigar words, opLen<<4|op, MIDSH = 01234); MD = md_pool + md_off, NUL-terminated */
+} bwaflow_aln_t;
+typedef struct bwaflow_cigar_batch bwaflow_cigar_batch_t;
+int bwaflow_cigar_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_bases, int64_t max_jobs, const bwaflow_pe_opt_t *po,
+                               bwaflow_cigar_batch_t **out);
+void bwaflow_cigar_batch_destroy(bwaflow_cigar_batch_t *b);
+/* job j: region job_reg[j] (as it stands when mem_reg2aln would be called: sub, csub, secondary .. filled) of read job_read[j] */
+int bwaflow_cigar_submit(bwaflow_cigar_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off, int64_t n_jobs,
+                         const int32_t *job_read, const bwaflow_alnreg_t *job_reg);
+int bwaflow_cigar_collect(bwaflow_cigar_batch_t *b, const bwaflow_aln_t **aln, const uint32_t **cigar_pool, const char **md_pool,
+                          bwaflow_timing_t *timing);
 
 /* ---- index construction for synthetic references (workload preparation; the arrays equal what `bwa index`
  *      + bwa_idx_load leave in memory, bwa/bwtindex.c:256-324).  codes: 0..3 = ACGT, >=4 = N, contigs concatenated. */

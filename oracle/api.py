@@ -274,6 +274,24 @@ def ref_ksw_align2(query, target, mat, o_del, e_del, o_ins, e_ins, xtra):
     return out
 
 
+FLAT_ALN = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("flag", "<i4"), ("is_rev", "<i4"), ("is_alt", "<i4"), ("mapq", "<i4"), ("NM", "<i4"),
+                     ("n_cigar", "<i4"), ("score", "<i4"), ("sub", "<i4"), ("alt_sc", "<i4"), ("pad", "<i4")])
+
+
+def ref_reg2aln(ref, nt4_read, reg):
+    """the reference's mem_reg2aln on one region of one read -> (FLAT_ALN record, cigar array, MD bytes)"""
+    L = ref.L
+    L.bwaref_reg2aln.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    q = np.ascontiguousarray(nt4_read, dtype=np.uint8)
+    r = np.ascontiguousarray(reg).reshape(1)
+    out = np.zeros(1, dtype=FLAT_ALN)
+    cig = np.zeros(2048, dtype=np.uint32)
+    md = np.zeros(8192, dtype=np.uint8)
+    rc = L.bwaref_reg2aln(ref.h, len(q), _p(q), _p(r), _p(out), _p(cig), len(cig), _p(md), len(md))
+    assert rc == 0
+    return out[0], cig[:out[0]["n_cigar"]].copy(), bytes(md[:int(np.argmax(md == 0))])
+
+
 def ref_ksw_extend2(query, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0):
     q = np.ascontiguousarray(query, dtype=np.uint8)
     t = np.ascontiguousarray(target, dtype=np.uint8)

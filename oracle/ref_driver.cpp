@@ -545,4 +545,23 @@ void bwaref_swhook_fetch(flat_swjob_t *jobs, uint8_t *q, uint8_t *t)
   if (!g_swhook.tpool.empty()) memcpy(t, g_swhook.tpool.data(), g_swhook.tpool.size());
 }
 
+// mem_reg2aln (bwa/bwamem.c:1104-1174) on one region: the mem_aln_t fields, the CIGAR and the MD string stored behind it.
+struct flat_aln_t { int64_t pos; int32_t rid, flag, is_rev, is_alt, mapq, NM, n_cigar, score, sub, alt_sc, pad; };
+extern "C" mem_aln_t mem_reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const char *query, const mem_alnreg_t *ar);
+int bwaref_reg2aln(void *h, int l_query, const char *query, const mem_alnreg_t *ar, flat_aln_t *out, uint32_t *cigar, int cigar_cap, char *md, int md_cap)
+{
+  ref_t *r = (ref_t *)h;
+  mem_aln_t a = mem_reg2aln(r->opt, r->idx->bns, r->idx->pac, l_query, query, ar);
+  out->pos = a.pos; out->rid = a.rid; out->flag = a.flag; out->is_rev = a.is_rev; out->is_alt = a.is_alt; out->mapq = a.mapq; out->NM = a.NM;
+  out->n_cigar = a.n_cigar; out->score = a.score; out->sub = a.sub; out->alt_sc = a.alt_sc; out->pad = 0;
+  int ok = a.n_cigar <= cigar_cap;
+  if (a.cigar) {
+    if (ok) memcpy(cigar, a.cigar, a.n_cigar * 4);
+    const char *m = (const char *)(a.cigar + a.n_cigar);
+    if ((int)strlen(m) + 1 <= md_cap) strcpy(md, m); else ok = 0;
+    free(a.cigar);
+  } else md[0] = 0;
+  return ok ? 0 : -1;
+}
+
 } // extern "C"
