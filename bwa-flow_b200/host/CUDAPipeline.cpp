@@ -6,11 +6,12 @@
 
 static void check(int rc) { if (rc) throw std::runtime_error(bwaflow_last_error()); }
 
-CUDABatchPool::CUDABatchPool(bwaflow_ctx_t *ctx, int n_batches, int64_t max_reads, int64_t max_bases)
+CUDABatchPool::CUDABatchPool(bwaflow_ctx_t *ctx, int n_batches, int64_t max_reads, int64_t max_bases, const bwaflow_chain_opt_t *copt,
+                             const int32_t *ctg_is_alt)
 {
   for (int i = 0; i < n_batches; ++i) {
     bwaflow_hot_batch_t *b = nullptr;
-    check(bwaflow_hot_batch_create(ctx, max_reads, max_bases, nullptr, nullptr, &b));
+    check(bwaflow_hot_batch_create(ctx, max_reads, max_bases, copt, ctg_is_alt, &b));
     all_.push_back(b);
     free_.push(b);
   }
@@ -23,6 +24,29 @@ bwaflow_hot_batch_t *CUDABatchPool::take()
   return b;
 }
 void CUDABatchPool::give(bwaflow_hot_batch_t *b) { free_.push(b); }
+
+CUDAEnv::CUDAEnv(const bwaflow_index_t *idx, const bwaflow_opt_t *opt, const bwaflow_chain_opt_t *copt, const int32_t *ctg_is_alt, int n_devices,
+                 int batches_per_device, int64_t max_reads, int64_t max_bases)
+    : max_reads_(max_reads), max_bases_(max_bases)
+{
+  if (copt) copt_ = *copt; else bwaflow_chain_opt_default(&copt_);
+  const int visible = bwaflow_device_count();
+  if (visible <= 0) throw std::runtime_error("CUDAEnv: no CUDA device (there is no CPU fallback on this path)");
+  if (n_devices <= 0 || n_devices > visible) n_devices = visible;
+  for (int d = 0; d < n_devices; ++d) {                        // the index is replicated: every GPU gets its own copy in HBM
+    PE pe; pe.device = d; pe.ctx = nullptr; pe.pool = nullptr;
+    check(bwaflow_ctx_create(d, idx, opt, &pe.ctx));
+    if (batches_per_device > 0) {
+      pe.pool = new CUDABatchPool(pe.ctx, batches_per_device, max_reads, max_bases, &copt_, ctg_is_alt);
+      for (auto *b : pe.pool->all()) owner_[b] = pe.pool;
+    }
+    pes_.push_back(pe);
+  }
+}
+CUDAEnv::~CUDAEnv()
+{
+  for (auto &pe : pes_) { delete pe.pool; bwaflow_ctx_destroy(pe.ctx); }
+}
 
 void SeedPositionTable::put(uint64_t start_idx, Entry &&e)
 {
@@ -47,7 +71,9 @@ static inline uint8_t nt4(char c)
 
 void SeqsToChainsCUDA::compute(int wid)
 {
-  (void)wid;
+  CUDABatchPool *pool_ = this->pool_;
+  bwaflow_ctx_t *ctx_ = this->ctx_;
+  if (env_) { CUDAEnv::PE &pe = env_->getPE(wid); pool_ = pe.pool; ctx_ = pe.ctx; }    // this worker's GPU
   std::vector<uint8_t> bases;
   std::vector<int64_t> off;
   bwaflow_smem_batch_t *smem = nullptr;                        // interval mode: this worker's SMemTask
@@ -121,9 +147,7 @@ ChainsRecord ChainsPipe::compute(ChainsRecord const &record)
   out.bwtintvs = NULL; out.bwtintv_nums = NULL;
   SeedPositionTable::Entry sp = pos_->take(record.start_idx);
   bwaflow_chain_result_t *res = nullptr;
-  bwaflow_chain_opt_t copt;
-  bwaflow_chain_opt_default(&copt);                            // from aux->opt in a bwa-flow build (w, max_chain_gap, mask_level, drop_ratio ..)
-  check(bwaflow_chain_build(&copt, ctg_->l_pac, ctg_->n_seqs, ctg_->offset, ctg_->len, nullptr, n, read_off.data(), intv.data(),
+  check(bwaflow_chain_build(&copt_, ctg_->l_pac, ctg_->n_seqs, ctg_->offset, ctg_->len, ctg_->is_alt, n, read_off.data(), intv.data(),
                             intv_off.data(), sp.pos.data(), sp.pos_off.data(), 1, &res));
   const bwaflow_chain_t *ch; const bwaflow_seed_t *sd; const int64_t *coff; int64_t n_ch, n_sd;
   bwaflow_chain_result_view(res, &ch, &n_ch, &sd, &n_sd, &coff);
@@ -151,7 +175,7 @@ ChainsRecord ChainsPipe::compute(ChainsRecord const &record)
 
 void ChainsToRegionsCUDA::compute(int wid)
 {
-  (void)wid;
+  bwaflow_ctx_t *ctx_ = env_ ? env_->getPE(wid).ctx : this->ctx_;      // interval mode: this worker's GPU
   bwaflow_c2a_batch_t *c2a = nullptr;                          // interval mode: this worker's SWTask, created on first use
   int64_t c2a_chains = 0, c2a_seeds = 0;
   for (;;) {
@@ -201,7 +225,7 @@ void ChainsToRegionsCUDA::compute(int wid)
       out.alnreg[i].a = (mem_alnreg_t *)malloc((k ? k : 1) * sizeof(mem_alnreg_t));
       memcpy(out.alnreg[i].a, regs + roff[i], k * sizeof(mem_alnreg_t));           // bwaflow_alnreg_t == mem_alnreg_t (88 bytes)
     }
-    if (rec.tag == 1) pool_->give(task);
+    if (rec.tag == 1) { if (env_) env_->give(task); else pool_->give(task); }
     this->pushOutput(out);
   }
   if (c2a) bwaflow_c2a_batch_destroy(c2a);

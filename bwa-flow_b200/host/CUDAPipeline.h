@@ -12,10 +12,13 @@
 // two Task buffers every FPGA worker owns (src/fpga/FPGAPipeline.cpp:374-386).
 class CUDABatchPool {
  public:
-  CUDABatchPool(bwaflow_ctx_t *ctx, int n_batches, int64_t max_reads, int64_t max_bases);
+  // copt / ctg_is_alt: the chaining options (from aux->opt) and bns->anns[].is_alt of the device-side ChainsPipe hop; null = defaults / no ALT contigs
+  CUDABatchPool(bwaflow_ctx_t *ctx, int n_batches, int64_t max_reads, int64_t max_bases, const bwaflow_chain_opt_t *copt = nullptr,
+                const int32_t *ctg_is_alt = nullptr);
   ~CUDABatchPool();
   bwaflow_hot_batch_t *take();
   void give(bwaflow_hot_batch_t *b);
+  const std::vector<bwaflow_hot_batch_t *> &all() const { return all_; }
 
  private:
   kestrelFlow::Queue<bwaflow_hot_batch_t *, 16> free_;
@@ -35,8 +38,33 @@ class SeedPositionTable {
   std::map<uint64_t, Entry> tab_;
 };
 
-// What the host chaining needs from bntseq_t (bwa/bntseq.h:56-64)
-struct ContigTable { int64_t l_pac; int32_t n_seqs; const int64_t *offset; const int32_t *len; };
+// What the host chaining needs from bntseq_t (bwa/bntseq.h:56-64); is_alt may be null (no ALT contigs)
+struct ContigTable { int64_t l_pac; int32_t n_seqs; const int64_t *offset; const int32_t *len; const int32_t *is_alt; };
+
+// The role of BWAOCLEnv (src/fpga/BWAOCLEnv.h:67-258): owns the device side -- one context (index replica) and one batch pool per
+// GPU -- and hands every stage worker its processing element: getPE(wid) binds worker wid to device wid % n_devices, as
+// BWAOCLEnv::getPE binds a worker thread to an FPGA device/bank.  Records are dealt to the GPUs by whichever worker pops them from
+// the kflow queue; a batch goes back to the pool it came from.
+class CUDAEnv {
+ public:
+  struct PE { int device; bwaflow_ctx_t *ctx; CUDABatchPool *pool; };
+  // n_devices <= 0: every visible GPU.  batches_per_device = device batches in flight per GPU (0: interval mode, no fused batches).
+  CUDAEnv(const bwaflow_index_t *idx, const bwaflow_opt_t *opt, const bwaflow_chain_opt_t *copt, const int32_t *ctg_is_alt, int n_devices,
+          int batches_per_device, int64_t max_reads, int64_t max_bases);
+  ~CUDAEnv();
+  int n_devices() const { return (int)pes_.size(); }
+  PE &getPE(int wid) { return pes_[(size_t)wid % pes_.size()]; }
+  void give(bwaflow_hot_batch_t *b) { owner_.at(b)->give(b); }
+  const bwaflow_chain_opt_t &chain_opt() const { return copt_; }
+  int64_t max_reads() const { return max_reads_; }
+  int64_t max_bases() const { return max_bases_; }
+
+ private:
+  std::vector<PE> pes_;
+  std::map<bwaflow_hot_batch_t *, CUDABatchPool *> owner_;
+  bwaflow_chain_opt_t copt_;
+  int64_t max_reads_, max_bases_;
+};
 
 class SeqsToChainsCUDA : public kestrelFlow::MapPartitionStage<SeqsRecord, ChainsRecord, INPUT_DEPTH, COMPUTE_DEPTH> {
  public:
@@ -48,9 +76,14 @@ class SeqsToChainsCUDA : public kestrelFlow::MapPartitionStage<SeqsRecord, Chain
   SeqsToChainsCUDA(int n_workers, bwaflow_ctx_t *ctx, SeedPositionTable *pos, int64_t max_reads, int64_t max_bases)
       : kestrelFlow::MapPartitionStage<SeqsRecord, ChainsRecord, INPUT_DEPTH, COMPUTE_DEPTH>(n_workers, false), pool_(nullptr), ctx_(ctx), pos_(pos),
         max_reads_(max_reads), max_bases_(max_bases) {}
+  // several GPUs: worker wid drives env->getPE(wid); fast mode when the environment holds fused batches, else interval mode
+  SeqsToChainsCUDA(int n_workers, CUDAEnv *env, SeedPositionTable *pos = nullptr)
+      : kestrelFlow::MapPartitionStage<SeqsRecord, ChainsRecord, INPUT_DEPTH, COMPUTE_DEPTH>(n_workers, false), env_(env), pool_(nullptr), ctx_(nullptr),
+        pos_(pos), max_reads_(env->max_reads()), max_bases_(env->max_bases()) {}
   void compute(int wid);
 
  private:
+  CUDAEnv *env_ = nullptr;
   CUDABatchPool *pool_;
   bwaflow_ctx_t *ctx_;
   SeedPositionTable *pos_;
@@ -59,13 +92,16 @@ class SeqsToChainsCUDA : public kestrelFlow::MapPartitionStage<SeqsRecord, Chain
 
 class ChainsPipe : public kestrelFlow::MapStage<ChainsRecord, ChainsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH> {
  public:
-  ChainsPipe(int n = 1, const ContigTable *ctg = nullptr, SeedPositionTable *pos = nullptr)
-      : kestrelFlow::MapStage<ChainsRecord, ChainsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH>(n, false), ctg_(ctg), pos_(pos) {}
+  // copt: the chaining options of aux->opt (w, max_chain_gap, mask_level, drop_ratio, min_seed_len, max_occ ..); null = bwa's defaults
+  ChainsPipe(int n = 1, const ContigTable *ctg = nullptr, SeedPositionTable *pos = nullptr, const bwaflow_chain_opt_t *copt = nullptr)
+      : kestrelFlow::MapStage<ChainsRecord, ChainsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH>(n, false), ctg_(ctg), pos_(pos)
+  { if (copt) copt_ = *copt; else bwaflow_chain_opt_default(&copt_); }
   ChainsRecord compute(ChainsRecord const &record);
 
  private:
   const ContigTable *ctg_;
   SeedPositionTable *pos_;
+  bwaflow_chain_opt_t copt_;
 };
 
 class ChainsToRegionsCUDA : public kestrelFlow::MapPartitionStage<ChainsRecord, RegionsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH> {
@@ -73,9 +109,13 @@ class ChainsToRegionsCUDA : public kestrelFlow::MapPartitionStage<ChainsRecord, 
   ChainsToRegionsCUDA(int n_workers, CUDABatchPool *pool, bwaflow_ctx_t *ctx = nullptr, int64_t max_reads = 0, int64_t max_bases = 0)
       : kestrelFlow::MapPartitionStage<ChainsRecord, RegionsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH>(n_workers, false), pool_(pool), ctx_(ctx),
         max_reads_(max_reads), max_bases_(max_bases) {}
+  ChainsToRegionsCUDA(int n_workers, CUDAEnv *env)
+      : kestrelFlow::MapPartitionStage<ChainsRecord, RegionsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH>(n_workers, false), env_(env), pool_(nullptr), ctx_(nullptr),
+        max_reads_(env->max_reads()), max_bases_(env->max_bases()) {}
   void compute(int wid);
 
  private:
+  CUDAEnv *env_ = nullptr;
   CUDABatchPool *pool_;
   bwaflow_ctx_t *ctx_;
   int64_t max_reads_, max_bases_;

@@ -49,9 +49,10 @@ class RegionsSink : public kestrelFlow::SinkStage<RegionsRecord, COMPUTE_DEPTH> 
 
 int main(int argc, char **argv)
 {
-  if (argc < 3) { fprintf(stderr, "usage: %s case.bin regions.bin [n_workers] [fast|intervals]\n", argv[0]); return 2; }
+  if (argc < 3) { fprintf(stderr, "usage: %s case.bin regions.bin [n_workers] [fast|intervals] [n_gpus (0 = all)] [--use_gpu]\n", argv[0]); return 2; }
   const int n_workers = argc > 3 ? atoi(argv[3]) : 2;
   const bool fast = !(argc > 4 && !strcmp(argv[4], "intervals"));
+  const int n_gpus = argc > 5 ? atoi(argv[5]) : 1;
   FILE *f = fopen(argv[1], "rb");
   if (!f) { perror(argv[1]); return 2; }
   CaseHeader h;
@@ -66,8 +67,6 @@ int main(int argc, char **argv)
   ix.primary = h.primary; memcpy(ix.L2, h.L2, sizeof(ix.L2)); ix.seq_len = h.seq_len; ix.bwt_size = h.bwt_size; ix.bwt = bwt.data();
   ix.n_sa = h.n_sa; ix.sa_intv = h.sa_intv; ix.sa = sa.data(); ix.l_pac = h.l_pac; ix.pac = pac.data(); ix.n_seqs = (int32_t)h.n_seqs;
   ix.ctg_offset = coff.data(); ix.ctg_len = clen.data();
-  bwaflow_ctx_t *ctx = nullptr;
-  if (bwaflow_ctx_create(0, &ix, nullptr, &ctx)) { fprintf(stderr, "%s\n", bwaflow_last_error()); return 1; }
   std::vector<bseq1_t> seqs(h.n_reads);
   int64_t max_rec_bases = 0;
   for (int64_t i = 0; i < h.n_reads; ++i) {
@@ -80,14 +79,18 @@ int main(int argc, char **argv)
   }
   int rc = 0;
   try {
-    CUDABatchPool pool(ctx, fast ? 2 * n_workers : 0, h.reads_per_record, max_rec_bases + 16);
+    // what main() does under --use_gpu (the place of `new BWAOCLEnv()` under --use_fpga, src/main.cpp:201-231): options from aux->opt,
+    // one index replica and two batches per worker on every GPU
+    bwaflow_opt_t opt; bwaflow_opt_default(&opt);
+    bwaflow_chain_opt_t copt; bwaflow_chain_opt_default(&copt);
+    CUDAEnv cuda_env(&ix, &opt, &copt, /*bns->anns[].is_alt*/ nullptr, n_gpus, fast ? 2 * n_workers : 0, h.reads_per_record, max_rec_bases + 16);
     SeedPositionTable seed_pos;
-    ContigTable ctg = {h.l_pac, (int32_t)h.n_seqs, coff.data(), clen.data()};
+    ContigTable ctg = {h.l_pac, (int32_t)h.n_seqs, coff.data(), clen.data(), nullptr};
     ReadsSource src(&seqs, (int)h.reads_per_record);
-    SeqsToChainsCUDA seq2chain_fast(n_workers, &pool), seq2chain_intv(n_workers, ctx, &seed_pos, h.reads_per_record, max_rec_bases + 16);
-    SeqsToChainsCUDA &seq2chain_cuda_stage = fast ? seq2chain_fast : seq2chain_intv;
-    ChainsPipe chainpipe_stage(1, &ctg, &seed_pos);
-    ChainsToRegionsCUDA chain2reg_cuda_stage(n_workers, fast ? &pool : nullptr, ctx, h.reads_per_record, max_rec_bases + 16);
+    SeqsToChainsCUDA seq2chain_cuda_stage(n_workers, &cuda_env, &seed_pos);
+    ChainsPipe chainpipe_stage(1, &ctg, &seed_pos, &copt);
+    ChainsToRegionsCUDA chain2reg_cuda_stage(n_workers, &cuda_env);
+    fprintf(stderr, "CUDAEnv: %d GPU(s), %d workers per stage, %s mode\n", cuda_env.n_devices(), n_workers, fast ? "fast" : "interval");
     RegionsSink sink;
     kestrelFlow::Pipeline compute_flow(5, n_workers);
     compute_flow.addStage(0, &src);
@@ -113,6 +116,5 @@ int main(int argc, char **argv)
     fclose(o);
     fprintf(stderr, "%lld reads in %zu records -> %zu regions\n", (long long)n, sink.got.size(), all.size());
   } catch (std::exception &e) { fprintf(stderr, "error: %s\n", e.what()); rc = 1; }
-  bwaflow_ctx_destroy(ctx);
   return rc;
 }

@@ -13,11 +13,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("case,per_record,workers,mode", [("c1", 400, 2, "fast"), ("c1", 97, 3, "fast"), ("c5", 2000, 1, "fast"),
-                                                          ("c1", 250, 2, "intervals"), ("c5", 300, 2, "intervals")])
-def test_cpp_stage_classes_match_golden(case, per_record, workers, mode, request, tmp_path):
+@pytest.mark.parametrize("case,per_record,workers,mode,gpus", [("c1", 400, 2, "fast", 1), ("c1", 97, 3, "fast", 1), ("c5", 2000, 1, "fast", 1),
+                                                               ("c1", 250, 2, "intervals", 1), ("c5", 300, 2, "intervals", 1),
+                                                               ("c1", 97, 4, "fast", 0), ("c5", 150, 4, "intervals", 0)])
+def test_cpp_stage_classes_match_golden(case, per_record, workers, mode, gpus, request, tmp_path):
     """fast = chains stay in HBM (tag 1); intervals = the FPGA flow: SMEM intervals to the host, ChainsPipe chains them, stage 4
-    takes mem_chain_v lists (tag 0)."""
+    takes mem_chain_v lists (tag 0).  gpus = 0: CUDAEnv takes every visible GPU (index replicated), worker wid drives GPU
+    wid % n_gpus and the kflow queue deals the records -- on a one-GPU box that is the single-GPU path again."""
     from bwaflow_b200 import capi
     g = request.getfixturevalue("golden_" + case)
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "bwa-flow_b200", "host")], check=True)
@@ -38,7 +40,7 @@ def test_cpp_stage_classes_match_golden(case, per_record, workers, mode, request
         off.tofile(f)
         bases.tofile(f)
     out = str(tmp_path / "regions.bin")
-    r = subprocess.run([os.path.join(ROOT, "bwa-flow_b200", "cuda_stage_demo"), path, out, str(workers), mode], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(ROOT, "bwa-flow_b200", "cuda_stage_demo"), path, out, str(workers), mode, str(gpus)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     raw = open(out, "rb").read()
     n = struct.unpack_from("<q", raw, 0)[0]
