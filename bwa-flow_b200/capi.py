@@ -406,9 +406,106 @@ class CigarBatch:
         mds = [C.string_at(mp.value + int(a["md_off"][j])) for j in range(self.n)]
         return a, cigars, mds, t
 
+    def dedup_patch(self, bases, read_off, regs, reg_off):
+        """mem_sort_dedup_patch for every read (bwaflow_dedup_patch) -> (regs, reg_off, n_patch_jobs, rounds)"""
+        L = self.L
+        L.bwaflow_dedup_patch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        regs = np.ascontiguousarray(regs, dtype=ALNREG)
+        reg_off = np.ascontiguousarray(reg_off, dtype=np.int64)
+        out = np.zeros(len(regs) + 1, dtype=ALNREG)
+        out_off = np.zeros(len(reg_off), dtype=np.int64)
+        nj, rounds = C.c_int64(), C.c_int32()
+        check(L.bwaflow_dedup_patch(self.h, len(read_off) - 1, _p(bases), _p(read_off), _p(regs), _p(reg_off), _p(out), _p(out_off),
+                                    C.byref(nj), C.byref(rounds)))
+        return out[:out_off[-1]], out_off, nj.value, rounds.value
+
     def close(self):
         if self.h:
             self.L.bwaflow_cigar_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class SamOpt(C.Structure):
+    _fields_ = [("flag", C.c_int32), ("T", C.c_int32), ("drop_ratio", C.c_float), ("XA_drop_ratio", C.c_float),
+                ("max_XA_hits", C.c_int32), ("max_XA_hits_alt", C.c_int32), ("n_threads", C.c_int32), ("_pad", C.c_int32)]
+
+
+class SamTiming(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("dedup_ms", "matesw_ms", "pair_ms", "cigar_ms", "text_ms", "total_ms")] + \
+               [(k, C.c_int64) for k in ("n_patch_jobs", "n_matesw_jobs", "n_matesw_used", "n_cigar_jobs", "sam_bytes")]
+
+
+def default_sam_opt():
+    so = SamOpt()
+    lib().bwaflow_sam_opt_default(C.byref(so))
+    return so
+
+
+def _blob(strings):
+    """list of str/bytes -> (NUL-terminated blob as uint8 array, int64 offsets)"""
+    bs = [x if isinstance(x, bytes) else x.encode() for x in strings]
+    off = np.zeros(len(bs), dtype=np.int64)
+    if bs:
+        off[1:] = np.cumsum([len(x) + 1 for x in bs[:-1]])
+    blob = np.frombuffer(b"".join(x + b"\0" for x in bs) + b"\0", dtype=np.uint8).copy()
+    return blob, off
+
+
+class SamBatch:
+    """Stage 5 for one batch: regions of stage 4 -> per-read SAM text (bwaflow_sam_*)."""
+
+    def __init__(self, ctx: Context, max_reads, max_bases, ctg_names, po=None, so=None, ctg_is_alt=None, rg_id=None):
+        self.L = ctx.L
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        L = self.L
+        L.bwaflow_sam_batch_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 5 + [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.bwaflow_sam_process.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 9 + [C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                                                        C.c_void_p, C.POINTER(SamTiming)]
+        L.bwaflow_sam_batch_destroy.argtypes = [C.c_void_p]
+        L.bwaflow_sam_header.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64]
+        L.bwaflow_sam_header.restype = C.c_int64
+        names = [x if isinstance(x, bytes) else x.encode() for x in ctg_names]
+        arr = (C.c_char_p * len(names))(*names)
+        alt = np.ascontiguousarray(ctg_is_alt, dtype=np.uint8) if ctg_is_alt is not None else None
+        check(L.bwaflow_sam_batch_create(ctx.h, max_reads, max_bases, C.byref(po) if po is not None else None,
+                                         C.byref(so) if so is not None else None, arr, _p(alt) if alt is not None else None, None,
+                                         rg_id.encode() if rg_id else None, C.byref(self.h)))
+
+    def process(self, bases, quals, read_off, names, regs, reg_off, start_idx=0, comments=None):
+        """names: list of read names; quals: uint8 array parallel to bases or None -> (list of per-read SAM bytes, pestat, timing)"""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        regs = np.ascontiguousarray(regs, dtype=ALNREG)
+        reg_off = np.ascontiguousarray(reg_off, dtype=np.int64)
+        quals = np.ascontiguousarray(quals, dtype=np.uint8) if quals is not None else None
+        nb, no = _blob(names)
+        cb = co = None
+        if comments is not None:
+            cb, co = _blob([c if c is not None else b"" for c in comments])
+            co = np.where(np.array([c is None for c in comments]), -1, co).astype(np.int64)
+        n = len(read_off) - 1
+        sam, off = C.c_void_p(), C.c_void_p()
+        pes = np.zeros(4, dtype=PESTAT)
+        t = SamTiming()
+        check(self.L.bwaflow_sam_process(self.h, n, _p(bases), _p(quals) if quals is not None else None, _p(read_off), _p(nb), _p(no),
+                                         _p(cb) if cb is not None else None, _p(co) if co is not None else None, _p(regs), _p(reg_off),
+                                         start_idx, C.byref(sam), C.byref(off), _p(pes), C.byref(t)))
+        o = np.array(_view(off.value, n + 1, np.dtype("<i8")))
+        text = C.string_at(sam.value, int(o[-1])) if o[-1] else b""
+        return [text[o[i]:o[i + 1]] for i in range(n)], pes, t
+
+    def header(self, hdr_line=None, pg_line=None):
+        n = self.L.bwaflow_sam_header(self.h, hdr_line, pg_line, None, 0)
+        buf = C.create_string_buffer(int(n) + 1)
+        self.L.bwaflow_sam_header(self.h, hdr_line, pg_line, buf, n)
+        return buf.raw[:n]
+
+    def close(self):
+        if self.h:
+            self.L.bwaflow_sam_batch_destroy(self.h)
             self.h = C.c_void_p()
 
 

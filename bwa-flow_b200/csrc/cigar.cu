@@ -21,7 +21,7 @@ constexpr int CG_MINUS_INF = -0x40000000;
 
 struct CgJob {
   int64_t rb, re, q_src;          // reference interval; first base of the read in the batch's base array
-  int32_t qb, qe, l_query, truesc, w_reg, w_cap, _p0, _p1;
+  int32_t qb, qe, l_query, truesc, w_reg, w_cap, mode, _p1;   // mode 1: one score-only bwa_gen_cigar2 call with w_ = w_reg (mem_patch_reg)
   int64_t z_off, cig_off, md_off; // this job's slices of the backtrack / CIGAR / MD scratch
   int32_t cig_cap, md_cap;
 };
@@ -102,17 +102,18 @@ __global__ void __launch_bounds__(32) cigar_kernel(const CgArgs a)
       auto T = [&](int i) -> int { return cg_ref_base(a.ix, rev ? jb.rb + (rlen - 1 - i) : jb.rb + i); };
       if (lq <= 0 || jb.rb >= jb.re || (jb.rb < a.ix.l_pac && jb.re > a.ix.l_pac)) o.err = 1;
       // ---- mem_reg2aln's band: inferred from the local score, capped by the region's and 4 * opt->w (:1123-1131)
+      const bool sco = jb.mode == 1;                        // mem_patch_reg's call (bwa/bwamem.c:433): the caller's band, score only
       int w2 = cg_infer_bw(lq, rlen, jb.truesc, a.a, a.o_del, a.e_del);
       { const int t = cg_infer_bw(lq, rlen, jb.truesc, a.a, a.o_ins, a.e_ins); w2 = w2 > t ? w2 : t; }
       if (w2 > a.w) w2 = w2 < jb.w_reg ? w2 : jb.w_reg;
+      if (sco) w2 = jb.w_reg;
       int score = 0, last_sc = -(1 << 30), n_cigar = 0, it = 0;
       if (!o.err)
         do {
-          w2 = w2 < a.w << 2 ? w2 : a.w << 2;
+          if (!sco) w2 = w2 < a.w << 2 ? w2 : a.w << 2;
           n_cigar = 0;
           if (lq == rlen && w2 == 0) {                      // bwa/bwa.c:141-149: no gap possible, no DP
-            cig[0] = (uint32_t)lq << 4;
-            n_cigar = 1;
+            if (!sco) { cig[0] = (uint32_t)lq << 4; n_cigar = 1; }
             score = 0;
             for (int k = 0; k < lq; ++k) score += a.mat[T(k) * 5 + Q(k)];
           } else {
@@ -155,11 +156,12 @@ __global__ void __launch_bounds__(32) cigar_kernel(const CgArgs a)
                 f -= a.e_ins;
                 d |= f > t ? 2 << 4 : 0;
                 f = f > t ? f : t;
-                zi[j - beg] = d;
+                if (!sco) zi[j - beg] = d;
               }
               ring[(size_t)(end & M_) * 32] = make_int2(h1, CG_MINUS_INF);
             }
             score = ring[(size_t)(lq & M_) * 32].x;
+            if (sco) break;
             // ---- backtrack
             int i = rlen - 1, k = (i + w + 1 < lq ? i + w + 1 : lq) - 1, which = 0;
             auto push = [&](int op, int len) {
@@ -177,12 +179,13 @@ __global__ void __launch_bounds__(32) cigar_kernel(const CgArgs a)
             if (o.err) break;
             for (int x = 0; x < n_cigar >> 1; ++x) { const uint32_t t = cig[x]; cig[x] = cig[n_cigar - 1 - x]; cig[n_cigar - 1 - x] = t; }
           }
-          if (score == last_sc || w2 == a.w << 2) break;      // :1134
+          if (sco || score == last_sc || w2 == a.w << 2) break;      // :1134
           last_sc = score;
           w2 <<= 1;
         } while (++it < 3 && score < jb.truesc - a.a);
       // ---- NM and MD, bwa/bwa.c:164-197
       int NM = -1, l = 0;
+      if (sco) { o.pos = 0; o.is_rev = 0; o.score = score; a.out[job] = o; continue; }
       if (!o.err) {
         int x = 0, y = 0, u = 0, n_mm = 0, n_gap = 0;
         const char *int2base = jb.rb < a.ix.l_pac ? "ACGTN" : "TGCAN";
@@ -277,6 +280,12 @@ struct bwaflow_cigar_batch {
   bool pending;
 };
 
+namespace bwaflow {
+int64_t cigar_max_jobs(const bwaflow_cigar_batch_t *b) { return b->max_jobs; }
+bwaflow_ctx_t *cigar_ctx(const bwaflow_cigar_batch_t *b) { return b->ctx; }
+const bwaflow_pe_opt_t *cigar_po(const bwaflow_cigar_batch_t *b) { return &b->po; }
+}
+
 // mem_approx_mapq_se, bwa/bwamem.c:967-991 (mapQ_coef_len > 0 branch and the MEM_MAPQ_COEF one)
 static int approx_mapq_se(const bwaflow_opt_t &o, const bwaflow_pe_opt_t &po, const bwaflow_alnreg_t &a)
 {
@@ -308,6 +317,39 @@ static int cg_grow(T **p, size_t *cap, size_t need)
   cudaFree(*p);
   *cap = need + need / 4 + 4096;
   BF_CUDA(cudaMalloc(p, *cap * sizeof(T)));
+  return 0;
+}
+
+// one launch of cigar_kernel over the batch's job array in queue order `order`: ring size by the widest band, row state in HBM
+// when a band does not fit the shared ring
+static int cg_launch(bwaflow_cigar_batch *b, int64_t n_jobs, const uint32_t *order, int w_max, int lq_max, int wide)
+{
+  const bwaflow_opt_t &o = b->ctx->par.opt;
+  int r;
+  CgArgs a;
+  a.jobs = b->d_jobs; a.order = order; a.n_jobs = (int)n_jobs; a.head = b->d_ctl; a.bases = b->d_bases; a.z = b->d_z; a.cig = b->d_cig;
+  a.md = b->d_md; a.out = b->d_out; a.ix = b->ctx->ix; a.geh = nullptr; a.geh_stride = 0;
+  for (int i = 0; i < 25; ++i) a.mat[i] = o.mat[i];
+  a.a = o.a; a.o_del = o.o_del; a.e_del = o.e_del; a.o_ins = o.o_ins; a.e_ins = o.e_ins; a.w = o.w;
+  const int R = 2 * w_max + 2 <= 64 ? 64 : 256;
+  const size_t smem = (size_t)R * 32 * sizeof(int2);
+  int blocks = (int)((n_jobs + 31) / 32);
+  if (wide) {                                             // bands beyond the shared ring: row state of lq + 1 columns per lane in HBM
+    const int cap_blocks = b->ctx->n_sm * 8;
+    if (blocks > cap_blocks) blocks = cap_blocks;
+    a.geh_stride = lq_max + 2;
+    if ((r = cg_grow(&b->d_geh, &b->geh_cap, (size_t)blocks * 32 * a.geh_stride))) return r;
+    a.geh = b->d_geh;
+    cigar_kernel<0><<<blocks, 32, 0, b->stream>>>(a);
+  } else if (R == 64) {
+    BF_CUDA(cudaFuncSetAttribute(cigar_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int cap_blocks = b->ctx->n_sm * 12;
+    cigar_kernel<64><<<blocks < cap_blocks ? blocks : cap_blocks, 32, smem, b->stream>>>(a);
+  } else {
+    BF_CUDA(cudaFuncSetAttribute(cigar_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int cap_blocks = b->ctx->n_sm * 3;
+    cigar_kernel<256><<<blocks < cap_blocks ? blocks : cap_blocks, 32, smem, b->stream>>>(a);
+  }
   return 0;
 }
 
@@ -411,30 +453,7 @@ int bwaflow_cigar_submit(bwaflow_cigar_batch_t *b, int64_t n_reads, const uint8_
     cub::DoubleBuffer<uint32_t> k(b->d_keys[0], b->d_keys[1]), v(b->d_order[0], b->d_order[1]);
     size_t tmp = b->tmp_bytes;
     BF_CUDA(cub::DeviceRadixSort::SortPairs(b->d_tmp, tmp, k, v, (int)n_jobs, 0, 32, b->stream));
-    CgArgs a;
-    a.jobs = b->d_jobs; a.order = v.Current(); a.n_jobs = (int)n_jobs; a.head = b->d_ctl; a.bases = b->d_bases; a.z = b->d_z; a.cig = b->d_cig;
-    a.md = b->d_md; a.out = b->d_out; a.ix = b->ctx->ix; a.geh = nullptr; a.geh_stride = 0;
-    for (int i = 0; i < 25; ++i) a.mat[i] = o.mat[i];
-    a.a = o.a; a.o_del = o.o_del; a.e_del = o.e_del; a.o_ins = o.o_ins; a.e_ins = o.e_ins; a.w = o.w;
-    const int R = 2 * w_max + 2 <= 64 ? 64 : 256;
-    const size_t smem = (size_t)R * 32 * sizeof(int2);
-    int blocks = (int)((n_jobs + 31) / 32);
-    if (wide) {                                             // bands beyond the shared ring: row state of lq + 1 columns per lane in HBM
-      const int cap_blocks = b->ctx->n_sm * 8;
-      if (blocks > cap_blocks) blocks = cap_blocks;
-      a.geh_stride = lq_max + 2;
-      if ((r = cg_grow(&b->d_geh, &b->geh_cap, (size_t)blocks * 32 * a.geh_stride))) return r;
-      a.geh = b->d_geh;
-      cigar_kernel<0><<<blocks, 32, 0, b->stream>>>(a);
-    } else if (R == 64) {
-      BF_CUDA(cudaFuncSetAttribute(cigar_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const int cap_blocks = b->ctx->n_sm * 12;
-      cigar_kernel<64><<<blocks < cap_blocks ? blocks : cap_blocks, 32, smem, b->stream>>>(a);
-    } else {
-      BF_CUDA(cudaFuncSetAttribute(cigar_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const int cap_blocks = b->ctx->n_sm * 3;
-      cigar_kernel<256><<<blocks < cap_blocks ? blocks : cap_blocks, 32, smem, b->stream>>>(a);
-    }
+    if ((r = cg_launch(b, n_jobs, v.Current(), w_max, lq_max, wide))) return r;
     cigar_sizes_kernel<<<(unsigned)((n_jobs + 1 + 255) / 256), 256, 0, b->stream>>>(b->d_out, n_jobs, b->d_sz);
     for (int k2 = 0; k2 < 2; ++k2) {
       tmp = b->tmp_bytes;
@@ -505,6 +524,49 @@ int bwaflow_cigar_collect(bwaflow_cigar_batch_t *b, const bwaflow_aln_t **aln, c
   if (aln) *aln = b->aln.data();
   if (cigar_pool) *cigar_pool = b->cig.data();
   if (md_pool) *md_pool = b->md.data();
+  return 0;
+}
+
+int bwaflow_cigar_global_scores(bwaflow_cigar_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off, int upload,
+                                int64_t n_jobs, const bwaflow_gscore_job_t *jobs, int32_t *scores)
+{
+  BF_REQUIRE(b && !b->pending && read_off && (n_jobs == 0 || (jobs && scores)), -22, "bwaflow_cigar_global_scores: bad argument or a submit is pending");
+  BF_REQUIRE(n_reads <= b->max_reads && read_off[n_reads] <= b->max_bases && n_jobs >= 0 && n_jobs <= b->max_jobs, -7,
+             "bwaflow_cigar_global_scores: batch capacity exceeded");
+  BF_CUDA(cudaSetDevice(b->ctx->device));
+  const bwaflow_opt_t &o = b->ctx->par.opt;
+  if (upload) { BF_REQUIRE(bases, -22, "bwaflow_cigar_global_scores: no bases"); BF_CUDA(cudaMemcpyAsync(b->d_bases, bases, read_off[n_reads], cudaMemcpyHostToDevice, b->stream)); }
+  if (n_jobs == 0) { BF_CUDA(cudaStreamSynchronize(b->stream)); return 0; }
+  b->jobs.resize((size_t)n_jobs); b->vals.resize((size_t)n_jobs);
+  int wide = 0, w_max = 0, lq_max = 1;
+  for (int64_t j = 0; j < n_jobs; ++j) {
+    const bwaflow_gscore_job_t &q = jobs[j];
+    BF_REQUIRE(q.read >= 0 && q.read < n_reads && q.qb >= 0 && q.qe > q.qb && q.qe <= read_off[q.read + 1] - read_off[q.read] && q.rb >= 0 && q.re > q.rb && q.w >= 0,
+               -22, "bwaflow_cigar_global_scores: job %lld is not an interval of its read", (long long)j);
+    CgJob &g = b->jobs[(size_t)j];
+    memset(&g, 0, sizeof(g));
+    g.rb = q.rb; g.re = q.re; g.q_src = read_off[q.read]; g.qb = q.qb; g.qe = q.qe; g.l_query = (int)(read_off[q.read + 1] - read_off[q.read]);
+    g.w_reg = q.w; g.mode = 1;
+    const int lq = q.qe - q.qb, rlen = (int)(q.re - q.rb);
+    g.w_cap = cg_band(lq, rlen, o.mat[0], o.o_del, o.e_del, o.o_ins, o.e_ins, q.w);
+    b->vals[(size_t)j] = (uint32_t)j;
+    if (2 * g.w_cap + 2 > 256) wide = 1;
+    if (g.w_cap > w_max) w_max = g.w_cap;
+    if (lq > lq_max) lq_max = lq;
+  }
+  BF_CUDA(cudaMemsetAsync(b->d_ctl, 0, 4 * sizeof(int), b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->d_jobs, b->jobs.data(), n_jobs * sizeof(CgJob), cudaMemcpyHostToDevice, b->stream));
+  BF_CUDA(cudaMemcpyAsync(b->d_order[0], b->vals.data(), n_jobs * 4, cudaMemcpyHostToDevice, b->stream));
+  int r;
+  if ((r = cg_launch(b, n_jobs, b->d_order[0], w_max, lq_max, wide))) return r;
+  BF_CUDA(cudaGetLastError());
+  b->outs.resize((size_t)n_jobs);
+  BF_CUDA(cudaMemcpyAsync(b->outs.data(), b->d_out, n_jobs * sizeof(CgOut), cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaStreamSynchronize(b->stream));
+  for (int64_t j = 0; j < n_jobs; ++j) {
+    BF_REQUIRE(b->outs[(size_t)j].err == 0, -34, "global-score job %lld failed on the device (code %d)", (long long)j, b->outs[(size_t)j].err);
+    scores[j] = b->outs[(size_t)j].score;
+  }
   return 0;
 }
 

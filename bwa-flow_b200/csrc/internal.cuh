@@ -83,6 +83,10 @@ struct bwaflow_ctx {
 };
 
 namespace bwaflow {
+// what sam.cu needs to know about a CIGAR batch (cigar.cu)
+int64_t cigar_max_jobs(const bwaflow_cigar_batch_t *b);
+bwaflow_ctx_t *cigar_ctx(const bwaflow_cigar_batch_t *b);
+const bwaflow_pe_opt_t *cigar_po(const bwaflow_cigar_batch_t *b);
 void fill_score(const bwaflow_opt_t &o, DevScore &s);
 
 struct Timer {

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <vector>
 #include "internal.cuh"
+#include "stage5_host.h"
 #include "batches.cuh"
 #include "klib_sort.h"
 
@@ -45,56 +46,6 @@ __global__ void matesw_fill_kernel(const MsFill *f, int64_t n, const uint8_t *ba
 }
 
 // ---- host pieces -------------------------------------------------------------------------------------------------------------
-
-typedef bwaflow_alnreg_t Reg;
-static inline int reg_is_alt(const Reg &r) { return (int)(r.n_comp_is_alt >> 30); }
-
-// mem_infer_dir, bwa/bwamem_pair.c:26-33
-static inline int infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t *dist)
-{
-  const int r1 = b1 >= l_pac, r2 = b2 >= l_pac;
-  const int64_t p2 = r1 == r2 ? b2 : (l_pac << 1) - 1 - b2;
-  *dist = p2 > b1 ? p2 - b1 : b1 - p2;
-  return (r1 == r2 ? 0 : 1) ^ (p2 > b1 ? 0 : 3);
-}
-
-// mem_sort_dedup_patch (bwa/bwamem.c:446-498) as mem_matesw calls it: bns = pac = query = 0, so mem_patch_reg returns 0 and no two
-// hits are ever merged
-struct RegEndLt { bool operator()(const Reg &a, const Reg &b) const { return a.re < b.re; } };                       // alnreg_slt2, :400
-struct RegScoreLt { bool operator()(const Reg &a, const Reg &b) const
-  { return a.score > b.score || (a.score == b.score && (a.rb < b.rb || (a.rb == b.rb && a.qb < b.qb))); } };          // alnreg_slt, :403
-static int sort_dedup(const bwaflow_pe_opt_t &po, int n, Reg *a)
-{
-  int m, i, j;
-  if (n <= 1) return n;
-  klib_introsort(n, a, RegEndLt());
-  for (i = 0; i < n; ++i) a[i].n_comp_is_alt = (a[i].n_comp_is_alt & 0xC0000000u) | 1u;
-  for (i = 1; i < n; ++i) {
-    Reg *p = &a[i];
-    if (p->rid != a[i - 1].rid || p->rb >= a[i - 1].re + po.max_chain_gap) continue;
-    for (j = i - 1; j >= 0 && p->rid == a[j].rid && p->rb < a[j].re + po.max_chain_gap; --j) {
-      Reg *q = &a[j];
-      if (q->qe == q->qb) continue;
-      const int64_t orr = q->re - p->rb;
-      const int64_t oq = q->qb < p->qb ? q->qe - p->qb : p->qe - q->qb;
-      const int64_t mr = q->re - q->rb < p->re - p->rb ? q->re - q->rb : p->re - p->rb;
-      const int64_t mq = q->qe - q->qb < p->qe - p->qb ? q->qe - q->qb : p->qe - p->qb;
-      if (orr > po.mask_level_redun * mr && oq > po.mask_level_redun * mq) {
-        if (p->score < q->score) { p->qe = p->qb; break; }
-        else q->qe = q->qb;
-      }
-    }
-  }
-  for (i = 0, m = 0; i < n; ++i)
-    if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
-  n = m;
-  klib_introsort(n, a, RegScoreLt());
-  for (i = 1; i < n; ++i)
-    if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
-  for (i = 1, m = 1; i < n; ++i)
-    if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
-  return m;
-}
 
 // bns_pos2rid, bwa/bntseq.c:349-363
 static int pos2rid(const bwaflow_ctx_t *c, int64_t pos_f)

@@ -276,6 +276,63 @@ int bwaflow_cigar_submit(bwaflow_cigar_batch_t *b, int64_t n_reads, const uint8_
 int bwaflow_cigar_collect(bwaflow_cigar_batch_t *b, const bwaflow_aln_t **aln, const uint32_t **cigar_pool, const char **md_pool,
                           bwaflow_timing_t *timing);
 
+/* ---- region de-duplication (stage 5, first step): mem_sort_dedup_patch (bwa/bwamem.c:446-498) for every read of a batch, as
+ *      RegionsToSam::compute runs it with the real bns / pac / query (src/Pipeline.cpp:560-568), i.e. WITH mem_patch_reg (:415-444):
+ *      two colinear hits are merged when a banded global alignment over their union (bwa_gen_cigar2 with n_cigar = 0, bwa/bwa.c:121,
+ *      -> ksw_global2 score only) scores at least PATCH_MIN_SC_RATIO of what the hits predict.  The scans run on the host; every
+ *      global alignment they ask for runs on the device through the CIGAR batch's kernel in its score-only mode.  A read whose scan
+ *      needs a score that is not known yet is suspended, the requests of all suspended reads go to the device as one launch, and the
+ *      scans are redone (a merge changes what later tests ask for, so the requests cannot be enumerated up front); *rounds = number
+ *      of launches.  regs_out needs room for reg_off[n_reads] regions.  mask_level_redun / max_chain_gap are the CIGAR batch's. */
+typedef struct { int32_t read, qb, qe, w; int64_t rb, re; } bwaflow_gscore_job_t;   /* query[qb..qe) of `read` vs reference [rb, re), band w_ */
+/* scores[j] = *score of bwa_gen_cigar2(mat, gaps, w, l_pac, pac, qe - qb, query + qb, rb, re, &score, 0, 0).  upload != 0 copies the
+ * batch's bases to the device first; 0 = those of the previous call are still resident.  Blocks until the scores are back. */
+int bwaflow_cigar_global_scores(bwaflow_cigar_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off, int upload,
+                                int64_t n_jobs, const bwaflow_gscore_job_t *jobs, int32_t *scores);
+int bwaflow_dedup_patch(bwaflow_cigar_batch_t *b, int64_t n_reads, const uint8_t *bases, const int64_t *read_off,
+                        const bwaflow_alnreg_t *regs, const int64_t *reg_off, bwaflow_alnreg_t *regs_out, int64_t *reg_off_out,
+                        int64_t *n_patch_jobs, int32_t *rounds);
+
+/* ---- stage 5 as a whole: RegionsToSam::compute (src/Pipeline.cpp:546-648) for one batch = the role a RegionsToSamCUDA stage
+ *      plays behind slot 5 of compute_flow.  Regions of stage 4 in, per-read SAM text out (the string mem_aln2sam_hts builds before
+ *      sam_parse1, src/bwa_wrapper.cpp:452-590 -- the comparison point of SURVEY 8c):
+ *        mem_sort_dedup_patch + ALT marking -> mem_pestat -> per pair mem_sam_pe_hts (src/bwa_wrapper.cpp:640-790): mate rescue,
+ *        mem_mark_primary_se, mem_pair, mapping qualities, mem_reg2aln for every reported hit and every XA candidate of mem_gen_alt
+ *        (bwa/bwamem_extra.c:99-152), mem_aln2sam_hts; single-end batches: mem_mark_primary_se + mem_reg2sam_hts (:592-637).
+ *      Device: ksw_global2 (patch scores, CIGARs) and ksw_align2 (mate rescue).  Host (worker threads over pairs): the sequential
+ *      decisions in between and the text. */
+typedef struct {
+  int32_t flag;                     /* MEM_F_* of bwa/bwamem.h:14-24: PE 0x2, NOPAIRING 0x4, ALL 0x8, NO_MULTI 0x10 (-M, bwa-flow's
+                                       default, src/config.cpp:16), NO_RESCUE 0x20, REF_HDR 0x100, SOFTCLIP 0x200, XB 0x2000 */
+  int32_t T;                        /* minimum score to output, default 30 */
+  float drop_ratio, XA_drop_ratio;  /* 0.50, 0.80 */
+  int32_t max_XA_hits, max_XA_hits_alt;   /* 5, 200 */
+  int32_t n_threads, _pad;          /* host threads of the decision / text phases; < 1: all cores */
+} bwaflow_sam_opt_t;
+void bwaflow_sam_opt_default(bwaflow_sam_opt_t *so);       /* flag = PE | NO_MULTI */
+typedef struct {
+  float dedup_ms, matesw_ms, pair_ms, cigar_ms, text_ms, total_ms;     /* host wall clock per phase (the device work is inside) */
+  int64_t n_patch_jobs, n_matesw_jobs, n_matesw_used, n_cigar_jobs, sam_bytes;
+} bwaflow_sam_timing_t;
+typedef struct bwaflow_sam_batch bwaflow_sam_batch_t;
+/* ctg_names: n_seqs NUL-terminated names (bns->anns[i].name); ctg_is_alt / ctg_anno (XR:Z with MEM_F_REF_HDR) may be NULL;
+ * rg_id: the read-group ID printed as RG:Z (bwa_rg_id), NULL or "" for none.  The strings are copied. */
+int bwaflow_sam_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_bases, const bwaflow_pe_opt_t *po,
+                             const bwaflow_sam_opt_t *so, const char *const *ctg_names, const uint8_t *ctg_is_alt,
+                             const char *const *ctg_anno, const char *rg_id, bwaflow_sam_batch_t **out);
+void bwaflow_sam_batch_destroy(bwaflow_sam_batch_t *b);
+/* One batch.  bases: nt4 codes, read r = bases[read_off[r] .. read_off[r+1]); quals: same offsets, NULL = '*'; names / comments:
+ * NUL-terminated strings at names + name_off[r] (comment_off[r] < 0 or comments == NULL: none); reads 2k and 2k+1 are mates when
+ * MEM_F_PE is set.  regs / reg_off: stage 4's output.  start_idx = SeqsRecord::start_idx (the pair id (start_idx>>1)+k seeds the
+ * tie-breaking hashes, src/Pipeline.cpp:589).  Output: sam = the reads' SAM lines concatenated in read order, read r's lines =
+ * sam[sam_off[r] .. sam_off[r+1]); valid until the next call on this batch.  pes_out (may be NULL) = mem_pestat of the batch. */
+int bwaflow_sam_process(bwaflow_sam_batch_t *b, int64_t n_reads, const uint8_t *bases, const uint8_t *quals, const int64_t *read_off,
+                        const char *names, const int64_t *name_off, const char *comments, const int64_t *comment_off,
+                        const bwaflow_alnreg_t *regs, const int64_t *reg_off, int64_t start_idx,
+                        const char **sam, const int64_t **sam_off, bwaflow_pestat_t pes_out[4], bwaflow_sam_timing_t *timing);
+/* @HD / @SQ / @PG header lines as bwa_format_sam_hdr writes them (src/bwa_wrapper.cpp:25-35); returns the length, copies at most cap bytes */
+int64_t bwaflow_sam_header(bwaflow_sam_batch_t *b, const char *hdr_line /* @RG line etc., may be NULL */, const char *pg_line, char *buf, int64_t cap);
+
 /* ---- index construction for synthetic references (workload preparation; the arrays equal what `bwa index`
  *      + bwa_idx_load leave in memory, bwa/bwtindex.c:256-324).  codes: 0..3 = ACGT, >=4 = N, contigs concatenated. */
 typedef struct bwaflow_built_index bwaflow_built_index_t;
