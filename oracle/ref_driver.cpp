@@ -226,7 +226,8 @@ int bwaref_contig_name(void *h, int i, char *buf, int cap)
 }
 int bwaref_sam_header(void *h, char *buf, int cap)
 { // src/bwa_wrapper.cpp:25-35 with the default read group of src/config.cpp:10 left out (rg_line = 0)
-  kstring_t s; bwa_format_sam_hdr(((ref_t *)h)->idx->bns, 0, &s);
+  kstring_t s = {0, 0, 0};                       // bwa_format_sam_hdr resets l and s but not m
+  bwa_format_sam_hdr(((ref_t *)h)->idx->bns, 0, &s);
   int l = (int)s.l; if (buf && cap > l) memcpy(buf, s.s, l + 1);
   free(s.s); return l;
 }
