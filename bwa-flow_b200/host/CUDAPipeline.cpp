@@ -230,3 +230,63 @@ void ChainsToRegionsCUDA::compute(int wid)
   }
   if (c2a) bwaflow_c2a_batch_destroy(c2a);
 }
+
+void RegionsToSamCUDA::compute(int wid)
+{
+  bwaflow_ctx_t *ctx = env_->getPE(wid).ctx;
+  bwaflow_sam_batch_t *sam = nullptr;
+  check(bwaflow_sam_batch_create(ctx, env_->max_reads(), env_->max_bases(), &cfg_.po, &cfg_.so, cfg_.ctg_names, cfg_.ctg_is_alt, cfg_.ctg_anno,
+                                 cfg_.rg_id, &sam));
+  std::vector<uint8_t> bases, quals;
+  std::vector<char> names, comments;
+  std::vector<int64_t> off, name_off, comment_off, reg_off;
+  std::vector<bwaflow_alnreg_t> regs;
+  for (;;) {
+    RegionsRecord rec = RegionsRecord();
+    bool ready = this->getInput(rec);
+    while (!this->isFinal() && !ready) {
+      std::this_thread::sleep_for(std::chrono::microseconds(10));
+      ready = this->getInput(rec);
+    }
+    if (!ready && !(ready = this->getInput(rec))) break;
+    const int n = rec.batch_num;
+    bases.clear(); quals.clear(); names.clear(); comments.clear(); regs.clear();
+    off.assign(1, 0); reg_off.assign(1, 0); name_off.clear(); comment_off.clear();
+    bool have_qual = true, have_comment = false;
+    for (int i = 0; i < n; ++i) if (!rec.seqs[i].qual) have_qual = false;
+    for (int i = 0; i < n; ++i) {
+      const bseq1_t *s = &rec.seqs[i];                         // s->seq is nt4 already (stage 2 converted it in place)
+      bases.insert(bases.end(), (const uint8_t *)s->seq, (const uint8_t *)s->seq + s->l_seq);
+      if (have_qual) quals.insert(quals.end(), (const uint8_t *)s->qual, (const uint8_t *)s->qual + s->l_seq);
+      off.push_back((int64_t)bases.size());
+      name_off.push_back((int64_t)names.size());
+      names.insert(names.end(), s->name, s->name + strlen(s->name) + 1);
+      if (s->comment) { comment_off.push_back((int64_t)comments.size()); comments.insert(comments.end(), s->comment, s->comment + strlen(s->comment) + 1); have_comment = true; }
+      else comment_off.push_back(-1);
+      const mem_alnreg_v &v = rec.alnreg[i];
+      const bwaflow_alnreg_t *a = (const bwaflow_alnreg_t *)v.a;          // bwaflow_alnreg_t == mem_alnreg_t (88 bytes)
+      regs.insert(regs.end(), a, a + v.n);
+      reg_off.push_back((int64_t)regs.size());
+    }
+    if (!have_qual) for (int i = 0; i < n; ++i) if (rec.seqs[i].qual) throw std::runtime_error("RegionsToSamCUDA: a record mixes reads with and without qualities");
+    const char *text; const int64_t *toff;
+    check(bwaflow_sam_process(sam, n, bases.data(), have_qual ? quals.data() : nullptr, off.data(), names.data(), name_off.data(),
+                              have_comment ? comments.data() : nullptr, have_comment ? comment_off.data() : nullptr, regs.data(), reg_off.data(),
+                              (int64_t)rec.start_idx, &text, &toff, nullptr, nullptr));
+    for (int i = 0; i < n; ++i) {
+      bseq1_t *s = &rec.seqs[i];
+      const size_t l = (size_t)(toff[i + 1] - toff[i]);
+      s->sam = (char *)malloc(l + 1);
+      memcpy(s->sam, text + toff[i], l);
+      s->sam[l] = 0;
+      free(s->name); free(s->comment); free(s->seq); free(s->qual);      // Pipeline.cpp:632-638
+      s->name = s->comment = s->seq = s->qual = NULL;
+      if (rec.alnreg[i].a) free(rec.alnreg[i].a);                         // freeAligns
+    }
+    free(rec.alnreg);
+    SeqsRecord out;
+    out.start_idx = rec.start_idx; out.batch_num = n; out.seqs = rec.seqs;
+    this->pushOutput(out);
+  }
+  bwaflow_sam_batch_destroy(sam);
+}

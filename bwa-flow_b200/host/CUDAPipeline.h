@@ -120,3 +120,21 @@ class ChainsToRegionsCUDA : public kestrelFlow::MapPartitionStage<ChainsRecord, 
   bwaflow_ctx_t *ctx_;
   int64_t max_reads_, max_bases_;
 };
+
+// Slot 5: RegionsToSam (src/Pipeline.cpp:546-648) on the device where it is dynamic programming (patch scores, mate rescue, CIGARs)
+// and on this worker's thread where it is a per-pair decision or text; every worker owns one bwaflow_sam_batch on its GPU.
+// Output as the reference's: seqs[i].sam set, name / comment / seq / qual and the regions freed.
+struct SamStageConfig {
+  bwaflow_pe_opt_t po; bwaflow_sam_opt_t so;
+  const char *const *ctg_names; const uint8_t *ctg_is_alt; const char *const *ctg_anno; const char *rg_id;
+};
+class RegionsToSamCUDA : public kestrelFlow::MapPartitionStage<RegionsRecord, SeqsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH> {
+ public:
+  RegionsToSamCUDA(int n_workers, CUDAEnv *env, const SamStageConfig &cfg)
+      : kestrelFlow::MapPartitionStage<RegionsRecord, SeqsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH>(n_workers, false), env_(env), cfg_(cfg) {}
+  void compute(int wid);
+
+ private:
+  CUDAEnv *env_;
+  SamStageConfig cfg_;
+};
