@@ -25,21 +25,24 @@
 
 namespace bwaflow {
 
-// Level L+1 of the tables from level L: one thread per child, entry(P.c) = bwt_extend(entry(P)) forwards by c.
+// Level L of the tables from level L - 1: one thread per child, entry(P.c) = bwt_extend(entry(P)) forwards by c.
 __global__ void ktab_level_kernel(DevIndex ix, int L, uint4 *tab)
 {
   const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >> (2 * L)) return;
   Intv o;
+  int hist = 0;
   if (L == 1) o = set_intv(ix, (int)v);
   else {
-    int d;
-    const Intv p = unpack_entry(tab[ktab_base(L - 1) + (v >> 2)], &d);
+    const Intv p = unpack_entry(tab[ktab_base(L - 1) + (v >> 2)], &hist);
     unsigned long long nb = 0;
     if (p.x2 == 0) { o.x0 = o.x1 = o.x2 = 0; }
     else o = extend1(ix, p, 0, 3 - (int)(v & 3), &nb);
+    // the entry's spare 11 bits: did the interval change size at this level and at the ten before it (bit j = level L - j)?
+    // Lets the sweep kernel rebuild the forward list of the levels it jumps over (smem_sweep.cu, SM_J).
+    hist = (hist << 1 | (o.x2 != p.x2)) & 0x7ff;
   }
-  tab[ktab_base(L) + v] = pack_entry(o, 0);
+  tab[ktab_base(L) + v] = pack_entry(o, hist);
 }
 
 int build_level_tables(bwaflow_ctx *c, int K, void **d_tab)

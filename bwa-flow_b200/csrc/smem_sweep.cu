@@ -33,7 +33,7 @@
 namespace bwaflow {
 
 enum { SK_T = 0, SK_X = 1, SK_A = 2 };
-enum { SM_F = 0, SM_W = 1, SM_S = 2, SM_B = 3, SM_C = 4, SM_CF = 5 };   // forward sweep | window lookup | level walk | leftward extension | continue the previous anchored match | (that failed)
+enum { SM_F = 0, SM_W = 1, SM_S = 2, SM_B = 3, SM_C = 4, SM_CF = 5, SM_J = 6 };   // forward sweep | window lookup | level walk | leftward extension | continue the previous anchored match | (that failed) | forward sweep: all remaining table levels in one read
 enum { S_NONE = 0, S_FETCH, S_NEXT, S_ENTRY, S_ENTRY_DONE, S_CALL_DONE, S_FINISH, S_EXIT };
 
 #ifndef SWEEP_MIN_BLOCKS
@@ -60,6 +60,11 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
   int pb = 0, pe = 0;
   Intv ik = {0, 0, 0}, cand = {0, 0, 0}; int cand_beg = 0, cand_end = 0;
 
+  // The forward sweep walks the table levels one base at a time only up to length JL; from there the level-K entry of the K bases
+  // from sx gives the interval at length K, and its 11 history bits say at which of the levels in between the interval changed
+  // size -- which is all the forward list keeps of them (ends only: patterns of at most K bases are re-read from the tables).
+  const int JL = K >= 2 ? max(1, K - 11) : 0;
+  int jm = 0;
   auto tab = [&](int b, int L) -> Intv { int d; return unpack_entry(__ldg(ix.ktab + ktab_base(L) + q.code(b, L)), &d); };
   auto get_end = [&](int k) -> int { return k < 64 ? (int)fend[k] : entry_pos(fwd_l[k - fwd_ns]); };
   auto push_fwd = [&](const Intv &v, int end) {
@@ -76,6 +81,8 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
   };
   // kind of the next step for the pattern [pb, pe) growing by one base
   auto set_kind = [&]() { kind = (TEXT && is_text(ik)) ? SK_A : (pe - pb + 1 <= K ? SK_T : SK_X); ts = S_NONE; };
+  // next step of a forward sweep standing at q[pb, pe): the jump if the K bases from pb are all there
+  auto set_kind_fwd = [&]() { set_kind(); if (JL && pe - pb == JL && kind == SK_T && q.next_n(pb) >= pb + K) mode = SM_J; };
 
   for (;;) {
     // ---- the entry boundary (every ~4 steps of a lane): one straight-line block so that the lanes at a boundary run it together
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
         if (call) {                                          // forward sweep from sx (:338-363)
           fwd_n = 0; fwd_ns = 0; ik = set_intv(ix, q.base(sx)); pb = sx; pe = sx + 1; mode = SM_F;
           nb = q.prev_n(sx) + 1;
-          if (pe < q.len && !q.isN(pe)) set_kind();
+          if (pe < q.len && !q.isN(pe)) set_kind_fwd();
           else { push_fwd(ik, pe); fi = 0; lb = nb; ts = S_ENTRY; }
           break;
         }
@@ -169,7 +176,8 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
     Intv o = {0, 0, 0}; bool have = false;
     // ---- T: one table read
     if (ts == S_NONE && kind == SK_T) {
-      if (mode == SM_F) o = tab(pb, pe - pb + 1);
+      if (mode == SM_J) o = unpack_entry(__ldg(ix.ktab + ktab_base(K) + q.code(pb, K)), &jm);
+      else if (mode == SM_F) o = tab(pb, pe - pb + 1);
       else if (mode == SM_B) o = tab(pb - 1, pe - pb + 1);
       else o = tab(pe - sL, sL);                             // window / level walk: the sL bases ending at pe
       have = true;
@@ -188,13 +196,22 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
     if (have) {
       const bool small = o.x2 < (uint64_t)mi;
       if (TEXT && mi == 1 && o.x2 == 1) o = text_intv(ix.sa[o.x0]);       // unique from here on: anchor it in the text
-      if (mode == SM_F) {                                    // :350-363
+      if (mode == SM_J) {
+        mode = SM_F;
+        if (small) set_kind();                               // some prefix is too rare: take the levels one by one
+        else {
+          for (int L = pe - pb; L < K; ++L)                  // ends at which the interval changed size (level L -> L + 1)
+            if (jm >> (K - 1 - L) & 1) { fend[fwd_n++] = (uint8_t)(pb + L); ++fwd_ns; }
+          ik = o; pe = pb + K;
+          if (pe < q.len && !q.isN(pe)) set_kind(); else { push_fwd(ik, pe); fi = 0; lb = nb; ts = S_ENTRY; }
+        }
+      } else if (mode == SM_F) {                             // :350-363
         const bool changed = o.x2 != ik.x2;
         if (changed) push_fwd(ik, pe);
         if (changed && small) { fi = 0; lb = nb; ts = S_ENTRY; }
         else {
           ik = o; ++pe;
-          if (pe < q.len && !q.isN(pe)) set_kind(); else { push_fwd(ik, pe); fi = 0; lb = nb; ts = S_ENTRY; }
+          if (pe < q.len && !q.isN(pe)) set_kind_fwd(); else { push_fwd(ik, pe); fi = 0; lb = nb; ts = S_ENTRY; }
         }
       } else if (mode == SM_B) {                             // one more base on the left (:374-386)
         if (small) ts = S_ENTRY_DONE;
