@@ -4,7 +4,7 @@ usage: ncu_pick.py file.ncu-rep [kernel-substring]"""
 import csv, subprocess, sys
 rep = sys.argv[1]
 sub = sys.argv[2] if len(sys.argv) > 2 else ""
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 col = {h: i for i, h in enumerate(hdr)}

@@ -1,14 +1,14 @@
 #!/usr/bin/env python3
 """profiles/traffic.json from an ncu --set full report: dram__bytes_read.sum + dram__bytes_write.sum per launch of the hot-path
 kernels (the production instance of each = its longest captured launch), and their sum over the seeding stage, which is what
-bench.py reports as roofline.traffic.  usage: traffic_from_ncu.py seed.ncu-rep [more.ncu-rep ..] > profiles/traffic.json"""
+bench.py reports as roofline.traffic.  usage: traffic_from_ncu.py seed.ncu-rep|seed_raw.csv [more ..] > profiles/traffic.json"""
 import csv, json, subprocess, sys
 
 SEEDING = ("pack_reads_kernel", "smem_sweep_kernel", "smem_fast_p3_kernel")
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 out = {"source": "ncu --set full --clock-control none (tools/ncu_round.sh), reports: " + ", ".join(sys.argv[1:]), "kernels": {}}
 for rep in sys.argv[1:]:
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
