@@ -174,12 +174,29 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
     __syncwarp();                                            // lanes leave the transition loop at different times: rejoin them here
     if (__ballot_sync(full, ts != S_EXIT) == 0) break;
     Intv o = {0, 0, 0}; bool have = false;
-    // ---- T: one table read
-    if (ts == S_NONE && kind == SK_T) {
-      if (mode == SM_J) o = unpack_entry(__ldg(ix.ktab + ktab_base(K) + q.code(pb, K)), &jm);
-      else if (mode == SM_F) o = tab(pb, pe - pb + 1);
-      else if (mode == SM_B) o = tab(pb - 1, pe - pb + 1);
-      else o = tab(pe - sL, sL);                             // window / level walk: the sL bases ending at pe
+    // ---- T and A share ONE load site: two 8-byte words, of a level-table entry (T) or of the 2-bit text (A).  Lanes of either
+    // kind issue their loads together instead of one mode after the other, each waiting out its own latency.
+    const bool isT = ts == S_NONE && kind == SK_T, isA = TEXT && ts == S_NONE && kind == SK_A;
+    uint64_t w0 = 0, w1 = 0, tp = 0;
+    {
+      const uint64_t *lp = nullptr;
+      if (isT) {
+        int tb, tL;
+        if (mode == SM_J) { tb = pb; tL = K; }
+        else if (mode == SM_F) { tb = pb; tL = pe - pb + 1; }
+        else if (mode == SM_B) { tb = pb - 1; tL = pe - pb + 1; }
+        else { tb = pe - sL; tL = sL; }                      // window / level walk: the sL bases ending at pe
+        lp = (const uint64_t *)(ix.ktab + ktab_base(tL) + q.code(tb, tL));
+      } else if (isA) {
+        tp = mode == SM_B ? (ik.x0 >= 32 ? ik.x0 - 32 : 0) : ik.x0 + (uint64_t)(pe - pb);   // first text symbol of the window
+        lp = ix.text + (tp >> 5);
+      }
+      if (lp) { w0 = __ldg(lp); w1 = __ldg(lp + 1); }
+    }
+    if (isT) {
+      int d;
+      o = unpack_entry(make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32)), &d);
+      if (mode == SM_J) jm = d;
       have = true;
     }
     // ---- X: bwt_extend on the index once enough lanes want one
@@ -226,35 +243,37 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
         } else { --sL; mode = SM_S; }                        // walk the levels down: everything longer is too rare
       }
     }
-    // ---- A: anchored interval: compare up to 32 bases of the read with the text
-    if (TEXT && ts == S_NONE && kind == SK_A) {
+    // ---- A: anchored interval: compare up to 32 bases of the read with the text (words loaded above)
+    if (isA) {
+      const int sh = (int)(tp & 31) << 1;
+      const uint64_t twin = sh ? (w0 << sh | w1 >> (64 - sh)) : w0;                       // 32 text symbols from tp, MSB first
       if (mode == SM_B) {
         int cap = pb - lb;                                   // read bases available on the left (>= 1)
         if ((uint64_t)cap > ik.x0) cap = (int)ik.x0;         // ... and text symbols
         const int want = min(cap, 32);
         int n = 0;
         if (want > 0) {
-          const uint64_t diff = q.win_end(pb) ^ text_win_end(ix.text, ik.x0);
+          // the 32 symbols before x0, the last one at bit 0 (fewer than 32: the top of word 0 shifted down)
+          const uint64_t tend = ik.x0 >= 32 ? twin : (ik.x0 > 0 ? w0 >> (64 - 2 * (int)ik.x0) : 0ull);
+          const uint64_t diff = q.win_end(pb) ^ tend;
           n = min(diff ? (__ffsll((long long)diff) - 1) >> 1 : 32, want);
         }
         pb -= n; ik.x0 -= (uint64_t)n;
         if (!(n == 32 && cap > 32)) ts = S_ENTRY_DONE;
       } else if (mode == SM_C) {                             // does the previous occurrence also cover [cand_end, f_end)?
         const int want = f_end - pe;
-        const uint64_t tp = ik.x0 + (uint64_t)(pe - pb);
-        const uint64_t diff = q.win(pe) ^ text_win(ix.text, tp);
+        const uint64_t diff = q.win(pe) ^ twin;
         const int n = diff ? __clzll((long long)diff) >> 1 : 32;
         if (n >= want && tp + (uint64_t)want <= ix.seq_len) { pe = f_end; ts = S_ENTRY_DONE; }
         else { mode = SM_CF; ts = S_ENTRY; }
       } else {                                               // forward sweep on a unique interval: runs to the first mismatch
         const int lim = q.next_n(pe);
         const int want = lim - pe;
-        const uint64_t tp = ik.x0 + (uint64_t)(pe - pb);
         const int64_t tcap = (int64_t)ix.seq_len - (int64_t)tp;
         const int w = (int)min((int64_t)min(want, 32), max(tcap, (int64_t)0));
         int n = 0;
         if (w > 0) {
-          const uint64_t diff = q.win(pe) ^ text_win(ix.text, tp);
+          const uint64_t diff = q.win(pe) ^ twin;
           n = min(diff ? __clzll((long long)diff) >> 1 : 32, w);
         }
         pe += n;
