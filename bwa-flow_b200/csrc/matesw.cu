@@ -5,8 +5,11 @@
 //
 // Why "run ahead + replay" is exact: the window of a call depends only on the anchoring region (a copy taken before any rescue,
 // src/bwa_wrapper.cpp:660-663), the orientation, the insert-size bounds and the mate's length -- never on the hits rescued so
-// far.  What does depend on them is WHETHER an orientation is tried (skip[], bwamem_pair.c:121-127), so the device aligns the
-// superset and the replay consumes what the reference would have computed.
+// far.  What does depend on them is WHETHER an orientation is tried (skip[], bwamem_pair.c:121-127).  Most pairs already have a
+// properly placed mate and skip everything, so the device runs ahead only the windows that are not skipped given the hits the
+// pair starts with; the replay consumes them in the reference's order, and a pair whose replay asks for a window that was not
+// run (an earlier rescue of the same pair changed the skip flags) is suspended, its window goes to the device with those of
+// the other suspended pairs, and its replay is redone -- rounds until no pair is suspended (almost always one).
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
@@ -99,6 +102,7 @@ static bool matesw_window(const bwaflow_ctx_t *c, const bwaflow_opt_t &o, const 
 
 using namespace bwaflow;
 
+struct MsJobRef { uint32_t key; int64_t res; };            // key = end << 20 | anchor index << 2 | orientation
 struct bwaflow_matesw_batch {
   bwaflow_ctx_t *ctx;
   bwaflow_pe_opt_t po;
@@ -111,12 +115,162 @@ struct bwaflow_matesw_batch {
   // host side
   std::vector<Reg> regs; std::vector<int64_t> reg_off, read_off;
   bwaflow_pestat_t pes[4];
-  std::vector<bwaflow_sw_job_t> jobs; std::vector<MsFill> fills;
-  std::vector<bwaflow_sw_result_t> res;
+  std::vector<bwaflow_sw_job_t> jobs; std::vector<MsFill> fills;       // the round being run
+  std::vector<int64_t> job_pair; std::vector<uint32_t> job_key;
+  int max_q, max_t;
+  std::vector<bwaflow_sw_result_t> res;                                 // results of all rounds
+  std::vector<std::vector<MsJobRef>> pair_jobs;                         // per pair: which windows have a result
+  std::vector<std::vector<Reg>> pair_out[2];
   std::vector<Reg> out; std::vector<int64_t> out_off;
-  int64_t n_sw;
+  int64_t n_sw, n_run; int rounds;
+  float kernel_ms; double cells;
   bool pending;
 };
+
+// one window of the current round
+static void ms_add_job(bwaflow_matesw_batch *b, int64_t pr, uint32_t key, int64_t q_src, int l_ms, int is_rev, int64_t rb, int64_t re)
+{
+  const bwaflow_opt_t &o = b->ctx->par.opt;
+  int64_t qo = 0, to = 0;
+  if (!b->jobs.empty()) { qo = b->jobs.back().q_off + b->jobs.back().qlen; to = b->jobs.back().t_off + b->jobs.back().tlen; }
+  bwaflow_sw_job_t jb;
+  jb.qlen = l_ms; jb.tlen = (int)(re - rb); jb._pad = 0; jb.q_off = qo; jb.t_off = to;
+  jb.xtra = 0x40000 | 0x80000 | (l_ms * o.a < 250 ? 0x10000 : 0) | (o.min_seed_len * o.a);   // bwamem_pair.c:153
+  MsFill f; f.rb = rb; f.q_src = q_src; f.l_ms = l_ms; f.tlen = jb.tlen; f.is_rev = is_rev; f._pad = 0; f.q_off = qo; f.t_off = to;
+  b->jobs.push_back(jb); b->fills.push_back(f); b->job_pair.push_back(pr); b->job_key.push_back(key);
+  if (l_ms > b->max_q) b->max_q = l_ms;
+  if (jb.tlen > b->max_t) b->max_t = jb.tlen;
+}
+
+// the current round's jobs on the device: upload, fill the byte pools from the reads and the reference, ksw_align2, results back
+static int ms_enqueue_round(bwaflow_matesw_batch *b)
+{
+  const int64_t nj = (int64_t)b->jobs.size();
+  const int64_t qo = nj ? b->jobs.back().q_off + b->jobs.back().qlen : 0, to = nj ? b->jobs.back().t_off + b->jobs.back().tlen : 0;
+  if (!b->sw || nj > b->sw_jobs || qo > b->sw_q || to > b->sw_t) {
+    if (b->sw) bwaflow_sw_batch_destroy(b->sw);
+    b->sw_jobs = nj * 2 + 1024; b->sw_q = qo * 2 + 4096; b->sw_t = to * 2 + 4096;
+    int r = bwaflow_sw_batch_create(b->ctx, b->sw_jobs, b->sw_q, b->sw_t, &b->sw);
+    if (r) return r;
+  }
+  if (nj > b->fill_cap) {
+    cudaFree(b->d_fill);
+    b->fill_cap = nj * 2 + 1024;
+    BF_CUDA(cudaMalloc(&b->d_fill, b->fill_cap * sizeof(MsFill)));
+  }
+  const SwDeviceView v = sw_device_view(b->sw);
+  if (nj) {
+    BF_CUDA(cudaMemcpyAsync(v.jobs, b->jobs.data(), nj * sizeof(bwaflow_sw_job_t), cudaMemcpyHostToDevice, b->stream));
+    BF_CUDA(cudaMemcpyAsync(b->d_fill, b->fills.data(), nj * sizeof(MsFill), cudaMemcpyHostToDevice, b->stream));
+  }
+  BF_CUDA(cudaEventRecord(b->tm.ev[1], b->stream));
+  if (nj) {
+    matesw_fill_kernel<<<(unsigned)((nj * 32 + 255) / 256), 256, 0, b->stream>>>(b->d_fill, nj, b->d_bases, b->ctx->ix, v.q, v.t);
+    int r = sw_launch_device(b->sw, nj, b->max_q, b->max_t, b->stream);
+    if (r) return r;
+  }
+  BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
+  const size_t base = b->res.size();
+  b->res.resize(base + (size_t)nj);
+  if (nj) BF_CUDA(cudaMemcpyAsync(b->res.data() + base, v.out, nj * sizeof(bwaflow_sw_result_t), cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaMemcpyAsync(v.h_ctl, v.d_ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  BF_CUDA(cudaEventRecord(b->tm.ev[3], b->stream));
+  return 0;
+}
+
+// waits for the round and files its results under their pairs
+static int ms_finish_round(bwaflow_matesw_batch *b)
+{
+  BF_CUDA(cudaStreamSynchronize(b->stream));
+  const SwDeviceView v = sw_device_view(b->sw);
+  BF_REQUIRE(v.h_ctl[1] == 0, -34, "mate rescue: a ksw_align2 job is outside the supported range (device error %d)", v.h_ctl[1]);
+  const size_t nj = b->jobs.size(), base = b->res.size() - nj;
+  for (size_t k = 0; k < nj; ++k) b->pair_jobs[(size_t)b->job_pair[k]].push_back(MsJobRef{b->job_key[k], (int64_t)(base + k)});
+  float ms = 0;
+  cudaEventElapsedTime(&ms, b->tm.ev[1], b->tm.ev[2]);
+  b->kernel_ms += ms;
+  b->cells += (double)*(unsigned long long *)(v.h_ctl + 2);
+  b->n_run += (int64_t)nj;
+  if (nj) ++b->rounds;
+  b->jobs.clear(); b->fills.clear(); b->job_pair.clear(); b->job_key.clear(); b->max_q = b->max_t = 1;
+  return 0;
+}
+
+// The rescue block of mem_sam_pe for pair pr (src/bwa_wrapper.cpp:657-668 with mem_matesw, bwa/bwamem_pair.c:114-183, inside).
+// enumerate = true: nothing is consumed; every window the calls would run GIVEN THE HITS THE PAIR STARTS WITH is added to the
+// round.  enumerate = false: the replay proper; returns false (pair suspended, its missing window added to the round) when a
+// call needs a window that has no result yet.
+static bool ms_pair(bwaflow_matesw_batch *b, int64_t pr, bool enumerate, std::vector<Reg> ma[2], int64_t *n_total)
+{
+  const bwaflow_opt_t &o = b->ctx->par.opt;
+  const int64_t l_pac = b->ctx->ix.l_pac;
+  const bwaflow_pestat_t *pes = b->pes;
+  std::vector<Reg> bb[2];
+  for (int i = 0; i < 2; ++i) {
+    const Reg *a = b->regs.data() + b->reg_off[2 * pr + i];
+    const int64_t na = b->reg_off[2 * pr + i + 1] - b->reg_off[2 * pr + i];
+    ma[i].assign(a, a + na);
+    for (int64_t j = 0; j < na; ++j)
+      if (a[j].score >= a[0].score - b->po.pen_unpaired) bb[i].push_back(a[j]);   // src/bwa_wrapper.cpp:660-663
+  }
+  const std::vector<MsJobRef> &have = b->pair_jobs[(size_t)pr];
+  int64_t total = 0;
+  for (int i = 0; i < 2; ++i) {
+    const int64_t mate = 2 * pr + (i ^ 1);
+    const int l_ms = (int)(b->read_off[mate + 1] - b->read_off[mate]);
+    std::vector<Reg> &m = ma[i ^ 1];
+    for (size_t j = 0; j < bb[i].size() && (int)j < b->po.max_matesw; ++j) {
+      const Reg &a = bb[i][j];
+      // ---- mem_matesw, bwa/bwamem_pair.c:114-183
+      int skip[4], n = 0;
+      for (int r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
+      for (size_t k = 0; k < m.size(); ++k) {
+        int64_t dist;
+        const int r = infer_dir(l_pac, a.rb, m[k].rb, &dist);
+        if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
+      }
+      if (skip[0] + skip[1] + skip[2] + skip[3] == 4) continue;
+      for (int r = 0; r < 4; ++r) {
+        if (skip[r]) continue;
+        int is_rev; int64_t rb, re;
+        if (matesw_window(b->ctx, o, pes, a, l_ms, r, &is_rev, &rb, &re)) {
+          const uint32_t key = (uint32_t)i << 20 | (uint32_t)j << 2 | (uint32_t)r;
+          if (enumerate) { ms_add_job(b, pr, key, b->read_off[mate], l_ms, is_rev, rb, re); continue; }
+          int64_t ri = -1;
+          for (const MsJobRef &h : have) if (h.key == key) { ri = h.res; break; }
+          if (ri < 0) { ms_add_job(b, pr, key, b->read_off[mate], l_ms, is_rev, rb, re); return false; }
+          const bwaflow_sw_result_t aln = b->res[(size_t)ri];
+          if (aln.score >= o.min_seed_len && aln.qb >= 0) {
+            Reg g;
+            memset(&g, 0, sizeof(g));
+            g.rid = a.rid;
+            g.n_comp_is_alt = (uint32_t)reg_is_alt(a) << 30;
+            g.qb = is_rev ? l_ms - (aln.qe + 1) : aln.qb;
+            g.qe = is_rev ? l_ms - aln.qb : aln.qe + 1;
+            g.rb = is_rev ? (l_pac << 1) - (rb + aln.te + 1) : rb + aln.tb;
+            g.re = is_rev ? (l_pac << 1) - (rb + aln.tb) : rb + aln.te + 1;
+            g.score = aln.score;
+            g.csub = aln.score2;
+            g.secondary = -1;
+            g.seedcov = (int)((g.re - g.rb < g.qe - g.qb ? g.re - g.rb : g.qe - g.qb) >> 1);
+            m.push_back(g);
+            size_t k;
+            for (k = 0; k + 1 < m.size(); ++k)
+              if (m[k].score < g.score) break;
+            const size_t at = k;
+            for (k = m.size() - 1; k > at; --k) m[k] = m[k - 1];
+            m[at] = g;
+          }
+          ++n;
+        }
+        if (n && !enumerate) m.resize((size_t)sort_dedup(b->po, (int)m.size(), m.data()));
+      }
+      total += n;
+    }
+  }
+  *n_total += total;
+  return true;
+}
 
 extern "C" {
 
@@ -225,71 +379,26 @@ int bwaflow_matesw_submit(bwaflow_matesw_batch_t *b, int64_t n_reads, const uint
   BF_REQUIRE(n_reads >= 0 && n_reads <= b->max_reads && (n_reads & 1) == 0 && read_off[n_reads] <= b->max_bases, -7,
              "bwaflow_matesw_submit: batch capacity exceeded or odd read count");
   BF_CUDA(cudaSetDevice(b->ctx->device));
-  const bwaflow_opt_t &o = b->ctx->par.opt;
   b->n_reads = n_reads;
   b->regs.assign(regs, regs + reg_off[n_reads]);
   b->reg_off.assign(reg_off, reg_off + n_reads + 1);
   b->read_off.assign(read_off, read_off + n_reads + 1);
   memcpy(b->pes, pes, sizeof(b->pes));
-  // every ksw_align2 call the rescue block can make, in the order the replay will meet them
-  b->jobs.clear(); b->fills.clear();
-  int64_t qo = 0, to = 0; int max_q = 1, max_t = 1;
-  if (!b->po.no_rescue)
-    for (int64_t pr = 0; pr < n_reads >> 1; ++pr)
-      for (int i = 0; i < 2; ++i) {
-        const Reg *a = b->regs.data() + reg_off[2 * pr + i];
-        const int64_t na = reg_off[2 * pr + i + 1] - reg_off[2 * pr + i];
-        const int64_t mate = 2 * pr + (i ^ 1);
-        const int l_ms = (int)(read_off[mate + 1] - read_off[mate]);
-        int taken = 0;
-        for (int64_t j = 0; j < na && taken < b->po.max_matesw; ++j) {
-          if (!(a[j].score >= a[0].score - b->po.pen_unpaired)) continue;
-          ++taken;
-          for (int r = 0; r < 4; ++r) {
-            if (pes[r].failed) continue;
-            int is_rev; int64_t rb, re;
-            if (!matesw_window(b->ctx, o, pes, a[j], l_ms, r, &is_rev, &rb, &re)) continue;
-            bwaflow_sw_job_t jb;
-            jb.qlen = l_ms; jb.tlen = (int)(re - rb); jb._pad = 0; jb.q_off = qo; jb.t_off = to;
-            jb.xtra = 0x40000 | 0x80000 | (l_ms * o.a < 250 ? 0x10000 : 0) | (o.min_seed_len * o.a);   // bwamem_pair.c:153
-            MsFill f; f.rb = rb; f.q_src = read_off[mate]; f.l_ms = l_ms; f.tlen = jb.tlen; f.is_rev = is_rev; f._pad = 0; f.q_off = qo; f.t_off = to;
-            b->jobs.push_back(jb); b->fills.push_back(f);
-            qo += l_ms; to += jb.tlen;
-            if (l_ms > max_q) max_q = l_ms;
-            if (jb.tlen > max_t) max_t = jb.tlen;
-          }
-        }
-      }
-  const int64_t nj = (int64_t)b->jobs.size();
-  if (!b->sw || nj > b->sw_jobs || qo > b->sw_q || to > b->sw_t) {
-    if (b->sw) bwaflow_sw_batch_destroy(b->sw);
-    b->sw_jobs = nj * 2 + 1024; b->sw_q = qo * 2 + 4096; b->sw_t = to * 2 + 4096;
-    int r = bwaflow_sw_batch_create(b->ctx, b->sw_jobs, b->sw_q, b->sw_t, &b->sw);
-    if (r) return r;
+  const int64_t n_pairs = n_reads >> 1;
+  b->pair_jobs.resize((size_t)n_pairs);
+  for (auto &v : b->pair_jobs) v.clear();
+  b->res.clear(); b->jobs.clear(); b->fills.clear(); b->job_pair.clear(); b->job_key.clear(); b->max_q = b->max_t = 1;
+  b->n_run = 0; b->rounds = 0; b->kernel_ms = 0; b->cells = 0;
+  // round 0: the windows the calls run given the hits every pair starts with
+  if (!b->po.no_rescue) {
+    std::vector<Reg> ma[2];
+    int64_t dummy = 0;
+    for (int64_t pr = 0; pr < n_pairs; ++pr) ms_pair(b, pr, true, ma, &dummy);
   }
-  if (nj > b->fill_cap) {
-    cudaFree(b->d_fill);
-    b->fill_cap = nj * 2 + 1024;
-    BF_CUDA(cudaMalloc(&b->d_fill, b->fill_cap * sizeof(MsFill)));
-  }
-  const SwDeviceView v = sw_device_view(b->sw);
   BF_CUDA(cudaEventRecord(b->tm.ev[0], b->stream));
   BF_CUDA(cudaMemcpyAsync(b->d_bases, bases, read_off[n_reads], cudaMemcpyHostToDevice, b->stream));
-  if (nj) {
-    BF_CUDA(cudaMemcpyAsync(v.jobs, b->jobs.data(), nj * sizeof(bwaflow_sw_job_t), cudaMemcpyHostToDevice, b->stream));
-    BF_CUDA(cudaMemcpyAsync(b->d_fill, b->fills.data(), nj * sizeof(MsFill), cudaMemcpyHostToDevice, b->stream));
-  }
-  BF_CUDA(cudaEventRecord(b->tm.ev[1], b->stream));
-  if (nj) {
-    matesw_fill_kernel<<<(unsigned)((nj * 32 + 255) / 256), 256, 0, b->stream>>>(b->d_fill, nj, b->d_bases, b->ctx->ix, v.q, v.t);
-    int r = sw_launch_device(b->sw, nj, max_q, max_t, b->stream);
-    if (r) return r;
-  }
-  BF_CUDA(cudaEventRecord(b->tm.ev[2], b->stream));
-  b->res.resize((size_t)nj);
-  if (nj) BF_CUDA(cudaMemcpyAsync(b->res.data(), v.out, nj * sizeof(bwaflow_sw_result_t), cudaMemcpyDeviceToHost, b->stream));
-  BF_CUDA(cudaMemcpyAsync(v.h_ctl, v.d_ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-  BF_CUDA(cudaEventRecord(b->tm.ev[3], b->stream));
+  int r = ms_enqueue_round(b);
+  if (r) return r;
   b->pending = true;
   return 0;
 }
@@ -298,98 +407,58 @@ int bwaflow_matesw_collect(bwaflow_matesw_batch_t *b, const bwaflow_alnreg_t **r
                            int64_t *n_sw, int64_t *n_jobs, bwaflow_timing_t *t)
 {
   BF_REQUIRE(b && b->pending, -22, "bwaflow_matesw_collect: nothing submitted");
-  BF_CUDA(cudaStreamSynchronize(b->stream));
   b->pending = false;
-  const SwDeviceView v = sw_device_view(b->sw);
-  BF_REQUIRE(v.h_ctl[1] == 0, -34, "mate rescue: a ksw_align2 job is outside the supported range (device error %d)", v.h_ctl[1]);
-  const bwaflow_opt_t &o = b->ctx->par.opt;
-  const int64_t l_pac = b->ctx->ix.l_pac;
-  const bwaflow_pestat_t *pes = b->pes;
-  b->out.clear(); b->out_off.assign(1, 0);
-  int64_t cur = 0, total = 0;
-  std::vector<Reg> ma[2], bb[2];
-  for (int64_t pr = 0; pr < b->n_reads >> 1; ++pr) {
-    for (int i = 0; i < 2; ++i) {
-      const Reg *a = b->regs.data() + b->reg_off[2 * pr + i];
-      const int64_t na = b->reg_off[2 * pr + i + 1] - b->reg_off[2 * pr + i];
-      ma[i].assign(a, a + na);
-      bb[i].clear();
-      for (int64_t j = 0; j < na; ++j)
-        if (a[j].score >= a[0].score - b->po.pen_unpaired) bb[i].push_back(a[j]);   // src/bwa_wrapper.cpp:660-663
-    }
-    if (!b->po.no_rescue)
-      for (int i = 0; i < 2; ++i) {
-        const int64_t mate = 2 * pr + (i ^ 1);
-        const int l_ms = (int)(b->read_off[mate + 1] - b->read_off[mate]);
-        std::vector<Reg> &m = ma[i ^ 1];
-        for (size_t j = 0; j < bb[i].size() && (int)j < b->po.max_matesw; ++j) {
-          const Reg &a = bb[i][j];
-          // ---- mem_matesw, bwa/bwamem_pair.c:114-183
-          int skip[4], n = 0;
-          for (int r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
-          for (size_t k = 0; k < m.size(); ++k) {
-            int64_t dist;
-            const int r = infer_dir(l_pac, a.rb, m[k].rb, &dist);
-            if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
-          }
-          const bool all_skipped = skip[0] + skip[1] + skip[2] + skip[3] == 4;
-          for (int r = 0; r < 4; ++r) {
-            if (pes[r].failed) continue;
-            int is_rev; int64_t rb, re;
-            const bool has_job = matesw_window(b->ctx, o, pes, a, l_ms, r, &is_rev, &rb, &re);
-            const int64_t job = has_job ? cur++ : -1;            // the device ran it whether or not the reference would have
-            if (all_skipped || skip[r]) continue;
-            if (has_job) {
-              const bwaflow_sw_result_t aln = b->res[(size_t)job];
-              if (aln.score >= o.min_seed_len && aln.qb >= 0) {
-                Reg g;
-                memset(&g, 0, sizeof(g));
-                g.rid = a.rid;
-                g.n_comp_is_alt = (uint32_t)reg_is_alt(a) << 30;
-                g.qb = is_rev ? l_ms - (aln.qe + 1) : aln.qb;
-                g.qe = is_rev ? l_ms - aln.qb : aln.qe + 1;
-                g.rb = is_rev ? (l_pac << 1) - (rb + aln.te + 1) : rb + aln.tb;
-                g.re = is_rev ? (l_pac << 1) - (rb + aln.tb) : rb + aln.te + 1;
-                g.score = aln.score;
-                g.csub = aln.score2;
-                g.secondary = -1;
-                g.seedcov = (int)((g.re - g.rb < g.qe - g.qb ? g.re - g.rb : g.qe - g.qb) >> 1);
-                m.push_back(g);
-                size_t k;
-                for (k = 0; k + 1 < m.size(); ++k)
-                  if (m[k].score < g.score) break;
-                const size_t at = k;
-                for (k = m.size() - 1; k > at; --k) m[k] = m[k - 1];
-                m[at] = g;
-              }
-              ++n;
-            }
-            if (n) m.resize((size_t)sort_dedup(b->po, (int)m.size(), m.data()));
-          }
-          total += n;
+  int r;
+  if ((r = ms_finish_round(b))) return r;
+  float h2d_ms = 0;
+  cudaEventElapsedTime(&h2d_ms, b->tm.ev[0], b->tm.ev[1]);
+  const int64_t n_pairs = b->n_reads >> 1;
+  for (int i = 0; i < 2; ++i) b->pair_out[i].resize((size_t)n_pairs);
+  std::vector<int64_t> todo((size_t)n_pairs), again;
+  for (int64_t pr = 0; pr < n_pairs; ++pr) todo[(size_t)pr] = pr;
+  int64_t total = 0;
+  std::vector<Reg> ma[2];
+  for (int round = 0; !todo.empty(); ++round) {
+    BF_REQUIRE(round < 64, -5, "mate rescue: the replay did not settle");
+    again.clear();
+    for (int64_t pr : todo) {
+      if (b->po.no_rescue) {
+        for (int i = 0; i < 2; ++i) {
+          const Reg *a = b->regs.data() + b->reg_off[2 * pr + i];
+          b->pair_out[i][(size_t)pr].assign(a, a + (b->reg_off[2 * pr + i + 1] - b->reg_off[2 * pr + i]));
         }
+        continue;
       }
+      int64_t n = 0;
+      if (ms_pair(b, pr, false, ma, &n)) {
+        total += n;
+        for (int i = 0; i < 2; ++i) b->pair_out[i][(size_t)pr].swap(ma[i]);
+      } else again.push_back(pr);
+    }
+    if (again.empty()) break;
+    if ((r = ms_enqueue_round(b))) return r;               // the windows the suspended pairs asked for
+    if ((r = ms_finish_round(b))) return r;
+    todo.swap(again);
+  }
+  b->out.clear(); b->out_off.assign(1, 0);
+  for (int64_t pr = 0; pr < n_pairs; ++pr)
     for (int i = 0; i < 2; ++i) {
-      b->out.insert(b->out.end(), ma[i].begin(), ma[i].end());
+      const std::vector<Reg> &v = b->pair_out[i][(size_t)pr];
+      b->out.insert(b->out.end(), v.begin(), v.end());
       b->out_off.push_back((int64_t)b->out.size());
     }
-  }
-  BF_REQUIRE(cur == (int64_t)b->jobs.size(), -5, "mate rescue: the replay met %lld windows, %lld were run", (long long)cur, (long long)b->jobs.size());
   b->n_sw = total;
   if (t) {
     memset(t, 0, sizeof(*t));
-    cudaEventElapsedTime(&t->h2d_ms, b->tm.ev[0], b->tm.ev[1]);
-    cudaEventElapsedTime(&t->kernel_ms, b->tm.ev[1], b->tm.ev[2]);
-    cudaEventElapsedTime(&t->d2h_ms, b->tm.ev[2], b->tm.ev[3]);
-    cudaEventElapsedTime(&t->total_ms, b->tm.ev[0], b->tm.ev[3]);
-    t->n_launches = b->jobs.empty() ? 0 : 2;
-    t->work_units = (double)*(unsigned long long *)(v.h_ctl + 2);
+    t->h2d_ms = h2d_ms; t->kernel_ms = b->kernel_ms; t->total_ms = h2d_ms + b->kernel_ms;
+    t->n_launches = 2 * b->rounds;
+    t->work_units = b->cells;
   }
   if (regs_out) *regs_out = b->out.data();
   if (reg_off_out) *reg_off_out = b->out_off.data();
   if (n_regs) *n_regs = (int64_t)b->out.size();
   if (n_sw) *n_sw = total;
-  if (n_jobs) *n_jobs = (int64_t)b->jobs.size();
+  if (n_jobs) *n_jobs = b->n_run;
   return 0;
 }
 
