@@ -80,6 +80,7 @@ def parse():
     ap.add_argument("--parity-reads", type=int, default=100_000, help="reads compared with the compiled reference in the CPU leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ext-microbench", action="store_true")
+    ap.add_argument("--no-sam-stage", action="store_true", help="skip the stage-5 (RegionsToSam) measurement on one record")
     ap.add_argument("--ext-jobs", type=int, default=10_000_000, help="extension jobs dumped for the config[1] micro-benchmark")
     ap.add_argument("--in-flight", type=int, default=2,
                     help="device batches in flight per GPU, each driven by its own host thread and stream (the FPGA stages give every "
@@ -597,6 +598,30 @@ def main():
             "counts": {"n_intv": parts[-1].n_intv, "n_pos": parts[-1].n_pos, "n_chains": parts[-1].n_chains,
                        "n_seeds": parts[-1].n_seeds, "n_regs": n_regs, "stage4_reads_left_by_first_replay": second_round[0], "stage4_second_round_jobs": second_round[1],
                        "stage4_reads_on_exact_kernel": n_exact_reads}}
+    # ---- stage 5 (RegionsToSam) on the first record of the step: regions of the hot path in, SAM text out (one worker; in the
+    # pipeline every stage worker runs its own record).  Not part of `value` / `e2e`: the headline metric is the path up to mem_alnreg_t.
+    sam_text = None
+    if world == 1 and not args.no_sam_stage:
+        n_sr = min(reads.n, reads_per_record)
+        s_off = np.array(read_off[:n_sr + 1], dtype=np.int64)
+        r_off = np.array(out["alnreg_off"][:n_sr + 1], dtype=np.int64)
+        s_regs = np.array(out["alnreg"][:r_off[-1]])
+        ctg_names = ["chr%d" % (i + 1) for i in range(len(ref.lengths))] if not hasattr(ref, "names") else [n if isinstance(n, str) else n.decode() for n in ref.names]
+        sb = capi.SamBatch(ctx, n_sr, int(s_off[-1]) + 16, ctg_names)
+        start_idx = int(rec_ids[0]) * reads_per_record
+        tms = []
+        for it in range(4):
+            sam_text, _, st = sb.process(bases[:s_off[-1]], reads.quals[:s_off[-1]], s_off, reads.names[:n_sr], s_regs, r_off, start_idx)
+            if it:
+                tms.append(st)
+        mean = lambda k: float(np.mean([getattr(t, k) for t in tms]))
+        line["sam_stage"] = {"what": "bwaflow_sam_process on one kflow record: mem_sort_dedup_patch, mem_pestat, mate rescue, pairing, CIGAR / MD / NM, SAM text",
+                             "reads": int(n_sr), "ms": mean("total_ms"), "pairs_per_s_one_worker": n_sr / 2 / (mean("total_ms") * 1e-3),
+                             "phases_ms": {k: mean(k + "_ms") for k in ("dedup", "matesw", "pair", "cigar", "text")},
+                             "device_ms": {"ksw_align2": mean("matesw_kernel_ms"), "mem_reg2aln": mean("cigar_kernel_ms")},
+                             "patch_alignments": int(tms[-1].n_patch_jobs), "rescue_windows": int(tms[-1].n_matesw_jobs),
+                             "rescues_used": int(tms[-1].n_matesw_used), "cigar_jobs": int(tms[-1].n_cigar_jobs), "sam_bytes": int(tms[-1].sam_bytes)}
+        sb.close()
     if not args.no_ext_microbench:
         line["ext_microbench"] = ext_microbench(ctx, peak_gcups, args.ext_jobs)
     if world == 1 and not args.no_cpu_baseline:
@@ -621,6 +646,16 @@ def main():
                                 "max_off_max": int(jobs["max_off"].max()) if len(jobs) else 0,
                                 "against": "oracle/_ref (the compiled reference: mem_seq2chain_wrapper + mem_chain2aln) on the same index"}
         rb.free()
+        if sam_text is not None:
+            # SAM parity at full record size: the reference's stages 2-5 on the same record (same start_idx), byte for byte (untimed)
+            n_sr = len(sam_text)
+            rb = cpu.R.batch(reads.slice(0, n_sr), int(rec_ids[0]) * reads_per_record)
+            rb.seq2chains()
+            rb.chains2regions()
+            r_sam, r_soff = rb.regions2sam()
+            line["sam_stage"]["sam_identical_to_reference"] = bool(bytes(r_sam) == b"".join(sam_text))
+            line["sam_stage"]["reference_sam_bytes"] = int(len(r_sam))
+            rb.free()
         line["cpu_baseline"] = {"value": sample / sec, "unit": "pairs/s", "cores": cpu.cores, "kind": "reference", "per_core": sample / sec / cpu.cores,
                                 "sample": "%d pairs, stages 2+4 of the compiled reference (oracle/_ref: bwa/*.c + src/bwa_wrapper.cpp), "
                                           "one thread per core, %.1f s" % (sample, sec)}

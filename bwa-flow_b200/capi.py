@@ -434,7 +434,8 @@ class SamOpt(C.Structure):
 
 class SamTiming(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("dedup_ms", "matesw_ms", "pair_ms", "cigar_ms", "text_ms", "total_ms")] + \
-               [(k, C.c_int64) for k in ("n_patch_jobs", "n_matesw_jobs", "n_matesw_used", "n_cigar_jobs", "sam_bytes")]
+               [(k, C.c_int64) for k in ("n_patch_jobs", "n_matesw_jobs", "n_matesw_used", "n_cigar_jobs", "sam_bytes")] + \
+               [(k, C.c_float) for k in ("matesw_kernel_ms", "cigar_kernel_ms")]
 
 
 def default_sam_opt():

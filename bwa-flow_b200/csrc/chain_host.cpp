@@ -111,6 +111,15 @@ void bwaflow_chain_opt_default(bwaflow_chain_opt_t *o)
   o->min_seed_len = 19; o->max_occ = 500; o->mask_level = 0.50f; o->drop_ratio = 0.50f;
 }
 
+int32_t bwaflow_max_read_len(const bwaflow_chain_opt_t *opt)
+{
+  bwaflow_chain_opt_t d;
+  if (!opt) { bwaflow_chain_opt_default(&d); opt = &d; }
+  int32_t len = 1023;                                        // row state of the seeding kernels
+  while (len > 0 && needs_seed_rescoring(*opt, len)) --len;  // monotone: longer reads are re-scored, shorter ones are not
+  return len;
+}
+
 int bwaflow_chain_build(const bwaflow_chain_opt_t *opt, int64_t l_pac, int32_t n_seqs, const int64_t *ctg_offset,
                         const int32_t *ctg_len, const int32_t *ctg_is_alt,
                         int64_t n_reads, const int64_t *read_off,

@@ -120,6 +120,7 @@ struct bwaflow_matesw_batch {
   int max_q, max_t;
   std::vector<bwaflow_sw_result_t> res;                                 // results of all rounds
   std::vector<std::vector<MsJobRef>> pair_jobs;                         // per pair: which windows have a result
+  std::vector<uint8_t> pair_live;                                       // pair has windows to replay
   std::vector<std::vector<Reg>> pair_out[2];
   std::vector<Reg> out; std::vector<int64_t> out_off;
   int64_t n_sw, n_run; int rounds;
@@ -200,16 +201,16 @@ static int ms_finish_round(bwaflow_matesw_batch *b)
 // enumerate = true: nothing is consumed; every window the calls would run GIVEN THE HITS THE PAIR STARTS WITH is added to the
 // round.  enumerate = false: the replay proper; returns false (pair suspended, its missing window added to the round) when a
 // call needs a window that has no result yet.
-static bool ms_pair(bwaflow_matesw_batch *b, int64_t pr, bool enumerate, std::vector<Reg> ma[2], int64_t *n_total)
+static bool ms_pair(bwaflow_matesw_batch *b, int64_t pr, bool enumerate, std::vector<Reg> ma[2], std::vector<Reg> bb[2], int64_t *n_total)
 {
   const bwaflow_opt_t &o = b->ctx->par.opt;
   const int64_t l_pac = b->ctx->ix.l_pac;
   const bwaflow_pestat_t *pes = b->pes;
-  std::vector<Reg> bb[2];
   for (int i = 0; i < 2; ++i) {
     const Reg *a = b->regs.data() + b->reg_off[2 * pr + i];
     const int64_t na = b->reg_off[2 * pr + i + 1] - b->reg_off[2 * pr + i];
     ma[i].assign(a, a + na);
+    bb[i].clear();
     for (int64_t j = 0; j < na; ++j)
       if (a[j].score >= a[0].score - b->po.pen_unpaired) bb[i].push_back(a[j]);   // src/bwa_wrapper.cpp:660-663
   }
@@ -391,10 +392,13 @@ int bwaflow_matesw_submit(bwaflow_matesw_batch_t *b, int64_t n_reads, const uint
   b->n_run = 0; b->rounds = 0; b->kernel_ms = 0; b->cells = 0;
   // round 0: the windows the calls run given the hits every pair starts with
   if (!b->po.no_rescue) {
-    std::vector<Reg> ma[2];
+    std::vector<Reg> ma[2], bb[2];
     int64_t dummy = 0;
-    for (int64_t pr = 0; pr < n_pairs; ++pr) ms_pair(b, pr, true, ma, &dummy);
+    for (int64_t pr = 0; pr < n_pairs; ++pr) ms_pair(b, pr, true, ma, bb, &dummy);
   }
+  // a pair without a window in round 0 rescues nothing, so its hits never change and no later call can ask for one: it is final
+  b->pair_live.assign((size_t)n_pairs, 0);
+  for (int64_t pr : b->job_pair) b->pair_live[(size_t)pr] = 1;
   BF_CUDA(cudaEventRecord(b->tm.ev[0], b->stream));
   BF_CUDA(cudaMemcpyAsync(b->d_bases, bases, read_off[n_reads], cudaMemcpyHostToDevice, b->stream));
   int r = ms_enqueue_round(b);
@@ -414,23 +418,16 @@ int bwaflow_matesw_collect(bwaflow_matesw_batch_t *b, const bwaflow_alnreg_t **r
   cudaEventElapsedTime(&h2d_ms, b->tm.ev[0], b->tm.ev[1]);
   const int64_t n_pairs = b->n_reads >> 1;
   for (int i = 0; i < 2; ++i) b->pair_out[i].resize((size_t)n_pairs);
-  std::vector<int64_t> todo((size_t)n_pairs), again;
-  for (int64_t pr = 0; pr < n_pairs; ++pr) todo[(size_t)pr] = pr;
+  std::vector<int64_t> todo, again;
+  for (int64_t pr = 0; pr < n_pairs; ++pr) if (b->pair_live[(size_t)pr]) todo.push_back(pr);
   int64_t total = 0;
-  std::vector<Reg> ma[2];
+  std::vector<Reg> ma[2], bb[2];
   for (int round = 0; !todo.empty(); ++round) {
     BF_REQUIRE(round < 64, -5, "mate rescue: the replay did not settle");
     again.clear();
     for (int64_t pr : todo) {
-      if (b->po.no_rescue) {
-        for (int i = 0; i < 2; ++i) {
-          const Reg *a = b->regs.data() + b->reg_off[2 * pr + i];
-          b->pair_out[i][(size_t)pr].assign(a, a + (b->reg_off[2 * pr + i + 1] - b->reg_off[2 * pr + i]));
-        }
-        continue;
-      }
       int64_t n = 0;
-      if (ms_pair(b, pr, false, ma, &n)) {
+      if (ms_pair(b, pr, false, ma, bb, &n)) {
         total += n;
         for (int i = 0; i < 2; ++i) b->pair_out[i][(size_t)pr].swap(ma[i]);
       } else again.push_back(pr);
@@ -441,10 +438,13 @@ int bwaflow_matesw_collect(bwaflow_matesw_batch_t *b, const bwaflow_alnreg_t **r
     todo.swap(again);
   }
   b->out.clear(); b->out_off.assign(1, 0);
+  b->out.reserve(b->regs.size() + 64);
   for (int64_t pr = 0; pr < n_pairs; ++pr)
     for (int i = 0; i < 2; ++i) {
-      const std::vector<Reg> &v = b->pair_out[i][(size_t)pr];
-      b->out.insert(b->out.end(), v.begin(), v.end());
+      if (b->pair_live[(size_t)pr]) {
+        const std::vector<Reg> &v = b->pair_out[i][(size_t)pr];
+        b->out.insert(b->out.end(), v.begin(), v.end());
+      } else b->out.insert(b->out.end(), b->regs.begin() + b->reg_off[2 * pr + i], b->regs.begin() + b->reg_off[2 * pr + i + 1]);
       b->out_off.push_back((int64_t)b->out.size());
     }
   b->n_sw = total;

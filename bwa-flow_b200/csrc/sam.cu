@@ -622,9 +622,10 @@ int bwaflow_sam_process(bwaflow_sam_batch_t *b, int64_t n_reads, const uint8_t *
       rc = bwaflow_matesw_submit(b->mb, n_reads, bases, read_off, b->r1.data(), b->off1.data(), pes);
       if (rc) return rc;
       const bwaflow_alnreg_t *mr; const int64_t *mo; int64_t mn, n_sw, n_jobs;
-      rc = bwaflow_matesw_collect(b->mb, &mr, &mo, &mn, &n_sw, &n_jobs, nullptr);
+      bwaflow_timing_t mt;
+      rc = bwaflow_matesw_collect(b->mb, &mr, &mo, &mn, &n_sw, &n_jobs, &mt);
       if (rc) return rc;
-      tm.n_matesw_jobs = n_jobs; tm.n_matesw_used = n_sw;
+      tm.n_matesw_jobs = n_jobs; tm.n_matesw_used = n_sw; tm.matesw_kernel_ms = mt.kernel_ms;
       b->r2.assign(mr, mr + mn);
       b->off2.assign(mo, mo + n_reads + 1);
       cur = b->r2.data(); cur_off = b->off2.data();
@@ -675,8 +676,10 @@ int bwaflow_sam_process(bwaflow_sam_batch_t *b, int64_t n_reads, const uint8_t *
     rc = bwaflow_cigar_submit(b->cb, n_reads, bases, read_off, n, b->job_read.data() + s, b->job_reg.data() + s);
     if (rc) return rc;
     const bwaflow_aln_t *al; const uint32_t *cg; const char *md;
-    rc = bwaflow_cigar_collect(b->cb, &al, &cg, &md, nullptr);
+    bwaflow_timing_t ct;
+    rc = bwaflow_cigar_collect(b->cb, &al, &cg, &md, &ct);
     if (rc) return rc;
+    tm.cigar_kernel_ms += ct.kernel_ms;
     const int64_t cig_base = (int64_t)co.cig.size(), md_base = (int64_t)co.md.size();
     int64_t n_cig = 0, n_md = 0;
     for (int64_t j = 0; j < n; ++j) {

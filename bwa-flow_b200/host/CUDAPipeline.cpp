@@ -86,6 +86,17 @@ void SeqsToChainsCUDA::compute(int wid)
       ready = this->getInput(rec);
     }
     if (!ready && !(ready = this->getInput(rec))) break;
+    {                                                          // reads this backend cannot take
+      const int max_len = bwaflow_max_read_len(env_ ? &env_->chain_opt() : nullptr);
+      int bad = -1;
+      for (int i = 0; i < rec.batch_num && bad < 0; ++i) if (rec.seqs[i].l_seq > max_len) bad = i;
+      if (bad >= 0) {
+        if (unsupported_) { this->pushOutput(unsupported_(rec)); continue; }
+        throw std::runtime_error("SeqsToChainsCUDA: read " + std::to_string(rec.start_idx + (uint64_t)bad) + " has " + std::to_string(rec.seqs[bad].l_seq) +
+                                 " bases; this backend takes reads of up to " + std::to_string(max_len) +
+                                 " (mem_flt_chained_seeds re-scoring and the 1 024-base row state are not implemented): route the record to the CPU stages");
+      }
+    }
     bases.clear(); off.assign(1, 0);
     for (int i = 0; i < rec.batch_num; ++i) {                  // in-place nt4, as stage 2 must (src/bwa_wrapper.cpp:124-125)
       bseq1_t *s = &rec.seqs[i];

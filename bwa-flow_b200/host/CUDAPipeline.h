@@ -3,7 +3,9 @@
 // "Fast mode": stage 2 submits the whole hot path (bwaflow_hot_submit) and pushes a ChainsRecord with tag = 1 whose chain_ref
 // carries the device batch; ChainsPipe passes tag == 1 records through (src/Pipeline.cpp:409); stage 4 collects the regions.
 #pragma once
+#include <functional>
 #include <map>
+#include <string>
 #include "kflow_shim.h"      // <kflow/MapPartitionStage.h> etc. in a bwa-flow build
 #include "records.h"         // "Pipeline.h" in a bwa-flow build
 #include "../../include/bwaflow_cuda.h"
@@ -81,6 +83,10 @@ class SeqsToChainsCUDA : public kestrelFlow::MapPartitionStage<SeqsRecord, Chain
       : kestrelFlow::MapPartitionStage<SeqsRecord, ChainsRecord, INPUT_DEPTH, COMPUTE_DEPTH>(n_workers, false), env_(env), pool_(nullptr), ctx_(nullptr),
         pos_(pos), max_reads_(env->max_reads()), max_bases_(env->max_bases()) {}
   void compute(int wid);
+  // Records holding a read longer than bwaflow_max_read_len() cannot run on this backend.  Without a handler such a record is
+  // a std::runtime_error that names the read; an integration that keeps the reference's CPU stage registers it here
+  // (e.g. [&](SeqsRecord const &r) { return cpu_seq2chain_stage.compute(r); }) and the record takes that route instead.
+  void setUnsupportedHandler(std::function<ChainsRecord(SeqsRecord const &)> h) { unsupported_ = h; }
 
  private:
   CUDAEnv *env_ = nullptr;
@@ -88,6 +94,7 @@ class SeqsToChainsCUDA : public kestrelFlow::MapPartitionStage<SeqsRecord, Chain
   bwaflow_ctx_t *ctx_;
   SeedPositionTable *pos_;
   int64_t max_reads_, max_bases_;
+  std::function<ChainsRecord(SeqsRecord const &)> unsupported_;
 };
 
 class ChainsPipe : public kestrelFlow::MapStage<ChainsRecord, ChainsRecord, COMPUTE_DEPTH, COMPUTE_DEPTH> {

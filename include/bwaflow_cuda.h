@@ -187,6 +187,10 @@ typedef struct {
 } bwaflow_chain_opt_t;
 typedef struct bwaflow_chain_result bwaflow_chain_result_t;
 void bwaflow_chain_opt_default(bwaflow_chain_opt_t *opt);
+/* Longest read the path accepts with these options: below 1 024 bases (row state of the seeding kernels) and short enough that
+ * mem_flt_chained_seeds (bwa/bwamem.c:607-624) does not re-score seeds -- 724 bases at default options.  A batch holding a longer
+ * read is refused as a whole (-34); a caller that must take such reads checks lengths first and routes the record elsewhere. */
+int32_t bwaflow_max_read_len(const bwaflow_chain_opt_t *opt);
 int bwaflow_chain_build(const bwaflow_chain_opt_t *opt, int64_t l_pac, int32_t n_seqs, const int64_t *ctg_offset,
                         const int32_t *ctg_len, const int32_t *ctg_is_alt /* may be NULL */,
                         int64_t n_reads, const int64_t *read_off,
@@ -313,6 +317,7 @@ void bwaflow_sam_opt_default(bwaflow_sam_opt_t *so);       /* flag = PE | NO_MUL
 typedef struct {
   float dedup_ms, matesw_ms, pair_ms, cigar_ms, text_ms, total_ms;     /* host wall clock per phase (the device work is inside) */
   int64_t n_patch_jobs, n_matesw_jobs, n_matesw_used, n_cigar_jobs, sam_bytes;
+  float matesw_kernel_ms, cigar_kernel_ms;                             /* of which on the device (CUDA events): ksw_align2 / mem_reg2aln kernels */
 } bwaflow_sam_timing_t;
 typedef struct bwaflow_sam_batch bwaflow_sam_batch_t;
 /* ctg_names: n_seqs NUL-terminated names (bns->anns[i].name); ctg_is_alt / ctg_anno (XR:Z with MEM_F_REF_HDR) may be NULL;

@@ -32,9 +32,9 @@ def main():
         t0 = time.time()
         sam, pes, t = sb.process(nt4, reads.quals, reads.offsets, reads.names, out["alnreg"], out["alnreg_off"], k * reads.n)
         wall = time.time() - t0
-        print("record %d: %d reads, %d regions -> %.1f MB SAM; hot path %.1f ms on the device; stage 5 %.1f ms (dedup %.1f rescue %.1f pair %.1f cigar %.1f text %.1f), "
+        print("record %d: %d reads, %d regions -> %.1f MB SAM; hot path %.1f ms on the device; stage 5 %.1f ms (dedup %.1f rescue %.1f [device %.2f] pair %.1f cigar %.1f [device %.2f] text %.1f), "
               "python wall %.0f ms; %d patch, %d rescue windows (%d used), %d CIGAR jobs; %.2f M pairs/s through stage 5"
-              % (k, reads.n, len(out["alnreg"]), t.sam_bytes / 1e6, fp.last.total_ms, t.total_ms, t.dedup_ms, t.matesw_ms, t.pair_ms, t.cigar_ms,
+              % (k, reads.n, len(out["alnreg"]), t.sam_bytes / 1e6, fp.last.total_ms, t.total_ms, t.dedup_ms, t.matesw_ms, t.matesw_kernel_ms, t.pair_ms, t.cigar_ms, t.cigar_kernel_ms,
                  t.text_ms, wall * 1e3, t.n_patch_jobs, t.n_matesw_jobs, t.n_matesw_used, t.n_cigar_jobs, reads.n / 2 / t.total_ms / 1e3))
     fp.close(); sb.close(); ctx.close(); B.close()
 

@@ -1,5 +1,7 @@
 """CPU: the C-ABI library loads and exports every symbol include/bwaflow_cuda.h declares (no compute calls)."""
 import ctypes
+
+import numpy as np
 import os
 import re
 
@@ -40,3 +42,18 @@ def test_struct_sizes_match_reference_layouts():
     assert capi.SEED.itemsize == 24      # mem_seed_t
     assert capi.ALNREG.itemsize == 88    # mem_alnreg_t
     assert ctypes.sizeof(capi.Opt) == 88
+
+
+def test_max_read_len_follows_mem_flt_chained_seeds():
+    """reads long enough for mem_flt_chained_seeds to re-score seeds (bwa/bwamem.c:607-624: MEM_MINSC_COEF * log(l) <= MEM_SEEDSW_COEF * l)
+    are outside the path; bwaflow_max_read_len reports the last length below that (and below the 1 024-base row state)"""
+    import math
+    from bwaflow_b200 import capi
+    L = capi.lib()
+    L.bwaflow_max_read_len.argtypes = [ctypes.c_void_p]
+    got = L.bwaflow_max_read_len(None)
+    exp = max(l for l in range(1, 1024) if np.float32(5.5) * math.log(l) > np.float32(0.05) * l)
+    assert got == exp == 724
+    co = capi.default_chain_opt()
+    co.min_chain_weight = 40            # then min_l = MEM_HSP_COEF * min_chain_weight = 44: re-scoring from 880 bases on
+    assert L.bwaflow_max_read_len(ctypes.byref(co)) == 879

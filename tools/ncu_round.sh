@@ -4,7 +4,7 @@
 # exported to CSV on the box (raw page; source page of the seeding kernel) and deleted: gpurun_out/ must stay under 64 MiB.
 # usage: ncu_round.sh tag
 tag=${1:-r02a}
-B="python bench.py --steps 1 --warmup 1 --in-flight 1 --no-cpu-baseline --no-ext-microbench"
+B="python bench.py --steps 1 --warmup 1 --in-flight 1 --no-cpu-baseline --no-ext-microbench --no-sam-stage"
 $B > gpurun_out/plain_$tag.json 2> gpurun_out/plain_$tag.err || { echo "plain run failed"; tail -5 gpurun_out/plain_$tag.err; exit 1; }
 timeout 1200 ncu --set full --clock-control none --import-source on \
   -k regex:'pack_reads_kernel|smem_sweep_kernel|smem_fast_p3_kernel|seedpos_dev_kernel|chain_kernel' --launch-skip 10 -c 5 \
