@@ -15,8 +15,10 @@
 
 #ifdef __CUDACC__
 #define BF_HD __host__ __device__ __forceinline__
+#define BF_UNROLL _Pragma("unroll")
 #else
 #define BF_HD inline
+#define BF_UNROLL
 #endif
 
 namespace bwaflow {
@@ -67,20 +69,24 @@ BF_HD int intv2rid(const Ctg &c, int64_t rb, int64_t re)
 }
 
 // ---- bwa/kbtree.h over chain indices -----------------------------------------------------------------------
-// __kb_getp_aux: index of the last key <= k in the node (first of a run of equal keys); *r = sign of the comparison
+// __kb_getp_aux: index of the last key <= k in the node (first of a run of equal keys); *r = sign of the comparison.
+// klib's binary search is a lower bound over the node's sorted keys, i.e. the number of keys below k: all (at most 9) key
+// positions are loaded at once and counted, one memory latency instead of a chain of three or four dependent probes -- the
+// chaining kernel is bound by exactly that latency, and a read inside a repeat walks trees several levels deep per seed.
 BF_HD int bt_find(const Scratch &S, const Node &x, int64_t k, int *r)
 {
-  if (x.n == 0) return -1;
-  int begin = 0, end = x.n;
-  while (begin < end) {
-    const int mid = (begin + end) >> 1;
-    if (x.kpos[mid] < k) begin = mid + 1; else end = mid;
-  }
-  if (begin == x.n) { *r = 1; return x.n - 1; }
-  const int64_t kp = x.kpos[begin];
-  *r = (kp < k) - (k < kp);
-  if (*r < 0) --begin;
-  return begin;
+  const int n = x.n;
+  int64_t kp[BT_MAXK];
+BF_UNROLL
+  for (int m = 0; m < BT_MAXK; ++m) kp[m] = x.kpos[m];          // entries at and beyond n are never looked at below
+  if (n == 0) return -1;
+  int lt = 0, le = 0;
+BF_UNROLL
+  for (int m = 0; m < BT_MAXK; ++m) { lt += (m < n) & (kp[m] < k); le += (m < n) & (kp[m] <= k); }
+  if (lt == n) { *r = 1; return n - 1; }
+  if (le > lt) { *r = 0; return lt; }                            // kpos[lt] == k
+  *r = -1;
+  return lt - 1;
 }
 // kb_intervalp (only `lower` is used by the caller)
 BF_HD int bt_lower(const Scratch &S, int64_t k)
@@ -231,27 +237,48 @@ BF_HD int chain_flt(Scratch &S, const bwaflow_chain_opt_t &o, int n_chn)
   n_chn = k;
   if (n_chn == 0) return 0;
   klib_introsort(n_chn, a, FltLt());
+  // The overlap filter (:356-380) compares every chain with every chain kept so far: quadratic for a read inside a repeat (hundreds
+  // of chains of similar weight, all kept).  What the inner loop reads of a kept chain -- query span, weight, ALT flag -- sits in a
+  // compact array in kept order (16 bytes per entry, in the memory of S.chains, which is free once the chains are in S.sorted), and
+  // its `first` in an array of its own, so that four entries are loaded ahead of the tests instead of one dependent chain of loads
+  // (kept index -> chain -> fields) per entry.
+  struct KeptEnt { int beg, end, w, alt; };
+  KeptEnt *K = (KeptEnt *)S.chains;
+  int *F = (int *)(K + n_chn);                               // first[] of the kept chains (16 + 4 bytes per entry <= sizeof(Chain))
   int n_kept = 0;
-  a[0].kept = 3; S.kept[n_kept++] = 0;
+  a[0].kept = 3; S.kept[n_kept] = 0; K[n_kept] = KeptEnt{a[0].beg, a[0].end, a[0].w, a[0].is_alt}; F[n_kept] = -1; ++n_kept;
+  const int msl2 = o.min_seed_len << 1;
   for (i = 1; i < n_chn; ++i) {
-    int large_ovlp = 0, kk;
-    const int bi = a[i].beg, ei = a[i].end, wi = a[i].w, alt_i = a[i].is_alt;
-    for (kk = 0; kk < n_kept; ++kk) {
-      const int j = S.kept[kk];
-      const int bj = a[j].beg, ej = a[j].end;
-      const int b_max = bj > bi ? bj : bi, e_min = ej < ei ? ej : ei;
-      if (e_min > b_max && (!a[j].is_alt || alt_i)) {
-        const int li = ei - bi, lj = ej - bj, min_l = li < lj ? li : lj;
-        if (e_min - b_max >= min_l * o.mask_level && min_l < o.max_chain_gap) {
-          large_ovlp = 1;
-          if (a[j].first < 0) a[j].first = i;
-          if (wi < a[j].w * o.drop_ratio && a[j].w - wi >= o.min_seed_len << 1) break;
+    int large_ovlp = 0, kk = 0;
+    const int bi = a[i].beg, ei = a[i].end, wi = a[i].w, alt_i = a[i].is_alt, li = ei - bi;
+    bool dropped = false;
+    while (kk < n_kept && !dropped) {
+      KeptEnt e[4];
+      const int nb = n_kept - kk < 4 ? n_kept - kk : 4;
+      BF_UNROLL
+      for (int u = 0; u < 4; ++u) e[u] = K[kk + (u < nb ? u : 0)];
+      BF_UNROLL
+      for (int u = 0; u < 4; ++u) {
+        if (u >= nb || dropped) continue;
+        const int bj = e[u].beg, ej = e[u].end;
+        const int b_max = bj > bi ? bj : bi, e_min = ej < ei ? ej : ei;
+        if (e_min > b_max && (!e[u].alt || alt_i)) {
+          const int lj = ej - bj, min_l = li < lj ? li : lj;
+          if (e_min - b_max >= min_l * o.mask_level && min_l < o.max_chain_gap) {
+            large_ovlp = 1;
+            if (F[kk + u] < 0) F[kk + u] = i;
+            if (wi < e[u].w * o.drop_ratio && e[u].w - wi >= msl2) dropped = true;
+          }
         }
       }
+      kk += nb;
     }
-    if (kk == n_kept) { S.kept[n_kept++] = i; a[i].kept = large_ovlp ? 2 : 3; }
+    if (!dropped) {
+      S.kept[n_kept] = i; K[n_kept] = KeptEnt{bi, ei, wi, alt_i}; F[n_kept] = -1; ++n_kept;
+      a[i].kept = large_ovlp ? 2 : 3;
+    }
   }
-  for (i = 0; i < n_kept; ++i) { const Chain &c = a[S.kept[i]]; if (c.first >= 0) a[c.first].kept = 1; }
+  for (i = 0; i < n_kept; ++i) if (F[i] >= 0) a[F[i]].kept = 1;
   for (i = k = 0; i < n_chn; ++i) {
     if (a[i].kept == 0 || a[i].kept == 3) continue;
     if (++k >= o.max_chain_extend) break;
