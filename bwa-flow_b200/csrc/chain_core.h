@@ -221,36 +221,52 @@ struct FltLt { BF_HD bool operator()(const Chain &a, const Chain &b) const { ret
 BF_HD int chn_beg(const Scratch &S, const Chain &c) { return S.seeds[c.head].s.qbeg; }
 BF_HD int chn_end(const Scratch &S, const Chain &c) { return S.seeds[c.tail].s.qbeg + S.seeds[c.tail].s.len; }
 
-// mem_chain_flt, bwa/bwamem.c:336-394 on S.sorted[0..n_chn); returns the number of surviving chains (compacted in place)
-BF_HD int chain_flt(Scratch &S, const bwaflow_chain_opt_t &o, int n_chn)
+// mem_chain_flt, bwa/bwamem.c:336-394 on S.sorted[0..n_chn), in three steps so that the device can run the middle one -- the overlap
+// filter, quadratic in the number of chains for a read inside a repeat -- with a whole warp (hotpath.cu).
+struct KeptEnt { int beg, end, w, alt; };                      // what the filter reads of a kept chain
+BF_HD KeptEnt *flt_kept_ents(const Scratch &S) { return (KeptEnt *)S.chains; }            // S.chains is free once the chains are in S.sorted
+BF_HD int *flt_kept_first(const Scratch &S, int n_chn) { return (int *)(flt_kept_ents(S) + n_chn); }   // 16 + 4 bytes per entry <= sizeof(Chain)
+
+// (1) weights, query spans, minimum weight, klib introsort by weight (:341-354); returns the number of chains left
+BF_HD int flt_prepare(Scratch &S, const bwaflow_chain_opt_t &o, int n_chn)
 {
   Chain *a = S.sorted;
-  if (n_chn == 0) return 0;
-  int k = 0, i;
-  for (i = 0; i < n_chn; ++i) {
+  int k = 0;
+  for (int i = 0; i < n_chn; ++i) {
     Chain &c = a[i];
     c.first = -1; c.kept = 0;
     c.w = chain_weight(S, c);
     c.beg = chn_beg(S, c); c.end = chn_end(S, c);
     if (c.w >= o.min_chain_weight) a[k++] = c;
   }
-  n_chn = k;
-  if (n_chn == 0) return 0;
-  klib_introsort(n_chn, a, FltLt());
-  // The overlap filter (:356-380) compares every chain with every chain kept so far: quadratic for a read inside a repeat (hundreds
-  // of chains of similar weight, all kept).  What the inner loop reads of a kept chain -- query span, weight, ALT flag -- sits in a
-  // compact array in kept order (16 bytes per entry, in the memory of S.chains, which is free once the chains are in S.sorted), and
-  // its `first` in an array of its own, so that four entries are loaded ahead of the tests instead of one dependent chain of loads
-  // (kept index -> chain -> fields) per entry.
-  struct KeptEnt { int beg, end, w, alt; };
-  KeptEnt *K = (KeptEnt *)S.chains;
-  int *F = (int *)(K + n_chn);                               // first[] of the kept chains (16 + 4 bytes per entry <= sizeof(Chain))
+  if (k) klib_introsort(k, a, FltLt());
+  return k;
+}
+
+// one kept chain against chain i (:359-371): bit 0 = significant overlap, bit 1 = chain i is dropped here
+BF_HD int flt_test(const bwaflow_chain_opt_t &o, const KeptEnt &e, int bi, int ei, int wi, int alt_i)
+{
+  const int b_max = e.beg > bi ? e.beg : bi, e_min = e.end < ei ? e.end : ei;
+  if (e_min > b_max && (!e.alt || alt_i)) {
+    const int li = ei - bi, lj = e.end - e.beg, min_l = li < lj ? li : lj;
+    if (e_min - b_max >= min_l * o.mask_level && min_l < o.max_chain_gap)
+      return 1 | ((wi < e.w * o.drop_ratio && e.w - wi >= o.min_seed_len << 1) ? 2 : 0);
+  }
+  return 0;
+}
+
+// (2) the overlap filter (:355-380), one thread: kept chains in a compact array in kept order, four entries loaded ahead of the
+// tests instead of one dependent chain of loads (kept index -> chain -> fields) per entry.  Returns the number of kept chains.
+BF_HD int flt_filter(Scratch &S, const bwaflow_chain_opt_t &o, int n_chn)
+{
+  Chain *a = S.sorted;
+  KeptEnt *K = flt_kept_ents(S);
+  int *F = flt_kept_first(S, n_chn);
   int n_kept = 0;
   a[0].kept = 3; S.kept[n_kept] = 0; K[n_kept] = KeptEnt{a[0].beg, a[0].end, a[0].w, a[0].is_alt}; F[n_kept] = -1; ++n_kept;
-  const int msl2 = o.min_seed_len << 1;
-  for (i = 1; i < n_chn; ++i) {
+  for (int i = 1; i < n_chn; ++i) {
     int large_ovlp = 0, kk = 0;
-    const int bi = a[i].beg, ei = a[i].end, wi = a[i].w, alt_i = a[i].is_alt, li = ei - bi;
+    const int bi = a[i].beg, ei = a[i].end, wi = a[i].w, alt_i = a[i].is_alt;
     bool dropped = false;
     while (kk < n_kept && !dropped) {
       KeptEnt e[4];
@@ -260,16 +276,9 @@ BF_HD int chain_flt(Scratch &S, const bwaflow_chain_opt_t &o, int n_chn)
       BF_UNROLL
       for (int u = 0; u < 4; ++u) {
         if (u >= nb || dropped) continue;
-        const int bj = e[u].beg, ej = e[u].end;
-        const int b_max = bj > bi ? bj : bi, e_min = ej < ei ? ej : ei;
-        if (e_min > b_max && (!e[u].alt || alt_i)) {
-          const int lj = ej - bj, min_l = li < lj ? li : lj;
-          if (e_min - b_max >= min_l * o.mask_level && min_l < o.max_chain_gap) {
-            large_ovlp = 1;
-            if (F[kk + u] < 0) F[kk + u] = i;
-            if (wi < e[u].w * o.drop_ratio && e[u].w - wi >= msl2) dropped = true;
-          }
-        }
+        const int t = flt_test(o, e[u], bi, ei, wi, alt_i);
+        if (t & 1) { large_ovlp = 1; if (F[kk + u] < 0) F[kk + u] = i; }
+        if (t & 2) dropped = true;
       }
       kk += nb;
     }
@@ -278,6 +287,15 @@ BF_HD int chain_flt(Scratch &S, const bwaflow_chain_opt_t &o, int n_chn)
       a[i].kept = large_ovlp ? 2 : 3;
     }
   }
+  return n_kept;
+}
+
+// (3) shadowed hits, max_chain_extend, compaction (:381-393); returns the number of surviving chains
+BF_HD int flt_finish(Scratch &S, const bwaflow_chain_opt_t &o, int n_chn, int n_kept)
+{
+  Chain *a = S.sorted;
+  const int *F = flt_kept_first(S, n_chn);
+  int i, k;
   for (i = 0; i < n_kept; ++i) if (F[i] >= 0) a[F[i]].kept = 1;
   for (i = k = 0; i < n_chn; ++i) {
     if (a[i].kept == 0 || a[i].kept == 3) continue;
@@ -298,7 +316,8 @@ BF_HD bool needs_seed_rescoring(const bwaflow_chain_opt_t &o, int len)
 // One read.  intv[0..n_intv) sorted by info, positions of interval i at pos[pos_off[i]-pos_base .. ).  Chains land in
 // S.sorted[0..ret) (traversal order filtered by mem_chain_flt), their seeds are the linked lists in S.seeds.
 // *frac_rep receives (float)l_rep/len (src/bwa_wrapper.cpp:273-280,318).
-BF_HD int chain_read(Scratch &S, const bwaflow_chain_opt_t &o, const Ctg &ctg, int len, const bwaflow_intv_t *intv, int64_t n_intv,
+// chain_seeds = mem_chain_postprocess and the first step of mem_chain_flt (weights, sort): S.sorted[0..ret) by weight.
+BF_HD int chain_seeds(Scratch &S, const bwaflow_chain_opt_t &o, const Ctg &ctg, int len, const bwaflow_intv_t *intv, int64_t n_intv,
                      const int64_t *pos, const int64_t *pos_off, float *frac_rep)
 {
   S.n_seeds = S.n_chains = S.n_nodes = 0;
@@ -337,7 +356,21 @@ BF_HD int chain_read(Scratch &S, const bwaflow_chain_opt_t &o, const Ctg &ctg, i
   const int n = bt_inorder(S);
   for (int i = 0; i < n; ++i) S.sorted[i] = S.chains[S.order[i]];
   *frac_rep = (float)l_rep / len;
-  return chain_flt(S, o, n);
+  return flt_prepare(S, o, n);
+}
+
+// mem_chain_flt's remaining steps on what chain_seeds left in S.sorted[0..n)
+BF_HD int chain_filter(Scratch &S, const bwaflow_chain_opt_t &o, int n)
+{
+  if (n == 0) return 0;
+  return flt_finish(S, o, n, flt_filter(S, o, n));
+}
+
+// One read, everything on the calling thread
+BF_HD int chain_read(Scratch &S, const bwaflow_chain_opt_t &o, const Ctg &ctg, int len, const bwaflow_intv_t *intv, int64_t n_intv,
+                     const int64_t *pos, const int64_t *pos_off, float *frac_rep)
+{
+  return chain_filter(S, o, chain_seeds(S, o, ctg, len, intv, n_intv, pos, pos_off, frac_rep));
 }
 
 } // namespace chain

@@ -36,23 +36,84 @@ __device__ __forceinline__ Scratch read_scratch(const ChainArgs &a, int64_t r)
   return S;
 }
 
+// The overlap filter of mem_chain_flt (bwa/bwamem.c:355-380) for ONE read by a whole warp.  Chain i is tested against the chains kept
+// so far, 32 at a time; the sequential scan stops at the first kept chain that drops it, so every test the scan would not have
+// reached is discarded: `first` is only set (and large_ovlp only raised) up to and including that entry, exactly as the scan does.
+// Same arrays and the same result as chain::flt_filter.
+constexpr int CHAIN_FLT_WARP_MIN = 64;     // chains of a read from which the warp takes the filter over (quadratic work: a read inside a repeat has hundreds)
+__device__ int flt_filter_warp(Chain *a, KeptEnt *K, int *F, int *kept, int n_chn, const bwaflow_chain_opt_t &o, int lane)
+{
+  const unsigned full = 0xffffffffu;
+  if (lane == 0) { a[0].kept = 3; kept[0] = 0; K[0] = KeptEnt{a[0].beg, a[0].end, a[0].w, a[0].is_alt}; F[0] = -1; }
+  int n_kept = 1;
+  __syncwarp();
+  for (int i = 1; i < n_chn; ++i) {
+    const int bi = a[i].beg, ei = a[i].end, wi = a[i].w, alt_i = a[i].is_alt;     // one address for the warp
+    int large = 0;
+    bool dropped = false;
+    for (int base = 0; base < n_kept && !dropped; base += 32) {
+      const int kk = base + lane;
+      const int t = kk < n_kept ? flt_test(o, K[kk], bi, ei, wi, alt_i) : 0;
+      const unsigned ov = __ballot_sync(full, t & 1), br = __ballot_sync(full, t & 2);
+      unsigned upto = full;
+      if (br) { const int p = __ffs(br) - 1; upto = p == 31 ? full : (2u << p) - 1u; dropped = true; }
+      if (ov & upto) large = 1;
+      if ((t & 1) && ((upto >> lane) & 1u) && F[kk] < 0) F[kk] = i;
+    }
+    if (!dropped) {
+      if (lane == 0) { kept[n_kept] = i; K[n_kept] = KeptEnt{bi, ei, wi, alt_i}; F[n_kept] = -1; a[i].kept = large ? 2 : 3; }
+      ++n_kept;
+    }
+    __syncwarp();                                            // lane 0's append before the next chain's tests
+  }
+  return n_kept;
+}
+
 #ifndef CHAIN_MIN_BLOCKS
 #define CHAIN_MIN_BLOCKS 12      // 40 registers: 48 warps per SM hide more of the B-tree walk's load latency (5.2 -> 4.8 ms; 16 blocks / 32 registers spill too much: 5.6 ms)
 #endif
 __global__ void __launch_bounds__(128, CHAIN_MIN_BLOCKS) chain_kernel(const ChainArgs a)
 {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  bool act = r < a.n_reads;
+  int len = 0, n = 0, n_kept = 0;
+  int64_t i0 = 0, i1 = 0;
+  float fr = 0.f;
+  if (act) {
+    len = (int)(a.read_off[r + 1] - a.read_off[r]);
+    if (len >= a.opt.min_seed_len && needs_seed_rescoring(a.opt, len)) { atomicExch(a.err, 1); act = false; }
+  }
+  if (act) {
+    i0 = a.intv_off[r]; i1 = a.intv_off[r + 1];
+    if (i1 > a.out_cap || a.pos_off[i1] > a.pos_cap) act = false;          // left to the redo with larger buffers
+  }
+  Scratch S;
+  S.seeds = nullptr; S.chains = nullptr; S.nodes = nullptr; S.order = nullptr; S.sorted = nullptr; S.kept = nullptr;
+  S.n_seeds = S.n_chains = S.n_nodes = S.root = 0;
+  if (act) {
+    S = read_scratch(a, r);
+    n = chain_seeds(S, a.opt, a.ctg, len, a.intv + i0, i1 - i0, a.pos, a.pos_off + i0, &fr);
+  }
+  // the overlap filter: a read with few chains on its own thread, a read with many by the whole warp, one after the other
+  const bool heavy = act && n >= CHAIN_FLT_WARP_MIN;
+  if (act && !heavy && n > 0) n_kept = flt_filter(S, a.opt, n);
+  for (unsigned hm = __ballot_sync(full, heavy); hm; hm &= hm - 1) {
+    const int L = __ffs(hm) - 1;
+    Chain *sa = (Chain *)__shfl_sync(full, (unsigned long long)S.sorted, L);
+    KeptEnt *K = (KeptEnt *)__shfl_sync(full, (unsigned long long)S.chains, L);
+    int *kp = (int *)__shfl_sync(full, (unsigned long long)S.kept, L);
+    const int nn = __shfl_sync(full, n, L);
+    const int nk = flt_filter_warp(sa, K, (int *)(K + nn), kp, nn, a.opt, lane);
+    if (lane == L) n_kept = nk;
+  }
   if (r >= a.n_reads) return;
-  const int len = (int)(a.read_off[r + 1] - a.read_off[r]);
-  if (len >= a.opt.min_seed_len && needs_seed_rescoring(a.opt, len)) { atomicExch(a.err, 1); a.n_chains[r] = 0; a.n_seeds[r] = 0; return; }
-  const int64_t i0 = a.intv_off[r], i1 = a.intv_off[r + 1];
-  if (i1 > a.out_cap || a.pos_off[i1] > a.pos_cap) { a.n_chains[r] = 0; a.n_seeds[r] = 0; return; }
-  Scratch S = read_scratch(a, r);
-  float fr;
-  const int n = chain_read(S, a.opt, a.ctg, len, a.intv + i0, i1 - i0, a.pos, a.pos_off + i0, &fr);
+  if (act && n > 0) n = flt_finish(S, a.opt, n, n_kept);
   int ns = 0;
-  for (int c = 0; c < n; ++c) ns += S.sorted[c].n;
-  a.n_chains[r] = n; a.n_seeds[r] = ns; a.frac_rep[r] = fr;
+  if (act) for (int c = 0; c < n; ++c) ns += S.sorted[c].n;
+  a.n_chains[r] = act ? n : 0; a.n_seeds[r] = ns;
+  if (act) a.frac_rep[r] = fr;
 }
 
 // second pass: flat chains/seeds in the layout stage 4 takes (chains of read r at chain_off[r], seeds contiguous per chain)
