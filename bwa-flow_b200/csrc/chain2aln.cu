@@ -459,12 +459,14 @@ __global__ void c2a_spec_fill(int side, int64_t n_chains, const SpecDesc *desc, 
 
 // One thread per read: mem_chain2aln's seed loop (bwa/bwamem.c:676-792) in the reference's order, with the two extensions of
 // a chain's first seed taken from the speculative waves.  Sets strag[r] (and leaves no regions) when the read needs more.
-// `again`: second replay, only for the reads the first one left (strag[r] != 0), now with the wave-B results in `a`.
-__global__ void c2a_replay_kernel(C2AArgs a, int64_t n_reads, uint8_t *skipped, uint8_t *strag, int again)
+// WARP = false: the read on the calling thread.  WARP = true: all 32 lanes of the warp work on the same read (a read inside a repeat
+// has hundreds of chains, and the containment scan over the regions found so far makes the loop quadratic): every lane follows the
+// same control flow on the same values, the scan for the first containing region is split 32 regions at a time, lane 0 stores.
+template <bool WARP>
+__device__ void c2a_replay_read(const C2AArgs &a, int64_t r, uint8_t *skipped, uint8_t *strag, int lane)
 {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_reads) return;
-  if (again && !strag[r]) return;
+  const unsigned full = 0xffffffffu;
+  const bool writer = !WARP || lane == 0;
   const C2AOpt o = a.o;
   const int lq = (int)(a.read_off[r + 1] - a.read_off[r]);
   bwaflow_alnreg_t *av = a.regs + a.sbase[a.chain_off[r]];
@@ -476,23 +478,29 @@ __global__ void c2a_replay_kernel(C2AArgs a, int64_t n_reads, uint8_t *skipped, 
     const bwaflow_seed_t *sd = a.sseeds + s_base;
     for (int p = 0; p < ch.n_seeds; ++p) {
       const bwaflow_seed_t s = sd[p];
-      int i;
-      for (i = 0; i < n_av; ++i) {                             // :680-696
+      auto contains = [&](int i) -> bool {                     // :680-696: region i contains the seed and the seed is on its diagonal band
         const bwaflow_alnreg_t *q = &av[i];
         const int64_t prb = q->rb, pre = q->re; const int pqb = q->qb, pqe = q->qe;
-        if (s.rbeg < prb || s.rbeg + s.len > pre || s.qbeg < pqb || s.qbeg + s.len > pqe) continue;
-        if ((double)(s.len - q->seedlen0) > .1 * lq) continue;
+        if (s.rbeg < prb || s.rbeg + s.len > pre || s.qbeg < pqb || s.qbeg + s.len > pqe) return false;
+        if ((double)(s.len - q->seedlen0) > .1 * lq) return false;
         const int pw = q->w;
         int qd = s.qbeg - pqb; int64_t rdd = s.rbeg - prb;
         int mg = max_gap(o, qd < rdd ? qd : (int)rdd);
         int w = mg < pw ? mg : pw;
-        if (qd - rdd < w && rdd - qd < w) break;
+        if (qd - rdd < w && rdd - qd < w) return true;
         qd = pqe - (s.qbeg + s.len); rdd = pre - (s.rbeg + s.len);
         mg = max_gap(o, qd < rdd ? qd : (int)rdd);
         w = mg < pw ? mg : pw;
-        if (qd - rdd < w && rdd - qd < w) break;
+        return qd - rdd < w && rdd - qd < w;
+      };
+      bool found = false;
+      if (WARP) {
+        for (int base = 0; base < n_av && !found; base += 32)
+          found = __ballot_sync(full, base + lane < n_av && contains(base + lane)) != 0;
+      } else {
+        for (int i = 0; i < n_av && !found; ++i) found = contains(i);
       }
-      if (i < n_av) {                                          // :697-712
+      if (found) {                                             // :697-712
         int e;
         for (e = p - 1; e >= 0; --e) {
           if (skipped[s_base + e]) continue;
@@ -501,7 +509,11 @@ __global__ void c2a_replay_kernel(C2AArgs a, int64_t n_reads, uint8_t *skipped, 
           if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
           if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
         }
-        if (e < 0) { skipped[s_base + p] = 1; continue; }
+        if (e < 0) {
+          if (writer) skipped[s_base + p] = 1;
+          if (WARP) __syncwarp();
+          continue;
+        }
       }
       const bwaflow_ext_result_t *xl, *xr;
       if (!spec_lookup(a, ci, p, s_base + p, &xl, &xr)) { bail = true; break; }   // not run ahead
@@ -528,16 +540,42 @@ __global__ void c2a_replay_kernel(C2AArgs a, int64_t n_reads, uint8_t *skipped, 
         const bwaflow_seed_t t = sd[k];
         if (t.qbeg >= a_qb && t.qbeg + t.len <= a_qe && t.rbeg >= a_rb && t.rbeg + t.len <= a_re) cov += t.len;
       }
-      bwaflow_alnreg_t g;
-      memset(&g, 0, sizeof(g));
-      g.rb = a_rb; g.re = a_re; g.qb = a_qb; g.qe = a_qe; g.rid = ch.rid; g.score = a_score; g.truesc = a_truesc;
-      g.w = o.w; g.seedcov = cov; g.seedlen0 = s.len; g.frac_rep = ch.frac_rep;
-      av[n_av++] = g;
+      if (writer) {
+        bwaflow_alnreg_t g;
+        memset(&g, 0, sizeof(g));
+        g.rb = a_rb; g.re = a_re; g.qb = a_qb; g.qe = a_qe; g.rid = ch.rid; g.score = a_score; g.truesc = a_truesc;
+        g.w = o.w; g.seedcov = cov; g.seedlen0 = s.len; g.frac_rep = ch.frac_rep;
+        av[n_av] = g;
+      }
+      ++n_av;
+      if (WARP) __syncwarp();
     }
   }
-  strag[r] = bail ? 1 : 0;
-  if (bail) atomicAdd(a.err + 1, 1);                       // reads left to the exact kernel (reported, not an error; reset before a second replay)
-  a.n_regs[r] = bail ? 0 : n_av;
+  if (writer) {
+    strag[r] = bail ? 1 : 0;
+    if (bail) atomicAdd(a.err + 1, 1);                     // reads left to the exact kernel (reported, not an error; reset before a second replay)
+    a.n_regs[r] = bail ? 0 : n_av;
+  }
+}
+
+// `again`: second replay, only for the reads the first one left (strag[r] != 0), now with the wave-B results in `a`.
+constexpr int C2A_REPLAY_WARP_MIN = 64;     // seeds of a read from which the warp replays it together
+__global__ void c2a_replay_kernel(C2AArgs a, int64_t n_reads, uint8_t *skipped, uint8_t *strag, int again)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  const bool act = r < n_reads && !(again && !strag[r]);
+  bool heavy = false;
+  if (act) {
+    heavy = a.sbase[a.chain_off[r + 1]] - a.sbase[a.chain_off[r]] >= C2A_REPLAY_WARP_MIN;
+    if (!heavy) c2a_replay_read<false>(a, r, skipped, strag, lane);
+  }
+  for (unsigned hm = __ballot_sync(full, heavy); hm; hm &= hm - 1) {
+    const int64_t rr = __shfl_sync(full, (long long)r, __ffs(hm) - 1);
+    c2a_replay_read<true>(a, rr, skipped, strag, lane);
+    __syncwarp();
+  }
 }
 
 // wave B candidates: every later seed of the chains of the reads the first replay left
