@@ -24,6 +24,7 @@ struct bwaflow_smem_batch {
   int blocks_per_launch;
   // smem_fast.cu
   uint64_t *d_packed; int fast_blocks_per_sm, sweep_blocks_per_sm, x_min;
+  int *d_defer; int heavy_min;      // smem_sweep.cu: reads handed to the warp-per-read kernel
   bool want_rows;                   // intervals leave the device as BWT rows (interval API): no text-anchored entries
   bool count_blocks;                // this launch counts the reference's occ-block touches (exact instances)
   bool pending;

@@ -432,6 +432,7 @@ int bwaflow::smem_launch(bwaflow_smem_batch *b)
   const int64_t nr = b->n_reads;
   cudaStream_t st = b->stream;
   BF_CUDA(cudaMemsetAsync(b->d_ctl, 0, 8 * sizeof(int), st));
+  BF_CUDA(cudaMemsetAsync(b->d_defer, 0, 2 * sizeof(int), st));
   BF_CUDA(cudaMemsetAsync(b->d_off, 0, (nr + 1) * 8, st));
   if (nr == 0) return 0;
   const bwaflow_opt_t &o = b->ctx->par.opt;
@@ -440,7 +441,7 @@ int bwaflow::smem_launch(bwaflow_smem_batch *b)
   a.counts = b->d_counts; a.ctl = b->d_ctl; a.blocks = (unsigned long long *)(b->d_ctl + 4); a.ix = b->ctx->ix;
   a.min_seed_len = o.min_seed_len; a.split_len = (int)(o.min_seed_len * o.split_factor + .499);
   a.split_width = o.split_width; a.max_mem_intv = o.max_mem_intv;
-  a.packed = b->d_packed; a.x_min = b->x_min;
+  a.packed = b->d_packed; a.x_min = b->x_min; a.defer = b->d_defer; a.heavy_min = b->heavy_min;
   const bool count = b->count_blocks;
   if (b->max_len < 256 && !getenv("BWAFLOW_SMEM_LEGACY")) {
     // reads shorter than 256 bases: table / text-anchored kernels (smem_fast.cu).  Text anchoring needs the full suffix
@@ -613,6 +614,9 @@ int bwaflow_smem_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max
   BF_CUDA(cudaMalloc(&b->d_off, (max_reads + 2) * 8));
   BF_CUDA(cudaMallocHost(&b->h_off, (max_reads + 2) * 8));
   BF_CUDA(cudaMalloc(&b->d_ctl, 8 * sizeof(int)));
+  BF_CUDA(cudaMalloc(&b->d_defer, (max_reads + 4) * sizeof(int)));
+  b->heavy_min = 40;                             // forward matches of one call; ordinary reads have about 20 (the table levels plus a few)
+  if (const char *e = getenv("BWAFLOW_SMEM_HEAVY_MIN")) b->heavy_min = atoi(e);
   BF_CUDA(cudaMallocHost(&b->h_ctl, 8 * sizeof(int)));
   int r = smem_alloc_slots(b, 32);
   if (r) return r;
@@ -647,7 +651,7 @@ void bwaflow_smem_batch_destroy(bwaflow_smem_batch_t *b)
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->stream);
   cudaFree(b->d_bases); cudaFree(b->d_read_off); cudaFree(b->d_counts); cudaFree(b->d_cnt64); cudaFree(b->d_off);
-  cudaFreeHost(b->h_off); cudaFree(b->d_ctl); cudaFreeHost(b->h_ctl); cudaFree(b->d_slots); cudaFree(b->d_out);
+  cudaFreeHost(b->h_off); cudaFree(b->d_ctl); cudaFree(b->d_defer); cudaFreeHost(b->h_ctl); cudaFree(b->d_slots); cudaFree(b->d_out);
   cudaFreeHost(b->h_out); cudaFree(b->d_tmp); cudaFree(b->d_pcnt); cudaFree(b->d_poff); cudaFreeHost(b->h_poff);
   cudaFree(b->d_pos); cudaFreeHost(b->h_pos); cudaFree(b->d_packed); cudaFreeHost(b->h_stat);
   b->tm.destroy();

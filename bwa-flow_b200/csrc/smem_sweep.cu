@@ -87,6 +87,16 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
   for (;;) {
     // ---- the entry boundary (every ~4 steps of a lane): one straight-line block so that the lanes at a boundary run it together
     while (ts == S_ENTRY || ts == S_ENTRY_DONE) {
+      if (ts == S_ENTRY && fi == 0 && fwd_n >= a.heavy_min) {
+        // A call with this many forward matches is a read inside a repeat: its intervals stay large along the whole read and the
+        // leftward searches below cost (matches x read length) index steps, one after the other on this lane -- tens of
+        // milliseconds for a single read while the rest of the grid has long finished.  Such a read is handed, whole, to
+        // smem_heavy_kernel, which spreads the searches of a call over a warp.
+        a.defer[2 + atomicAdd(a.defer, 1)] = (int)r;
+        a.counts[r] = 0;
+        ts = S_FETCH;
+        break;
+      }
       if (ts == S_ENTRY_DONE) {                              // candidate logic (:392-400, :418-427) and the skip rule (:431-443)
         if (fi > 0 && pb > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
         cand = ik; cand_beg = pb; cand_end = f_end; lb = pb;
@@ -283,12 +293,142 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
   }
 }
 
+// Passes 1 and 2 of mem_collect_intv_new for the reads the sweep kernel handed over, ONE WARP PER READ.  Per call of
+// bwt_smem1a_new (src/bwa_wrapper.cpp:325-450): the forward sweep (:338-363) step by step on the index, every lane the same; then
+// the leftmost begin of every forward match -- the interval of q[b, e_i) has at least min_intv rows, b does not cross an N or the
+// read start -- 32 matches at a time, one per lane, each by plain leftward bwt_extend steps from the match's own interval (these
+// searches are independent: the bound the sweep kernel takes from the previous match only saves steps, interval sizes being
+// monotone in the pattern); then the candidate / emit logic (:392-400, :418-427, :431-443) over the 32 results in order.  No table
+// or text shortcuts: the reads that come here spend their time on large intervals.  Intervals leave as BWT rows.
 template <int MAXL>
-static int sweep_launch_t(const SmemArgs &a, int grid, bool text, cudaStream_t st)
+__global__ void __launch_bounds__(128) smem_heavy_kernel(const SmemArgs a)
+{
+  using R = Row<MAXL>;
+  constexpr int WROW = R::ROW_BYTES / 8;
+  extern __shared__ uint64_t s_heavy[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  constexpr int WSTRIDE = (WROW + 1) + 2 * MAXL + 2 * 32;      // row (padded to 16 bytes) + MAXL forward matches + 32 results, in 8-byte words
+  uint64_t *wbase = s_heavy + (size_t)wib * WSTRIDE;
+  LaneRead<MAXL> q;
+  q.bind(wbase);
+  uint4 *fwd = (uint4 *)(wbase + WROW + 1);                    // forward matches of the call: packed interval + end
+  uint4 *res = fwd + MAXL;                                     // results of the 32 matches in flight: packed interval + begin
+  const DevIndex &ix = a.ix;
+  const int msl = a.min_seed_len;
+  for (;;) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(a.defer + 1, 1);
+    slot = __shfl_sync(full, slot, 0);
+    if (slot >= a.defer[0]) break;
+    const int64_t r = a.defer[2 + slot];
+    const int len = (int)(a.read_off[r + 1] - a.read_off[r]);
+    bwaflow_intv_t *mem = a.slots + r * a.cap;
+    int n_mem = 0;
+    __syncwarp();
+    if (lane == 0) q.load(a.packed, r, len);
+    __syncwarp();
+    q.len = len;
+    { uint32_t any = 0; for (int t = 0; t < R::W; ++t) any |= q.nm[t]; q.anyN = any != 0; }
+    auto push_mem = [&](const Intv &v, int beg, int end) {
+      if (lane == 0 && n_mem < a.cap) {
+        bwaflow_intv_t o; o.x[0] = v.x0; o.x[1] = v.x1; o.x[2] = v.x2; o.info = (uint64_t)(uint32_t)beg << 32 | (uint32_t)end;
+        mem[n_mem] = o;
+      }
+      ++n_mem;
+    };
+    // one call of bwt_smem1a_new from sx with min_intv mi; returns the end of the longest forward match
+    auto call = [&](int sx, int mi) -> int {
+      unsigned long long nbk = 0;
+      int n = 0, pe = sx + 1;
+      Intv ik = set_intv(ix, q.base(sx));
+      for (;;) {                                               // forward sweep, :338-363
+        if (pe >= len || q.isN(pe)) { if (lane == 0) fwd[n] = pack_entry(ik, pe); ++n; break; }
+        const Intv o = extend1(ix, ik, 0, 3 - q.base(pe), &nbk);
+        const bool changed = o.x2 != ik.x2;
+        if (changed) { if (lane == 0) fwd[n] = pack_entry(ik, pe); ++n; }
+        if (changed && o.x2 < (uint64_t)mi) break;
+        ik = o; ++pe;
+      }
+      __syncwarp();
+      const int nb = q.prev_n(sx) + 1;
+      int fi = 0, cand_beg = 0, cand_end = 0, last_end = 0;
+      Intv cand = {0, 0, 0};
+      for (int base = 0; base < n; base += 32) {
+        const int my = base + lane;
+        int pb = sx, e_my = 0;
+        Intv im = {0, 0, 0};
+        bool go = false;
+        if (my < n) { im = unpack_entry(fwd[my], &e_my); go = pb > nb; }
+        while (__any_sync(full, go)) {                         // leftward extension of 32 matches, one index step each per round
+          if (go) {
+            const Intv o = extend1(ix, im, 1, q.base(pb - 1), &nbk);
+            if (o.x2 < (uint64_t)mi) go = false;
+            else { im = o; --pb; go = pb > nb; }
+          }
+        }
+        if (my < n) res[lane] = pack_entry(im, pb);
+        __syncwarp();
+        const int lim = n - base < 32 ? n - base : 32;
+        for (int u = 0; u < lim; ++u) {                        // the matches in order, every lane alike
+          const int j = base + u;
+          if (j < fi) continue;                                // passed over by the skip rule below
+          int pbj, f_end;
+          const Intv ij = unpack_entry(res[u], &pbj);
+          f_end = entry_pos(fwd[j]);
+          if (fi > 0 && pbj > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+          cand = ij; cand_beg = pbj; cand_end = f_end;
+          ++fi;
+          if (fi < n) {
+            int stop = 0, max_len = cand_beg + entry_pos(fwd[fi]);
+            while (max_len < msl && fi < n) {
+              ++fi;
+              if (fi < n) stop = entry_pos(fwd[fi]);
+              max_len = cand_beg + stop;
+            }
+          }
+          if (fi >= n && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
+        }
+        __syncwarp();
+      }
+      last_end = entry_pos(fwd[n - 1]);
+      __syncwarp();
+      return last_end;
+    };
+    if (len >= msl && len < MAXL) {
+      int x = 0;                                               // pass 1, :214-218
+      while (x < len) {
+        while (x < len && q.isN(x)) ++x;
+        if (x >= len) break;
+        x = call(x, 1);
+      }
+      const int old_n = n_mem < a.cap ? n_mem : a.cap;         // pass 2, :220-226
+      __syncwarp();
+      for (int k2 = 0; k2 < old_n; ++k2) {
+        const bwaflow_intv_t p = mem[k2];
+        const int s = (int)(p.info >> 32), e = (int)(uint32_t)p.info;
+        if (e - s < a.split_len || p.x[2] > (uint64_t)a.split_width) continue;
+        if (q.isN((s + e) >> 1)) continue;
+        call((s + e) >> 1, (int)p.x[2] + 1);
+      }
+    }
+    if (lane == 0) {
+      a.counts[r] = n_mem;
+      if (n_mem > a.cap) atomicExch(a.ctl + 1, 1);
+    }
+  }
+}
+
+template <int MAXL>
+static int sweep_launch_t(const SmemArgs &a, int grid, int heavy_grid, bool text, cudaStream_t st)
 {
   const size_t sh = 128 * (size_t)Row<MAXL>::ROW_BYTES;
   if (text) smem_sweep_kernel<MAXL, true><<<grid, 128, sh, st>>>(a);
   else smem_sweep_kernel<MAXL, false><<<grid, 128, sh, st>>>(a);
+  // the reads handed over (none on most batches: the warps find an empty queue and leave)
+  const size_t shh = 4 * (size_t)(Row<MAXL>::ROW_BYTES / 8 + 1 + 2 * MAXL + 2 * 32) * 8;
+  BF_CUDA(cudaFuncSetAttribute(smem_heavy_kernel<MAXL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shh));
+  smem_heavy_kernel<MAXL><<<heavy_grid, 128, shh, st>>>(a);
   BF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -299,7 +439,8 @@ int smem_sweep_launch(bwaflow_smem_batch *b, const SmemArgs &a, bool text)
   const int64_t want = (b->n_reads + 127) / 128;
   const int64_t cap = (int64_t)b->ctx->n_sm * b->sweep_blocks_per_sm;
   const int grid = (int)(want < cap ? want : cap);
-  return b->max_len < 160 ? sweep_launch_t<160>(a, grid, text, b->stream) : sweep_launch_t<256>(a, grid, text, b->stream);
+  const int hg = b->ctx->n_sm * 4;
+  return b->max_len < 160 ? sweep_launch_t<160>(a, grid, hg, text, b->stream) : sweep_launch_t<256>(a, grid, hg, text, b->stream);
 }
 
 int smem_sweep_setup(bwaflow_smem_batch *b)

@@ -182,3 +182,29 @@ def test_smem_slot_overflow_regrows(index_c1, golden_c1):
         assert intv[ioff[i]:ioff[i + 1]].tobytes() == exp.tobytes(), i
     b.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("case,heavy_min", [("c1", 1), ("c5", 1), ("c5", 12)])
+def test_smem_warp_per_read_kernel_matches_golden(case, heavy_min, request, monkeypatch):
+    """smem_heavy_kernel (one warp per read: the reads the sweep kernel hands over because a call found many forward matches, i.e.
+    reads inside repeats).  heavy_min = 1 hands EVERY read over, so the kernel is held to the golden intervals on all reads of both
+    cases; 12 mixes the two kernels inside one batch (a read may be handed over in the middle of pass 1 or in pass 2).  Also in the
+    hot path's anchored mode, where its rows and the sweep kernel's text-anchored entries meet in one interval list."""
+    from bwaflow_b200 import capi
+    monkeypatch.setenv("BWAFLOW_SMEM_HEAVY_MIN", str(heavy_min))
+    ix = request.getfixturevalue("index_" + case)
+    g = request.getfixturevalue("golden_" + case)
+    ctx = _ctx(ix)
+    nt4 = ix.reads.nt4()
+    b = capi.SmemBatch(ctx, ix.reads.n, len(nt4))
+    b.submit(nt4, ix.reads.offsets)
+    intv, off, t = b.collect()
+    assert (off == g["intv_off"]).all(), np.nonzero(off != g["intv_off"])[0][:5]
+    assert intv.tobytes() == g["intv"].tobytes()
+    b.set_anchored(True)
+    b.rerun()
+    intv4, off4, _ = b.collect()
+    assert (off4 == off).all()
+    _same_modulo_anchoring(ix, intv4, g["intv"])
+    b.close()
+    ctx.close()
