@@ -818,8 +818,8 @@ int bwaflow_c2a_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_
     // job does not fit is simply not run ahead
     int r = bwaflow_ext_batch_create(ctx, mc, 96 * mc + 4096, 288 * mc + 4096, &b->xb);
     if (r) return r;
-    // first-seed flanks of weak chains are long and die early: with that mix the packed engine only pays up to qlen 95 (measured)
-    ext_set_pair_classes(b->xb, 3);
+    // every class the two-columns-per-word engine can hold (qlen <= 255): no loss on 2x150 bp, stage 4 27.4 -> 23.9 ms on 2x250 bp
+    ext_set_pair_classes(b->xb, 6);
     ext_set_order_rows(b->xb, 1);
   }
   BF_CUDA(cudaMalloc(&b->d_slot_chain, ms * 4));
@@ -827,7 +827,7 @@ int bwaflow_c2a_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_
     // wave B: up to one job per seed slot, pools as above
     int r = bwaflow_ext_batch_create(ctx, ms, 96 * ms + 4096, 288 * ms + 4096, &b->xb2);
     if (r) return r;
-    ext_set_pair_classes(b->xb2, 5);
+    ext_set_pair_classes(b->xb2, 6);
     ext_set_order_rows(b->xb2, 1);
     BF_CUDA(cudaMalloc(&b->d_resL2, ms * sizeof(bwaflow_ext_result_t)));
     BF_CUDA(cudaMalloc(&b->d_jslot, ms * 4));

@@ -22,7 +22,7 @@ namespace bwaflow {
 constexpr int EXT_NCLASS = 8;
 constexpr int EXT_NQ = EXT_NCLASS + 1;
 constexpr int CTL_HIST = 0, CTL_QUEUE = EXT_NCLASS, CTL_ERR = CTL_QUEUE + 2 * EXT_NQ, CTL_CELLS = CTL_ERR + 2, CTL_INTS = CTL_CELLS + 2;
-constexpr int EXT_PAIR_CLASSES = 5;      // classes 0..4 (qlen <= 159) run on the packed two-jobs-per-lane engine; wider row states leave too few warps per SM for it to pay (measured)
+constexpr int EXT_PAIR_CLASSES = 6;      // classes 0..5 (qlen <= 255) can run on the packed engines; which of them do is set per batch (ext_set_pair_classes, BWAFLOW_EXT_PAIR_CLASSES)
 // qlen <= qmax runs in class c with `threads` lanes per block; row state = threads*(qmax+1)*4 bytes
 __constant__ int c_ext_qmax[EXT_NCLASS] = {31, 63, 95, 127, 159, 255, 511, 1023};
 static const int h_ext_qmax[EXT_NCLASS] = {31, 63, 95, 127, 159, 255, 511, 1023};
@@ -430,7 +430,7 @@ int bwaflow_ext_batch_create(bwaflow_ctx_t *ctx, int64_t max_jobs, int64_t max_q
   b->pair_sync = 0;
   b->order_rows = 0;
   if (const char *s = getenv("BWAFLOW_EXT_ORDER_ROWS")) b->order_rows = atoi(s) != 0;
-  b->pair_classes = EXT_PAIR_CLASSES;
+  b->pair_classes = 5;                            // raw job batches: packed up to qlen 159 (measured crossover on long-lived jobs)
   if (const char *s = getenv("BWAFLOW_EXT_PAIR_CLASSES")) b->pair_classes = atoi(s) < EXT_PAIR_CLASSES ? atoi(s) : EXT_PAIR_CLASSES;
   if (const char *s = getenv("BWAFLOW_EXT_PAIR_SYNC")) b->pair_sync = atoi(s) != 0;
   b->multi_stream = true;
