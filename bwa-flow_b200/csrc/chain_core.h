@@ -239,7 +239,27 @@ BF_HD int flt_prepare(Scratch &S, const bwaflow_chain_opt_t &o, int n_chn)
     c.beg = chn_beg(S, c); c.end = chn_end(S, c);
     if (c.w >= o.min_chain_weight) a[k++] = c;
   }
-  if (k) klib_introsort(k, a, FltLt());
+  if (k < 32) { if (k) klib_introsort(k, a, FltLt()); return k; }
+  // Many chains (a read inside a repeat): klib's introsort runs on (weight, index) pairs instead of the 48-byte chains -- it only
+  // ever looks at weights, so it makes the same comparisons and the same swaps and leaves the same order among equal weights --
+  // and the chains are then moved once, in place, along the cycles of that permutation.
+  struct WK { int w, idx; };
+  struct WKLt { BF_HD bool operator()(const WK &x, const WK &y) const { return x.w > y.w; } };
+  WK *wk = (WK *)S.chains;                                       // free once the chains are in S.sorted
+  for (int i = 0; i < k; ++i) { wk[i].w = a[i].w; wk[i].idx = i; }
+  klib_introsort(k, wk, WKLt());
+  for (int i = 0; i < k; ++i) {
+    if (wk[i].idx == i) continue;
+    const Chain tmp = a[i];
+    int j = i;
+    for (;;) {
+      const int src = wk[j].idx;
+      wk[j].idx = j;
+      if (src == i) { a[j] = tmp; break; }
+      a[j] = a[src];
+      j = src;
+    }
+  }
   return k;
 }
 
