@@ -34,7 +34,7 @@ namespace bwaflow {
 
 enum { SK_T = 0, SK_X = 1, SK_A = 2 };
 enum { SM_F = 0, SM_W = 1, SM_S = 2, SM_B = 3, SM_C = 4, SM_CF = 5, SM_J = 6 };   // forward sweep | window lookup | level walk | leftward extension | continue the previous anchored match | (that failed) | forward sweep: all remaining table levels in one read
-enum { S_NONE = 0, S_FETCH, S_NEXT, S_ENTRY, S_ENTRY_DONE, S_CALL_DONE, S_FINISH, S_EXIT };
+enum { S_NONE = 0, S_FETCH, S_NEXT, S_ENTRY, S_ENTRY_DONE, S_CALL_DONE, S_FINISH, S_EXIT, S_DEFER };
 
 #ifndef SWEEP_MIN_BLOCKS
 #define SWEEP_MIN_BLOCKS 6
@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
     }
     ++n_mem;
   };
+  // end of a forward sweep: on to its matches -- unless there are so many that the read is one for smem_heavy_kernel (S_DEFER)
+  auto fwd_done = [&]() { fi = 0; lb = nb; ts = fwd_n >= a.heavy_min ? S_DEFER : S_ENTRY; };
   // kind of the next step for the pattern [pb, pe) growing by one base
   auto set_kind = [&]() { kind = (TEXT && is_text(ik)) ? SK_A : (pe - pb + 1 <= K ? SK_T : SK_X); ts = S_NONE; };
   // next step of a forward sweep standing at q[pb, pe): the jump if the K bases from pb are all there
@@ -87,16 +89,6 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
   for (;;) {
     // ---- the entry boundary (every ~4 steps of a lane): one straight-line block so that the lanes at a boundary run it together
     while (ts == S_ENTRY || ts == S_ENTRY_DONE) {
-      if (ts == S_ENTRY && fi == 0 && fwd_n >= a.heavy_min) {
-        // A call with this many forward matches is a read inside a repeat: its intervals stay large along the whole read and the
-        // leftward searches below cost (matches x read length) index steps, one after the other on this lane -- tens of
-        // milliseconds for a single read while the rest of the grid has long finished.  Such a read is handed, whole, to
-        // smem_heavy_kernel, which spreads the searches of a call over a warp.
-        a.defer[2 + atomicAdd(a.defer, 1)] = (int)r;
-        a.counts[r] = 0;
-        ts = S_FETCH;
-        break;
-      }
       if (ts == S_ENTRY_DONE) {                              // candidate logic (:392-400, :418-427) and the skip rule (:431-443)
         if (fi > 0 && pb > cand_beg && cand_end - cand_beg >= msl) push_mem(cand, cand_beg, cand_end);
         cand = ik; cand_beg = pb; cand_end = f_end; lb = pb;
@@ -164,12 +156,21 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
           fwd_n = 0; fwd_ns = 0; ik = set_intv(ix, q.base(sx)); pb = sx; pe = sx + 1; mode = SM_F;
           nb = q.prev_n(sx) + 1;
           if (pe < q.len && !q.isN(pe)) set_kind_fwd();
-          else { push_fwd(ik, pe); fi = 0; lb = nb; ts = S_ENTRY; }
+          else { push_fwd(ik, pe); fwd_done(); }
           break;
         }
         ts = S_FINISH;                                       // pass 3 has its own kernel
         break;
       }
+      case S_DEFER:
+        // A call with this many forward matches is a read inside a repeat: its intervals stay large along the whole read and the
+        // leftward searches cost (matches x read length) index steps, one after the other on this lane -- tens of milliseconds
+        // for a single read while the rest of the grid has long finished.  Such a read is handed, whole, to smem_heavy_kernel,
+        // which spreads the searches of a call over a warp.
+        a.defer[2 + atomicAdd(a.defer, 1)] = (int)r;
+        a.counts[r] = 0;
+        ts = S_FETCH;
+        break;
       case S_CALL_DONE:
         if (pass == 1) x = get_end(fwd_n - 1);
         ts = S_NEXT;
@@ -230,15 +231,15 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
           for (int L = pe - pb; L < K; ++L)                  // ends at which the interval changed size (level L -> L + 1)
             if (jm >> (K - 1 - L) & 1) { fend[fwd_n++] = (uint8_t)(pb + L); ++fwd_ns; }
           ik = o; pe = pb + K;
-          if (pe < q.len && !q.isN(pe)) set_kind(); else { push_fwd(ik, pe); fi = 0; lb = nb; ts = S_ENTRY; }
+          if (pe < q.len && !q.isN(pe)) set_kind(); else { push_fwd(ik, pe); fwd_done(); }
         }
       } else if (mode == SM_F) {                             // :350-363
         const bool changed = o.x2 != ik.x2;
         if (changed) push_fwd(ik, pe);
-        if (changed && small) { fi = 0; lb = nb; ts = S_ENTRY; }
+        if (changed && small) { fwd_done(); }
         else {
           ik = o; ++pe;
-          if (pe < q.len && !q.isN(pe)) set_kind_fwd(); else { push_fwd(ik, pe); fi = 0; lb = nb; ts = S_ENTRY; }
+          if (pe < q.len && !q.isN(pe)) set_kind_fwd(); else { push_fwd(ik, pe); fwd_done(); }
         }
       } else if (mode == SM_B) {                             // one more base on the left (:374-386)
         if (small) ts = S_ENTRY_DONE;
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(128, SWEEP_MIN_BLOCKS) smem_sweep_kernel(const
           n = min(diff ? __clzll((long long)diff) >> 1 : 32, w);
         }
         pe += n;
-        if (!(n == 32 && want > 32 && tcap > 32)) { push_fwd(ik, pe); fi = 0; lb = nb; ts = S_ENTRY; }
+        if (!(n == 32 && want > 32 && tcap > 32)) { push_fwd(ik, pe); fwd_done(); }
       }
     }
   }
