@@ -615,7 +615,11 @@ int bwaflow_smem_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max
   BF_CUDA(cudaMallocHost(&b->h_off, (max_reads + 2) * 8));
   BF_CUDA(cudaMalloc(&b->d_ctl, 8 * sizeof(int)));
   BF_CUDA(cudaMalloc(&b->d_defer, (max_reads + 4) * sizeof(int)));
-  b->heavy_min = 40;                             // forward matches of one call; ordinary reads have about 20 (the table levels plus a few)
+  // forward matches of one call from which a read goes to the warp-per-read kernel.  An ordinary read has about log4(index rows)
+  // + 3 -- the interval shrinks at every base until it is unique, i.e. over about as many bases as the level tables are deep --
+  // a read inside a repeat several times that.  Measured at 3.1 Gbp (K = 14): 16 hands every read over (seeding 128 ms), 20
+  // some ordinary ones (14.2 ms), 24 none (13.7 ms); on the repeat-rich variant 19.3 ms at 40, 16.9 at 24, 15.8 at 20.
+  b->heavy_min = (ctx->ix.ktab_k > 0 ? ctx->ix.ktab_k : 16) + 10;
   if (const char *e = getenv("BWAFLOW_SMEM_HEAVY_MIN")) b->heavy_min = atoi(e);
   BF_CUDA(cudaMallocHost(&b->h_ctl, 8 * sizeof(int)));
   int r = smem_alloc_slots(b, 32);
