@@ -23,6 +23,7 @@ struct ChainArgs {
   // per-read scratch, carved by the read's first position index
   SeedNode *seeds; Chain *chains; Chain *sorted; int *order; int *kept; Node *nodes;
   int64_t *n_chains, *n_seeds; float *frac_rep; int *err;
+  int *heavy;                        // [0] reads set aside for chain_heavy_kernel, [1] its queue head, [2..] their ids
   bwaflow_chain_opt_t opt; Ctg ctg;
 };
 
@@ -75,45 +76,49 @@ __device__ int flt_filter_warp(Chain *a, KeptEnt *K, int *F, int *kept, int n_ch
 __global__ void __launch_bounds__(128, CHAIN_MIN_BLOCKS) chain_kernel(const ChainArgs a)
 {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n_reads) return;
+  const int len = (int)(a.read_off[r + 1] - a.read_off[r]);
+  if (len >= a.opt.min_seed_len && needs_seed_rescoring(a.opt, len)) { atomicExch(a.err, 1); a.n_chains[r] = 0; a.n_seeds[r] = 0; return; }
+  const int64_t i0 = a.intv_off[r], i1 = a.intv_off[r + 1];
+  if (i1 > a.out_cap || a.pos_off[i1] > a.pos_cap) { a.n_chains[r] = 0; a.n_seeds[r] = 0; return; }   // left to the redo with larger buffers
+  Scratch S = read_scratch(a, r);
+  float fr;
+  int n = chain_seeds(S, a.opt, a.ctg, len, a.intv + i0, i1 - i0, a.pos, a.pos_off + i0, &fr);
+  a.frac_rep[r] = fr;
+  if (n >= CHAIN_FLT_WARP_MIN) {                             // the overlap filter of this read is a warp's work: chain_heavy_kernel
+    a.n_chains[r] = n; a.n_seeds[r] = 0;
+    a.heavy[2 + atomicAdd(a.heavy, 1)] = (int)r;
+    return;
+  }
+  n = chain_filter(S, a.opt, n);
+  int ns = 0;
+  for (int c = 0; c < n; ++c) ns += S.sorted[c].n;
+  a.n_chains[r] = n; a.n_seeds[r] = ns;
+}
+
+// The rest of mem_chain_flt for the reads chain_kernel set aside (64 chains or more), one warp per read: the overlap filter by
+// the warp, marking / compaction and the counts by lane 0.  Usually there is none and the warps leave at once.
+__global__ void __launch_bounds__(128) chain_heavy_kernel(const ChainArgs a)
+{
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
-  bool act = r < a.n_reads;
-  int len = 0, n = 0, n_kept = 0;
-  int64_t i0 = 0, i1 = 0;
-  float fr = 0.f;
-  if (act) {
-    len = (int)(a.read_off[r + 1] - a.read_off[r]);
-    if (len >= a.opt.min_seed_len && needs_seed_rescoring(a.opt, len)) { atomicExch(a.err, 1); act = false; }
+  for (;;) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(a.heavy + 1, 1);
+    slot = __shfl_sync(full, slot, 0);
+    if (slot >= a.heavy[0]) break;
+    const int64_t r = a.heavy[2 + slot];
+    Scratch S = read_scratch(a, r);
+    const int nn = (int)a.n_chains[r];
+    const int nk = flt_filter_warp(S.sorted, flt_kept_ents(S), flt_kept_first(S, nn), S.kept, nn, a.opt, lane);
+    if (lane == 0) {
+      const int n = flt_finish(S, a.opt, nn, nk);
+      int ns = 0;
+      for (int c = 0; c < n; ++c) ns += S.sorted[c].n;
+      a.n_chains[r] = n; a.n_seeds[r] = ns;
+    }
+    __syncwarp();
   }
-  if (act) {
-    i0 = a.intv_off[r]; i1 = a.intv_off[r + 1];
-    if (i1 > a.out_cap || a.pos_off[i1] > a.pos_cap) act = false;          // left to the redo with larger buffers
-  }
-  Scratch S;
-  S.seeds = nullptr; S.chains = nullptr; S.nodes = nullptr; S.order = nullptr; S.sorted = nullptr; S.kept = nullptr;
-  S.n_seeds = S.n_chains = S.n_nodes = S.root = 0;
-  if (act) {
-    S = read_scratch(a, r);
-    n = chain_seeds(S, a.opt, a.ctg, len, a.intv + i0, i1 - i0, a.pos, a.pos_off + i0, &fr);
-  }
-  // the overlap filter: a read with few chains on its own thread, a read with many by the whole warp, one after the other
-  const bool heavy = act && n >= CHAIN_FLT_WARP_MIN;
-  if (act && !heavy && n > 0) n_kept = flt_filter(S, a.opt, n);
-  for (unsigned hm = __ballot_sync(full, heavy); hm; hm &= hm - 1) {
-    const int L = __ffs(hm) - 1;
-    Chain *sa = (Chain *)__shfl_sync(full, (unsigned long long)S.sorted, L);
-    KeptEnt *K = (KeptEnt *)__shfl_sync(full, (unsigned long long)S.chains, L);
-    int *kp = (int *)__shfl_sync(full, (unsigned long long)S.kept, L);
-    const int nn = __shfl_sync(full, n, L);
-    const int nk = flt_filter_warp(sa, K, (int *)(K + nn), kp, nn, a.opt, lane);
-    if (lane == L) n_kept = nk;
-  }
-  if (r >= a.n_reads) return;
-  if (act && n > 0) n = flt_finish(S, a.opt, n, n_kept);
-  int ns = 0;
-  if (act) for (int c = 0; c < n; ++c) ns += S.sorted[c].n;
-  a.n_chains[r] = act ? n : 0; a.n_seeds[r] = ns;
-  if (act) a.frac_rep[r] = fr;
 }
 
 // second pass: flat chains/seeds in the layout stage 4 takes (chains of read r at chain_off[r], seeds contiguous per chain)
@@ -153,6 +158,7 @@ struct bwaflow_hot_batch {
   chain::SeedNode *d_seeds; chain::Chain *d_chains, *d_sorted; int *d_order, *d_kept; chain::Node *d_nodes;
   int64_t *d_nch, *d_nsd, *d_choff, *d_sdoff, *h_tot; float *d_frac; int *d_err, *h_err;
   void *d_tmp; size_t tmp_bytes;
+  int *d_heavy;
   int32_t *d_ctg_alt;
   bwaflow_chain_opt_t copt;
   int64_t n_intv, n_pos, n_chains, n_seeds;
@@ -219,15 +225,17 @@ static int hot_enqueue_front(bwaflow_hot_batch *b)
   a.n_reads = nr; a.read_off = s->d_read_off; a.intv = s->d_out; a.intv_off = s->d_off; a.pos = s->d_pos; a.pos_off = s->d_poff;
   a.out_cap = s->out_cap; a.pos_cap = s->pos_cap;
   a.seeds = b->d_seeds; a.chains = b->d_chains; a.sorted = b->d_sorted; a.order = b->d_order; a.kept = b->d_kept; a.nodes = b->d_nodes;
-  a.n_chains = b->d_nch; a.n_seeds = b->d_nsd; a.frac_rep = b->d_frac; a.err = b->d_err; a.opt = b->copt;
+  a.n_chains = b->d_nch; a.n_seeds = b->d_nsd; a.frac_rep = b->d_frac; a.err = b->d_err; a.heavy = b->d_heavy; a.opt = b->copt;
   a.ctg = chain::Ctg{b->ctx->ix.n_seqs, b->ctx->ix.ctg_offset, b->ctx->ix.ctg_len, b->d_ctg_alt, b->ctx->ix.l_pac};
   b->cargs = a;
   BF_CUDA(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
+  BF_CUDA(cudaMemsetAsync(b->d_heavy, 0, 2 * sizeof(int), st));
   BF_CUDA(cudaMemsetAsync(b->d_choff, 0, (nr + 1) * 8, st));
   BF_CUDA(cudaMemsetAsync(b->d_sdoff, 0, (nr + 1) * 8, st));
   if (nr) {
     const unsigned grid = (unsigned)((nr + 127) / 128);
     chain_kernel<<<grid, 128, 0, st>>>(a);
+    chain_heavy_kernel<<<b->ctx->n_sm * 4, 128, 0, st>>>(a);
     fill_last_zero<<<1, 1, 0, st>>>(b->d_nch, nr);
     fill_last_zero<<<1, 1, 0, st>>>(b->d_nsd, nr);
     size_t tmp = b->tmp_bytes;
@@ -312,6 +320,7 @@ int bwaflow_hot_batch_create(bwaflow_ctx_t *ctx, int64_t max_reads, int64_t max_
   BF_CUDA(cudaMalloc(&b->d_sdoff, (max_reads + 2) * 8));
   BF_CUDA(cudaMalloc(&b->d_frac, (max_reads + 2) * 4));
   BF_CUDA(cudaMalloc(&b->d_err, 16));
+  BF_CUDA(cudaMalloc(&b->d_heavy, (max_reads + 4) * sizeof(int)));
   BF_CUDA(cudaMallocHost(&b->h_tot, 32));
   BF_CUDA(cudaMallocHost(&b->h_err, 16));
   BF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b->tmp_bytes, b->d_nch, b->d_choff, (int)(max_reads + 1), b->stream));
@@ -335,7 +344,7 @@ void bwaflow_hot_batch_destroy(bwaflow_hot_batch_t *b)
   if (b->c) { b->c->d_bases = nullptr; b->c->d_read_off = nullptr; b->c->stream = b->c->own_stream; bwaflow_c2a_batch_destroy(b->c); }
   bwaflow_smem_batch_destroy(b->s);
   cudaFree(b->d_seeds); cudaFree(b->d_chains); cudaFree(b->d_sorted); cudaFree(b->d_order); cudaFree(b->d_kept); cudaFree(b->d_nodes);
-  cudaFree(b->d_nch); cudaFree(b->d_nsd); cudaFree(b->d_choff); cudaFree(b->d_sdoff); cudaFree(b->d_frac); cudaFree(b->d_err);
+  cudaFree(b->d_nch); cudaFree(b->d_nsd); cudaFree(b->d_choff); cudaFree(b->d_sdoff); cudaFree(b->d_frac); cudaFree(b->d_err); cudaFree(b->d_heavy);
   cudaFreeHost(b->h_tot); cudaFreeHost(b->h_err); cudaFree(b->d_tmp); cudaFree(b->d_ctg_alt);
   for (int i = 0; i < 7; ++i) cudaEventDestroy(b->ev[i]);
   free(b);
