@@ -1,7 +1,8 @@
-"""Import shim: the product package lives in `bwa-flow_b200/` (a directory name Python cannot
-import directly); this module makes it importable as `bwaflow_b200`."""
-import os as _os
+"""bwaflow_b200: B200 (sm_100a) backend for bwa-flow's BWA-MEM per-read compute path.
 
-__path__ = [_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "bwa-flow_b200")]
-with open(_os.path.join(__path__[0], "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(__path__[0], "__init__.py"), "exec"))
+The product is `libbwaflow_cuda.so` (csrc/, C ABI in include/bwaflow_cuda.h).  This package is the
+thin Python host side used by tests and bench.py: ctypes bindings (`capi`), the stage mirrors
+(`stages`) and synthetic workload generators (`synth`).  There is no CPU fallback: importing `capi`
+without the built library, or creating a context without a GPU, raises.
+"""
+__version__ = "0.1.0"

@@ -2,7 +2,7 @@
 CPU path, oracle/ref_driver.cpp) and oracle/liboracle.so (our C restatement, oracle/oracle.c).
 
 Importable only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs.  Nothing under bwa-flow_b200/ imports this module.
+legs.  Nothing under bwaflow_b200/ imports this module.
 """
 from __future__ import annotations
 

@@ -3,7 +3,7 @@
  * Plain-C restatement of the reference's hot-path arithmetic, written from the
  * behaviour of the reference (each function cites the file:line it follows).
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
- * load this file's library; the product path (bwa-flow_b200/, include/) never
+ * load this file's library; the product path (bwaflow_b200/, include/) never
  * does and fails loudly without its CUDA library.
  *
  * Parity is PINNED: tests/test_oracle_golden.py checks every function here
@@ -278,7 +278,7 @@ int orc_collect_intv(const orc_index_t *ix, const orc_opt_t *opt, const uint8_t 
   return n;
 }
 
-/* The same search stated as a function (what bwa-flow_b200/csrc/smem_sweep.cu computes; kept here so that the equivalence
+/* The same search stated as a function (what bwaflow_b200/csrc/smem_sweep.cu computes; kept here so that the equivalence
  * is pinned on the CPU, tests/test_oracle_golden.py): both routes of the backward loop above ("back-enlarge" and
  * "forward-enlarge") return, for the forward match q[x, e), the leftmost begin b whose interval still has min_intv rows
  * (not crossing an N or the read start), because interval sizes only shrink as a pattern grows.  So the backward loop is:

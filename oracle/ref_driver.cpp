@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY (oracle/_ref).  Never linked into, imported by or
-// executed from the product path (bwa-flow_b200/, include/).  Only tests/,
+// executed from the product path (bwaflow_b200/, include/).  Only tests/,
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load the library this file builds.
 //

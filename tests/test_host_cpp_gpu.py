@@ -1,4 +1,4 @@
-"""GPU: the C++ host side -- the src/cuda stage classes (bwa-flow_b200/host/CUDAPipeline.{h,cpp}, the counterparts of
+"""GPU: the C++ host side -- the src/cuda stage classes (bwaflow_b200/host/CUDAPipeline.{h,cpp}, the counterparts of
 src/fpga/FPGAPipeline.{h,cpp}) wired as the compute_flow slice SeqsToChains -> ChainsPipe -> ChainsToRegions over a boost-free
 kflow stand-in, several kflow records in flight on two workers per stage.  Regions must equal the golden vectors of the
 compiled reference, read for read, whatever order the records complete in."""
@@ -22,7 +22,7 @@ def test_cpp_stage_classes_match_golden(case, per_record, workers, mode, gpus, r
     wid % n_gpus and the kflow queue deals the records -- on a one-GPU box that is the single-GPU path again."""
     from bwaflow_b200 import capi
     g = request.getfixturevalue("golden_" + case)
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "bwa-flow_b200", "host")], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "bwaflow_b200", "host")], check=True)
     B = capi.BuiltIndex(g["ref_codes"], g["ctg_len"])
     v = B.view
     off = np.ascontiguousarray(g["offsets"], dtype=np.int64)
@@ -40,7 +40,7 @@ def test_cpp_stage_classes_match_golden(case, per_record, workers, mode, gpus, r
         off.tofile(f)
         bases.tofile(f)
     out = str(tmp_path / "regions.bin")
-    r = subprocess.run([os.path.join(ROOT, "bwa-flow_b200", "cuda_stage_demo"), path, out, str(workers), mode, str(gpus)], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(ROOT, "bwaflow_b200", "cuda_stage_demo"), path, out, str(workers), mode, str(gpus)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     raw = open(out, "rb").read()
     n = struct.unpack_from("<q", raw, 0)[0]

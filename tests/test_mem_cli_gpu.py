@@ -1,4 +1,4 @@
-"""GPU: the stand-alone driver bwaflow_mem (bwa-flow_b200/host/mem_main.cpp) -- FASTQ files and a bwa index on disk in, SAM out, with
+"""GPU: the stand-alone driver bwaflow_mem (bwaflow_b200/host/mem_main.cpp) -- FASTQ files and a bwa index on disk in, SAM out, with
 every compute slot of compute_flow on the GPU (what `--use_gpu` switches on beside `--use_fpga`).  The SAM must equal, byte for byte,
 the text of the reference's stages 2-5 (oracle/_ref) run record by record with the same start_idx, for gzipped paired files cut
 into several records that complete out of order on several workers, for an interleaved file with comments and a read group, and
@@ -13,7 +13,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BIN = os.path.join(ROOT, "bwa-flow_b200", "bwaflow_mem")
+BIN = os.path.join(ROOT, "bwaflow_b200", "bwaflow_mem")
 
 
 def _setup(n_pairs, read_len, seed, paired=True):
@@ -66,7 +66,7 @@ def _body(path):
 
 
 def _build():
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "bwa-flow_b200", "host")], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "bwaflow_b200", "host")], check=True)
 
 
 def test_refuses_to_run_without_the_switch(tmp_path):
