@@ -438,6 +438,7 @@ def main():
             reference_arm(args, local)
         return
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner is not part of the one JSON line on stdout
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
