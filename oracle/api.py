@@ -262,6 +262,21 @@ SWJOB = np.dtype([("qlen", "<i4"), ("tlen", "<i4"), ("xtra", "<i4"), ("pad", "<i
 PES = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("pad", "<i4"), ("avg", "<f8"), ("std", "<f8")])
 
 
+def ref_fastq_dump(path1, path2=None, chunk_size=10_000_000):
+    """the reference's own parser and batching (kseq_read + bseq_read, bwa/bwa.c:53-85) on FASTA/FASTQ files -> dump text"""
+    L = ref_lib()
+    L.bwaref_fastq_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.bwaref_fastq_dump.restype = C.c_int64
+    L.bwaref_free.argtypes = [C.c_void_p]
+    out = C.c_void_p()
+    n = L.bwaref_fastq_dump(path1.encode(), path2.encode() if path2 else None, int(chunk_size), C.byref(out))
+    if n < 0:
+        raise RuntimeError("cannot open " + path1)
+    s = C.string_at(out.value, n)
+    L.bwaref_free(out)
+    return s
+
+
 def ref_ksw_align2(query, target, mat, o_del, e_del, o_ins, e_ins, xtra):
     """the reference's ksw_align2 (bwa/ksw.c:343-365) -> [score, te, qe, score2, te2, tb, qb]"""
     q = np.array(query, dtype=np.uint8)

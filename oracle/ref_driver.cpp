@@ -566,3 +566,39 @@ int bwaref_reg2aln(void *h, int l_query, const char *query, const mem_alnreg_t *
 }
 
 } // extern "C"
+
+// ---- ingest: the reference's own FASTA/FASTQ parser and batching, for the parity test of the host-side FastqSource -----------------
+// bseq_read (bwa/bwa.c:53-85) is the stock twin of getKseqBatch + KseqsToBseqs (src/Pipeline.cpp:98-202): kseq_read's parsing rules,
+// whole pairs until the record holds >= chunk_size bases, trim_readno, an empty comment is no comment.  Dump: one line
+// "#record <start_idx> <batch_num>" per record, then "name\tcomment\tseq\tqual" per read ("" for no comment, "*" for no quality).
+// (kseq_t / kseq_init / kseq_destroy: KSEQ_DECLARE(gzFile) in src/bwa_wrapper.h:29)
+extern "C" int64_t bwaref_fastq_dump(const char *p1, const char *p2, int chunk_size, char **out)
+{
+  gzFile f1 = gzopen(p1, "r"), f2 = p2 ? gzopen(p2, "r") : 0;
+  if (!f1 || (p2 && !f2)) return -1;
+  kseq_t *ks = kseq_init(f1), *ks2 = f2 ? kseq_init(f2) : 0;
+  std::string o;
+  int64_t start = 0;
+  for (;;) {
+    int n = 0;
+    bseq1_t *seqs = bseq_read(chunk_size, &n, ks, ks2);
+    if (n == 0) { free(seqs); break; }
+    o += "#record " + std::to_string(start) + " " + std::to_string(n) + "\n";
+    for (int i = 0; i < n; ++i) {
+      o += seqs[i].name; o += '\t';
+      if (seqs[i].comment) o += seqs[i].comment;
+      o += '\t'; o += seqs[i].seq; o += '\t';
+      o += seqs[i].qual ? seqs[i].qual : "*";
+      o += '\n';
+      free(seqs[i].name); free(seqs[i].comment); free(seqs[i].seq); free(seqs[i].qual);
+    }
+    free(seqs);
+    start += n;
+  }
+  kseq_destroy(ks); gzclose(f1);
+  if (ks2) { kseq_destroy(ks2); gzclose(f2); }
+  *out = (char *)malloc(o.size() + 1);
+  memcpy(*out, o.data(), o.size() + 1);
+  return (int64_t)o.size();
+}
+extern "C" void bwaref_free(void *p) { free(p); }
