@@ -12,8 +12,13 @@
  *   SMemTask{start,finish} (src/fpga/SMemTask.h:9-47)                     -> bwaflow_smem_{submit,collect}
  *   SWTask{start,finish}   (src/fpga/SWTask.h:9-50)                       -> bwaflow_c2a_{submit,collect}
  *                                                                            bwaflow_ext_{submit,collect}
+ *   both slots fused, chains never leaving HBM (ChainsRecord::tag = 1)      -> bwaflow_hot_{submit,collect}
+ *   RegionsToSam::compute (src/Pipeline.cpp:546-648), slot 5               -> bwaflow_sam_process, built from
+ *                                                                            bwaflow_dedup_patch, bwaflow_pestat,
+ *                                                                            bwaflow_matesw_*, bwaflow_cigar_*, bwaflow_sw_*
  * submit is asynchronous (H2D + kernels + D2H queued on the batch's own stream), collect blocks;
  * a worker keeps two batch objects to double-buffer, exactly as FPGAPipeline.cpp:374-386 does.
+ * The kflow stage classes over these calls are bwaflow_b200/host/CUDAPipeline.{h,cpp}.
  */
 #ifndef BWAFLOW_CUDA_H
 #define BWAFLOW_CUDA_H
