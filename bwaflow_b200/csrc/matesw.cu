@@ -394,7 +394,31 @@ int bwaflow_matesw_submit(bwaflow_matesw_batch_t *b, int64_t n_reads, const uint
   if (!b->po.no_rescue) {
     std::vector<Reg> ma[2], bb[2];
     int64_t dummy = 0;
-    for (int64_t pr = 0; pr < n_pairs; ++pr) ms_pair(b, pr, true, ma, bb, &dummy);
+    const int64_t l_pac = b->ctx->ix.l_pac;
+    for (int64_t pr = 0; pr < n_pairs; ++pr) {
+      // most pairs: every anchoring region already has a mate hit at a proper distance in every orientation that is not
+      // failed, so mem_matesw returns at once (bwamem_pair.c:121-127) -- decided here on the regions in place, without the
+      // copies the general path takes
+      bool quiet = true;
+      for (int i = 0; i < 2 && quiet; ++i) {
+        const Reg *a = b->regs.data() + reg_off[2 * pr + i], *m = b->regs.data() + reg_off[2 * pr + (i ^ 1)];
+        const int64_t na = reg_off[2 * pr + i + 1] - reg_off[2 * pr + i], nm = reg_off[2 * pr + (i ^ 1) + 1] - reg_off[2 * pr + (i ^ 1)];
+        int taken = 0;
+        for (int64_t j = 0; j < na && taken < b->po.max_matesw && quiet; ++j) {
+          if (!(a[j].score >= a[0].score - b->po.pen_unpaired)) continue;
+          ++taken;
+          int skip[4];
+          for (int r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
+          for (int64_t k = 0; k < nm; ++k) {
+            int64_t dist;
+            const int r = infer_dir(l_pac, a[j].rb, m[k].rb, &dist);
+            if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
+          }
+          if (skip[0] + skip[1] + skip[2] + skip[3] != 4) quiet = false;
+        }
+      }
+      if (!quiet) ms_pair(b, pr, true, ma, bb, &dummy);
+    }
   }
   // a pair without a window in round 0 rescues nothing, so its hits never change and no later call can ask for one: it is final
   b->pair_live.assign((size_t)n_pairs, 0);
@@ -439,6 +463,10 @@ int bwaflow_matesw_collect(bwaflow_matesw_batch_t *b, const bwaflow_alnreg_t **r
   }
   b->out.clear(); b->out_off.assign(1, 0);
   b->out.reserve(b->regs.size() + 64);
+  if (b->n_run == 0) {                                     // nothing was rescued anywhere: the regions leave as they came
+    b->out = b->regs;
+    b->out_off = b->reg_off;
+  } else
   for (int64_t pr = 0; pr < n_pairs; ++pr)
     for (int i = 0; i < 2; ++i) {
       if (b->pair_live[(size_t)pr]) {
