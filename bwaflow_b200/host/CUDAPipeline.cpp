@@ -63,11 +63,13 @@ SeedPositionTable::Entry SeedPositionTable::take(uint64_t start_idx)
   return e;
 }
 
-// nst_nt4_table (bwa/bntseq.c:47-64): A,C,G,T (either case) -> 0..3, everything else 4
-static inline uint8_t nt4(char c)
-{
-  switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return (uint8_t)c < 4 ? (uint8_t)c : 4; }
-}
+// nst_nt4_table (bwa/bntseq.c:47-64): A,C,G,T (either case) -> 0..3, everything else 4; codes 0..3 stay (stage 2 may see a record twice)
+struct Nt4Table {
+  uint8_t t[256];
+  Nt4Table() { for (int c = 0; c < 256; ++c) t[c] = c < 4 ? (uint8_t)c : 4; t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3; }
+};
+static const Nt4Table nt4_table;
+static inline uint8_t nt4(char c) { return nt4_table.t[(uint8_t)c]; }
 
 void SeqsToChainsCUDA::compute(int wid)
 {

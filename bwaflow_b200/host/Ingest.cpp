@@ -22,14 +22,25 @@ int FastxReader::getc_()
   return buf_[begin_++];
 }
 
-// up to the end of the line (the newline is consumed, a trailing '\r' dropped)
+// up to the end of the line (the newline is consumed, a trailing '\r' dropped); whole buffer stretches at a time
 void FastxReader::rest_of_line(std::string &s, bool append)
 {
   if (!append) s.clear();
   const size_t l0 = s.size();
-  int c;
-  while ((c = getc_()) != -1 && c != '\n') s.push_back((char)c);
-  if (s.size() > l0 + 0 && s.size() > 1 && s.back() == '\r') s.pop_back();
+  for (;;) {
+    if (begin_ >= end_) {
+      if (eof_) break;
+      begin_ = 0;
+      end_ = gzread(f_, buf_, sizeof(buf_));
+      if (end_ <= 0) { eof_ = 1; end_ = 0; break; }
+    }
+    const unsigned char *p = buf_ + begin_;
+    const unsigned char *nl = (const unsigned char *)memchr(p, '\n', (size_t)(end_ - begin_));
+    if (nl) { s.append((const char *)p, (size_t)(nl - p)); begin_ = (int)(nl - buf_) + 1; break; }
+    s.append((const char *)p, (size_t)(end_ - begin_));
+    begin_ = end_;
+  }
+  if (s.size() > l0 && s.size() > 1 && s.back() == '\r') s.pop_back();
 }
 
 int FastxReader::read(std::string &name, std::string &comment, std::string &seq, std::string &qual)

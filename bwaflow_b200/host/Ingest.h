@@ -25,7 +25,7 @@ class FastxReader {
   int getc_();
   void rest_of_line(std::string &s, bool append);
   gzFile f_;
-  unsigned char buf_[1 << 16];
+  unsigned char buf_[1 << 18];
   int begin_, end_, eof_, last_char_;
 };
 
