@@ -182,3 +182,56 @@ def test_reads_to_sam_through_this_library_only():
     ctx.close()
     B.close()
     ix.ref.close()
+
+
+def test_alt_contig_and_non_default_options():
+    """An ALT contig (bns->anns[].is_alt from the .alt file) and -k 17 -w 80: the ALT flag travels through chaining (mem_chain_flt's
+    ALT rules), the regions and stage 5 (mem_mark_primary_se's second round, alt_sc / pa:f, XA limits for ALT hits, the extra
+    supplementary ALT record of mem_sam_pe); the options reach seeding, chaining, extension and CIGAR generation."""
+    from bwaflow_b200 import capi, stages, synth
+    from oracle import api
+    base = synth.make_reference(1_200_000, n_contigs=2, seed=77)
+    rng = np.random.default_rng(78)
+    alt = base.contigs[0][200_000:230_000].copy()
+    mut = rng.random(len(alt)) < 0.015
+    alt[mut] = (alt[mut] + rng.integers(1, 4, int(mut.sum()))) % 4
+    ref = synth.Reference(list(base.names) + ["chr1_alt"], list(base.contigs) + [alt])
+    region = synth.Reference(["sub"], [base.contigs[0][190_000:240_000]])
+    ra = synth.simulate_pairs(region, 1500, 150, 0.01, seed=79)
+    rb = synth.simulate_pairs(ref, 500, 150, 0.01, seed=80)
+    reads = synth.ReadBatch(list(ra.names) + list(rb.names), np.concatenate([ra.bases, rb.bases]), np.concatenate([ra.quals, rb.quals]),
+                            np.concatenate([ra.offsets, rb.offsets[1:] + ra.offsets[-1]]))
+    td = tempfile.mkdtemp()
+    ref.write_fasta(os.path.join(td, "r.fa"))
+    api.build_index(os.path.join(td, "r.fa"), os.path.join(td, "r"))
+    open(os.path.join(td, "r.alt"), "w").write("@SQ\tSN:ignored\nchr1_alt\t0\tchr1\t200001\t60\t30000M\n")
+    R = api.Ref(os.path.join(td, "r"))
+    R.opt("min_seed_len", 17)
+    R.opt("w", 80)
+
+    class IX:
+        pass
+    ix = IX()
+    ix.ref, ix.reads = R, reads
+    regs0, off0, regs1, off1, exp = _ref_stage4(ix, 0)
+    is_alt = np.array([0, 0, 1], dtype=np.int32)
+    assert int(((regs1["n_comp_is_alt"] >> 30) != 0).sum()) > 100          # the reference marked ALT regions
+    B = capi.BuiltIndex(ref.concat(), ref.lengths)
+    opt = capi.default_opt()
+    opt.min_seed_len = 17
+    opt.w = 80
+    ctx = capi.Context(0, B.index(), opt, keepalive=B)
+    co = capi.default_chain_opt()
+    nt4 = reads.nt4()
+    fp = stages.FusedHotPath(ctx, reads.n, len(nt4), co, is_alt)
+    out = fp.run(stages.seqs_record(0, nt4, reads.offsets))
+    assert (out["alnreg_off"] == off0).all()
+    assert out["alnreg"].tobytes() == _as_alnreg(regs0).tobytes()
+    sb = capi.SamBatch(ctx, reads.n, len(nt4), R.contig_names(), ctg_is_alt=is_alt)
+    mine, pes, t = sb.process(nt4, reads.quals, reads.offsets, _names(reads), out["alnreg"], out["alnreg_off"], 0)
+    assert _first_diff(mine, exp) is None, _first_diff(mine, exp)
+    text = b"".join(exp)
+    print("ALT + options: %d reads, %d records, %d with pa:f, %d with XA, %d on chr1_alt" %
+          (reads.n, text.count(b"\n"), text.count(b"\tpa:f:"), text.count(b"\tXA:Z:"), sum(1 for l in text.split(b"\n") if l and l.split(b"\t")[2] == b"chr1_alt")))
+    assert text.count(b"\tpa:f:") > 0
+    fp.close(); sb.close(); ctx.close(); B.close(); R.close()
