@@ -235,3 +235,30 @@ def test_alt_contig_and_non_default_options():
           (reads.n, text.count(b"\n"), text.count(b"\tpa:f:"), text.count(b"\tXA:Z:"), sum(1 for l in text.split(b"\n") if l and l.split(b"\t")[2] == b"chr1_alt")))
     assert text.count(b"\tpa:f:") > 0
     fp.close(); sb.close(); ctx.close(); B.close(); R.close()
+
+
+@pytest.mark.parametrize("flag,T", [(0x2 | 0x8, 30), (0x2 | 0x200 | 0x10, 30), (0x2 | 0x4 | 0x10, 30), (0x2 | 0x20 | 0x10, 30), (0x2, 50), (0x8 | 0x200, 20)])
+def test_sam_option_flags(flag, T):
+    """mem_opt_t::flag and -T as stage 5 reads them: -a (all secondaries as records, no XA), -Y (soft clips on supplementary
+    records), -P (no pairing), -S (no rescue), without -M (supplementary 0x800 instead of 0x100), single-end with -a -Y, and a higher
+    output threshold (unmapped records for weak hits)"""
+    from bwaflow_b200 import capi, synth
+    ref = synth.make_reference(1_500_000, n_contigs=2, seed=91, repeat_copies=30, repeat_len=500)
+    reads = synth.simulate_pairs_indel(ref, 1500, 150, 0.05, seed=93)
+    ix = _make_ix(ref, reads, paired=bool(flag & 0x2))
+    ix.ref.opt("flag", flag)
+    ix.ref.opt("T", T)
+    regs0, off0, regs1, off1, exp = _ref_stage4(ix, 10)
+    B = capi.BuiltIndex(ref.concat(), ref.lengths)
+    ctx = capi.Context(0, B.index(), keepalive=B)
+    nt4 = reads.nt4()
+    so = capi.default_sam_opt()
+    so.flag = flag
+    so.T = T
+    sb = capi.SamBatch(ctx, reads.n, len(nt4), ix.ref.contig_names(), so=so)
+    mine, pes, t = sb.process(nt4, reads.quals, reads.offsets, _names(reads), _as_alnreg(regs0), off0, 10)
+    assert _first_diff(mine, exp) is None, _first_diff(mine, exp)
+    sb.close()
+    ctx.close()
+    B.close()
+    ix.ref.close()
