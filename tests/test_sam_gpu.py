@@ -262,3 +262,39 @@ def test_sam_option_flags(flag, T):
     ctx.close()
     B.close()
     ix.ref.close()
+
+
+def test_whole_path_with_scaled_scoring():
+    """-A 2 -B 6 -O 8 -E 2 -d 150 -L 7 -U 30 -T 50 through every stage: the biased packed extension cells with a != 1, the word
+    (16-bit) ksw_align2 kernel (l_ms * a >= 250), band inference and ksw_global2 with the scaled gaps, mapq with opt->a"""
+    from bwaflow_b200 import capi, stages, synth
+    ref = synth.make_reference(1_500_000, n_contigs=2, seed=95, repeat_copies=30, repeat_len=500)
+    reads = synth.simulate_pairs_indel(ref, 1500, 150, 0.04, seed=97)
+    ix = _make_ix(ref, reads)
+    vals = dict(a=2, b=6, o_del=8, e_del=2, o_ins=8, e_ins=2, zdrop=150, pen_clip5=7, pen_clip3=7, pen_unpaired=30, T=50)
+    for k, v in vals.items():
+        ix.ref.opt(k, v)
+    regs0, off0, regs1, off1, exp = _ref_stage4(ix, 0)
+    B = capi.BuiltIndex(ref.concat(), ref.lengths)
+    opt = capi.default_opt()
+    for k in ("a", "b", "o_del", "e_del", "o_ins", "e_ins", "zdrop", "pen_clip5", "pen_clip3"):
+        setattr(opt, k, vals[k])
+    mat = [(vals["a"] if i == j else -vals["b"]) if i < 4 and j < 4 else -1 for i in range(5) for j in range(5)]   # bwa_fill_scmat
+    for i, v in enumerate(mat):
+        opt.mat[i] = v
+    ctx = capi.Context(0, B.index(), opt, keepalive=B)
+    nt4 = reads.nt4()
+    fp = stages.FusedHotPath(ctx, reads.n, len(nt4))
+    out = fp.run(stages.seqs_record(0, nt4, reads.offsets))
+    assert (out["alnreg_off"] == off0).all()
+    assert out["alnreg"].tobytes() == _as_alnreg(regs0).tobytes()
+    po = capi.default_pe_opt()
+    po.pen_unpaired = vals["pen_unpaired"]
+    so = capi.default_sam_opt()
+    so.T = vals["T"]
+    sb = capi.SamBatch(ctx, reads.n, len(nt4), ix.ref.contig_names(), po=po, so=so)
+    mine, pes, t = sb.process(nt4, reads.quals, reads.offsets, _names(reads), out["alnreg"], out["alnreg_off"], 0)
+    assert _first_diff(mine, exp) is None, _first_diff(mine, exp)
+    print("scaled scoring: %d reads, %d rescue windows used, %d CIGAR jobs, %d reads on the exact stage-4 kernel"
+          % (reads.n, t.n_matesw_used, t.n_cigar_jobs, fp.batch.exact_reads()))
+    fp.close(); sb.close(); ctx.close(); B.close(); ix.ref.close()
