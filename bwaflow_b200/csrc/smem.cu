@@ -407,8 +407,16 @@ using namespace bwaflow;
 static int smem_alloc_slots(bwaflow_smem_batch *b, int cap)
 {
   if (b->d_slots) cudaFree(b->d_slots);
+  b->d_slots = nullptr;
   b->cap = cap; b->slots_cap = b->max_reads * cap;
-  BF_CUDA(cudaMalloc(&b->d_slots, b->slots_cap * sizeof(bwaflow_intv_t)));
+  // every read of the batch gets a slot of `cap` intervals (the slots grow x4 for all reads when one read fills its own): say
+  // so when that does not fit instead of failing in cudaMalloc
+  size_t free_b = 0, total_b = 0;
+  BF_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t need = (size_t)b->slots_cap * sizeof(bwaflow_intv_t);
+  BF_REQUIRE(need <= free_b, -12, "interval slots of %lld reads x %d intervals need %.1f GB of device memory, %.1f GB are free: a read of this batch "
+             "has more than %d intervals; use smaller batches", (long long)b->max_reads, cap, need / 1e9, free_b / 1e9, cap / 4);
+  BF_CUDA(cudaMalloc(&b->d_slots, need));
   return 0;
 }
 
